@@ -1,0 +1,187 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+    python oracle/gen_golden.py
+
+Imports janetyq/Finite-Element-Solver from /root/reference through `oracle/ref_shim.py`
+and records its outputs on small deterministic inputs: assembled CSR operators, element
+matrices, constrained solves, the cone filter, the OC update and a 5-iteration SIMP
+trajectory.  The fixtures are committed; this script is how they were made.  Inputs are
+stored with the outputs so the tests never need the reference tree.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+ref_shim.install()
+
+from fem.boundary import BCType, BoundaryConditions  # noqa: E402
+from fem.design import optimality_criteria_update  # noqa: E402
+from fem.elements import QuadraticTriangleElement  # noqa: E402
+from fem.equations import LinearElastic, Poisson  # noqa: E402
+from fem.forms import (LaplacianForm, LinearElasticForm, MaskedMassForm, MassForm,  # noqa: E402
+                       PrecomputedForm, ScaledForm)
+from fem.materials import LinearElasticMaterial  # noqa: E402
+from fem.mesh.structured import create_box_mesh, create_rect_mesh  # noqa: E402
+from fem.problem import LinearProblem, linear_elastic  # noqa: E402
+from fem.regions import everywhere, in_box, intersect, on_plane  # noqa: E402
+from fem.solve import LinearSolve  # noqa: E402
+from fem.solver import Solver  # noqa: E402
+from fem.space import FunctionSpace  # noqa: E402
+from fem.topology import TopologyOptimizer, calculate_smoothing_matrix  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+os.makedirs(OUT, exist_ok=True)
+
+
+def csr_fields(prefix, A):
+    return {f'{prefix}_indptr': A.indptr.astype(np.int64), f'{prefix}_indices': A.indices.astype(np.int64),
+            f'{prefix}_data': A.data.astype(np.float64)}
+
+
+def space_fields(V):
+    return {'vertices': V.mesh.vertices, 'elements': V.mesh.elements, 'boundary': V.mesh.boundary,
+            'element_nodes': V.element_nodes, 'node_coords': V.node_coords,
+            'boundary_nodes': V.boundary_nodes}
+
+
+def assembly_case(name, mesh, element_type=None):
+    d = mesh.spatial_dim
+    out = {}
+    V1 = FunctionSpace(mesh, element_type, n_components=1)
+    Vd = FunctionSpace(mesh, element_type, n_components=d)
+    out.update(space_fields(V1))
+    n_el = len(V1.element_nodes)
+    E_var = np.linspace(50.0, 200.0, n_el)
+    mask = (np.arange(len(V1.boundary_nodes)) % 3 != 0)
+    out['E_var'], out['facet_mask'] = E_var, mask
+    out['volumes'] = V1.element_volumes
+    forms = {
+        'lap': (V1, LaplacianForm(), False),
+        'mass1': (V1, MassForm(1), False),
+        'bmass1': (V1, MassForm(1), True),
+        'massd': (Vd, MassForm(d), False),
+        'bmassd': (Vd, MassForm(d), True),
+        'bmaskd': (Vd, MaskedMassForm(d, mask), True),
+        'elast': (Vd, LinearElasticForm(LinearElasticMaterial(200.0, 0.3)), False),
+        'elastvar': (Vd, LinearElasticForm(LinearElasticMaterial(E_var, 0.3)), False),
+        'lapscaled': (V1, ScaledForm(2.25, LaplacianForm()), False),
+    }
+    for key, (V, form, bnd) in forms.items():
+        A = V.assemble(form, boundary=bnd)
+        out.update(csr_fields(key, A))
+        geo = V.boundary_geometry if bnd else V.geometry
+        out[f'{key}_ke'] = form.element_matrices(geo)
+    K0 = LinearElasticForm(LinearElasticMaterial(200.0, 0.3)).element_matrices(Vd.geometry)
+    rho = np.linspace(0.2, 1.0, n_el)
+    out['rho'] = rho
+    out.update(csr_fields('precomp', Vd.assemble(PrecomputedForm(rho[:, None, None] ** 3 * K0))))
+    np.savez_compressed(os.path.join(OUT, f'assembly_{name}.npz'), **out)
+    print(name, 'n_el', n_el, 'nnz elast', out['elast_data'].size)
+
+
+def solve_cases():
+    out = {}
+    # 2D cantilever (ref: tests/test_backends.py:73-84)
+    mesh = create_rect_mesh([[0, 0], [2, 1]], (9, 5))
+    bc = BoundaryConditions()
+    bc.add(BCType.DIRICHLET, on_plane(0, 0.0), [0, 0])
+    bc.add(BCType.NEUMANN, on_plane(0, 2.0), [50, -10])
+    prob = linear_elastic(mesh, LinearElasticMaterial(200.0, 0.3), bc)
+    free, fixed, vals = prob.constraints
+    out.update({'c2d_vertices': mesh.vertices, 'c2d_elements': mesh.elements, 'c2d_boundary': mesh.boundary,
+                'c2d_free': free, 'c2d_fixed': fixed, 'c2d_vals': vals, 'c2d_load': prob.load,
+                'c2d_u': LinearSolve().solve(prob)})
+    # 3D cantilever (ref: tests/test_backends.py:109-113)
+    mesh = create_box_mesh([[0, 0, 0], [1, 1, 1]], (4, 4, 4))
+    bc = BoundaryConditions()
+    bc.add(BCType.DIRICHLET, on_plane(0, 0.0), [0, 0, 0])
+    bc.add(BCType.NEUMANN, on_plane(0, 1.0), [0, -5, 0])
+    prob = linear_elastic(mesh, LinearElasticMaterial(200.0, 0.3), bc)
+    free, fixed, vals = prob.constraints
+    out.update({'c3d_vertices': mesh.vertices, 'c3d_elements': mesh.elements, 'c3d_boundary': mesh.boundary,
+                'c3d_free': free, 'c3d_fixed': fixed, 'c3d_vals': vals, 'c3d_load': prob.load,
+                'c3d_u': LinearSolve().solve(prob)})
+    # Poisson, nonzero Dirichlet data + source + Robin on one side
+    mesh = create_rect_mesh([[0, 0], [1, 1]], (7, 6))
+    bc = BoundaryConditions()
+    bc.add(BCType.DIRICHLET, on_plane(0, 0.0), 1.5)
+    bc.add(BCType.DIRICHLET, on_plane(0, 1.0), -0.5)
+    bc.add_robin(on_plane(1, 1.0), 2.0, 0.75)
+    solver = Solver(mesh, Poisson(source=lambda p: [1.0 + p[0] * p[1]]), bc)
+    sol = solver.solve()
+    V = FunctionSpace(mesh)
+    prob = LinearProblem(V, LaplacianForm(), lambda p: [1.0 + p[0] * p[1]], bc)
+    free, fixed, vals = prob.constraints
+    A = prob.tangent(None)
+    out.update({'poi_vertices': mesh.vertices, 'poi_elements': mesh.elements, 'poi_boundary': mesh.boundary,
+                'poi_free': free, 'poi_fixed': fixed, 'poi_vals': vals, 'poi_load': prob.load,
+                'poi_u': sol.u, 'poi_A_dense': A.toarray()})
+    np.savez_compressed(os.path.join(OUT, 'solve.npz'), **out)
+    print('solve cases written')
+
+
+def simp_case():
+    # MBB beam of examples/solver_demos.py:1271-1288 on a small mesh
+    w, h = 3.0, 1.0
+    mesh = create_rect_mesh([[0, 0], [w, h]], (25, 9))
+    bc = BoundaryConditions()
+    bottom, top = on_plane(1, 0.0), on_plane(1, h)
+    bc.add(BCType.DIRICHLET, intersect(bottom, in_box([None, None], [0.04 * w, None])), [0, 0])
+    bc.add(BCType.DIRICHLET, intersect(bottom, in_box([0.96 * w, None], [None, None])), [None, 0])
+    bc.add(BCType.NEUMANN, intersect(top, in_box([0.4 * w, None], [0.6 * w, None])), [0, -0.5])
+    r = 2.5 * (w / 24)
+    topo = TopologyOptimizer(mesh, LinearElastic(200.0, 0.4), bc, iters=5, volume_frac=0.5,
+                             smoothing_radius=r, penalty=3.0)
+    sens_series = []
+    orig = topo._compliance_sensitivity
+
+    def spy(solution):
+        s = orig(solution)
+        sens_series.append(s.copy())
+        return s
+    topo._compliance_sensitivity = spy
+    hist = topo.solve()
+    free, fixed, vals = topo._problem.constraints
+    S = topo.smoothing_matrix
+    out = {'vertices': mesh.vertices, 'elements': mesh.elements, 'boundary': mesh.boundary,
+           'free': free, 'fixed': fixed, 'vals': vals, 'load': topo._problem.load,
+           'radius': r, 'E0': 200.0, 'nu': 0.4, 'penalty': 3.0, 'volume_frac': 0.5,
+           'rho': np.array(hist.rho), 'u': np.array(hist.u), 'compliance': np.array(hist.compliance),
+           'von_mises': np.array(hist.von_mises), 'sens': np.array(sens_series), 'rho_final': topo.rho,
+           'K0': topo._solid_stiffness, 'volumes': topo.space.element_volumes}
+    out.update(csr_fields('filter', S))
+    np.savez_compressed(os.path.join(OUT, 'simp.npz'), **out)
+    print('simp written; compliance', [float(c.sum()) for c in hist.compliance])
+
+    # the filter alone on a unit-square mesh (ref: tests/test_topology_optimization.py:129-174)
+    mesh = create_rect_mesh([[0, 0], [1, 1]], (12, 12))
+    S = calculate_smoothing_matrix(mesh, 0.15)
+    box = create_box_mesh([[0, 0, 0], [1, 1, 1]], (4, 4, 4))
+    S3 = calculate_smoothing_matrix(box, 0.3)
+    f = {'sq_vertices': mesh.vertices, 'sq_elements': mesh.elements, 'sq_r': 0.15,
+         'box_vertices': box.vertices, 'box_elements': box.elements, 'box_r': 0.3}
+    f.update(csr_fields('sq', S))
+    f.update(csr_fields('box', S3))
+    # OC update on random data
+    rng = np.random.default_rng(7)
+    rho = rng.uniform(0.05, 1.0, 500)
+    sens = rng.uniform(0.0, 3.0, 500)
+    vol = rng.uniform(0.5, 1.5, 500)
+    f.update({'oc_rho': rho, 'oc_sens': sens, 'oc_vol': vol,
+              'oc_out_04': optimality_criteria_update(rho, sens, vol, 0.4, move=0.1),
+              'oc_out_06': optimality_criteria_update(rho, sens, vol, 0.6, move=0.2)})
+    np.savez_compressed(os.path.join(OUT, 'filter_oc.npz'), **f)
+    print('filter/oc written')
+
+
+if __name__ == '__main__':
+    assembly_case('tri', create_rect_mesh([[0, 0], [2, 1]], (6, 5)))
+    assembly_case('tet', create_box_mesh([[0, 0, 0], [1, 2, 1.5]], (3, 4, 3)))
+    assembly_case('p2tri', create_rect_mesh([[0, 0], [1.5, 1]], (5, 4)), QuadraticTriangleElement)
+    solve_cases()
+    simp_case()

@@ -1,0 +1,36 @@
+"""Import shim for the upstream reference (TEST INFRASTRUCTURE; build container only).
+
+`import fem` fails here because `fem/__init__.py` pulls in matplotlib and
+`fem/backends.py` imports pyamg, neither installed.  Registering an empty
+`fem` package pointing at the reference tree skips `__init__`, and a stub `pyamg` lets
+`fem.backends` import.  The reference location is FES_REFERENCE, else /root/reference.
+Nothing on the GPU box may call this: /root/reference does not exist there.
+"""
+import os
+import sys
+import types
+
+
+def reference_root():
+    return os.environ.get('FES_REFERENCE', '/root/reference')
+
+
+def available():
+    return os.path.isdir(os.path.join(reference_root(), 'fem'))
+
+
+def install():
+    if 'fem' in sys.modules:
+        return
+    if not available():
+        raise RuntimeError(f'reference tree not found at {reference_root()}')
+    pkg = types.ModuleType('fem')
+    pkg.__path__ = [os.path.join(reference_root(), 'fem')]
+    sys.modules['fem'] = pkg
+    if 'pyamg' not in sys.modules:
+        stub = types.ModuleType('pyamg')
+
+        def _missing(*a, **k):
+            raise RuntimeError('pyamg is not installed')
+        stub.smoothed_aggregation_solver = _missing
+        sys.modules['pyamg'] = stub
