@@ -1,0 +1,24 @@
+"""fes_b200: the B200-native hot path of janetyq/Finite-Element-Solver.
+
+Python host code with the reference's API (FunctionSpace.assemble, DiscreteSystem/Backend,
+TopologyOptimizer) driving hand-written sm_100a kernels through the C ABI of libfes_b200.so.
+Importable as `fes_b200` (the directory name carries a hyphen).
+"""
+from . import _lib  # noqa: F401
+from .backends import B200Backend, JacobiPCGBackend  # noqa: F401
+from .boundary import BCType, BoundaryConditions  # noqa: F401
+from .csr import DeviceCSR  # noqa: F401
+from .design import optimality_criteria_update  # noqa: F401
+from .elements import (LinearLineElement, LinearTetrahedralElement, LinearTriangleElement,  # noqa: F401
+                       QuadraticLineElement, QuadraticTriangleElement)
+from .equations import LinearElastic, Poisson  # noqa: F401
+from .forms import (LaplacianForm, LinearElasticForm, MaskedMassForm, MassForm, PrecomputedForm,  # noqa: F401
+                    ScaledForm)
+from .materials import LinearElasticMaterial  # noqa: F401
+from .mesh import Mesh, create_box_mesh, create_rect_mesh  # noqa: F401
+from .problem import LinearProblem, linear_elastic, poisson  # noqa: F401
+from .space import FunctionSpace  # noqa: F401
+from .system import DiscreteSystem  # noqa: F401
+from .topology import TopologyOptimizer, calculate_smoothing_matrix  # noqa: F401
+
+__all__ = [n for n in dir() if not n.startswith('_')]
