@@ -1,0 +1,315 @@
+"""Benchmark of the fes-b200 hot path: elements assembled/sec into CSR on BASELINE.json's
+config 2 (2D P1 linear-elasticity cantilever, 3 998 792 triangles), with the HBM roofline of the
+fused assembly kernel, the CPU oracle timed beside it, and (in `extra`) the Jacobi-PCG solve of
+the same cantilever and SIMP design iterations/sec on config 4.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-extra]
+
+A step is one fused assembly of the stiffness values into the cached CSR pattern (the reference's
+warm `FunctionSpace.assemble`: geometry and scatter plan cached, element matrices + scatter per
+call).  Under torchrun (N > 1) every rank assembles its own slab of an N-times longer cantilever
+(owner-computes, ghost elements, no collective): weak scaling.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, 'oracle')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+RES = (2829, 708)                       # config 2: 3 998 792 triangles, 4 005 864 dofs
+CORNERS = [[0.0, 0.0], [4.0, 1.0]]
+E, NU = 200.0, 0.3
+METRIC, UNIT = 'elements assembled/sec into CSR', 'elements/s'
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, f in zip(names, r[2:6]) if f == 'Active'})
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (numpy/scipy restatement of the reference's warm assemble)
+# ---------------------------------------------------------------------------------------------
+def cpu_assemble_rate(sample_res=(1001, 251), repeats=3):
+    """Warm `assemble` of the oracle on a bounded sample of the same workload: the scatter plan
+    and geometry are built once (as the reference caches them), then element matrices + bincount
+    scatter are timed.  Returns (elements/s, description)."""
+    import fes_oracle as fo
+    v, e = fo.rect_mesh(CORNERS, sample_res)
+    geo = fo.geometry(fo.P1_TRI, v[e])
+    plan = fo.scatter_plan(e, 2, len(v))
+    best = float('inf')
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        plan.scatter(fo.ke_elastic(geo, E, NU))
+        best = min(best, time.perf_counter() - t0)
+    return len(e) / best, f'{len(e)} triangles ({sample_res[0]}x{sample_res[1]} nodes of the same cantilever), best of {repeats} warm assemblies'
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    rates = []
+    t_all = time.perf_counter()
+    for _ in range(max(1, args.warmup)):
+        cpu_assemble_rate(repeats=1)
+    for _ in range(args.steps):
+        r, sample = cpu_assemble_rate(repeats=1)
+        rates.append(r)
+        if time.perf_counter() - t_all > 240:
+            break
+    value = float(np.mean(rates))
+    n_el = 2 * (RES[0] - 1) * (RES[1] - 1)
+    out = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+           'steps': len(rates), 'warmup': args.warmup, 'ms_per_step': 1e3 * n_el / value,
+           'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+           'config': {'workload': 'config 2: 2D P1 linear-elasticity cantilever, 3 998 792 triangles '
+                                  '(CPU arm timed on a 500 000-triangle sample, rate per element)'},
+           'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': sample},
+           'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def slab_mesh(rank, world):
+    """Rank `rank`'s slab of a cantilever `world` times longer: the nodes it owns plus one ghost
+    column of cells on each interior side (owner-computes assembly needs no communication)."""
+    import fes_b200 as F
+    if world == 1:
+        return F.create_rect_mesh(CORNERS, RES)
+    corners = [[CORNERS[0][0] + rank * 4.0 - (4.0 / (RES[0] - 1)) * (rank > 0), 0.0],
+               [CORNERS[0][0] + (rank + 1) * 4.0 + (4.0 / (RES[0] - 1)) * (rank < world - 1), 1.0]]
+    nx = RES[0] + (rank > 0) + (rank < world - 1)
+    return F.create_rect_mesh(corners, (nx, RES[1]))
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import fes_b200 as F
+    from fes_b200 import _lib
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+    L = _lib.lib()
+
+    mesh = slab_mesh(rank, world)
+    n_el, n_nodes = len(mesh.elements), len(mesh.vertices)
+    V = F.FunctionSpace(mesh, n_components=2)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    plan = V.plan()
+    torch.cuda.synchronize()
+    plan_s = time.perf_counter() - t0
+    form = F.LinearElasticForm(F.LinearElasticMaterial(E, NU))
+    values = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
+    cf = form.lower(V).coeffs()
+
+    def step():
+        _lib.check(L.fes_assemble(plan.handle, _lib.P1_TRI, _lib.FORM_ELASTIC, 2, _lib.ptr(V._en_d),
+                                  _lib.ptr(V._coords_d), C.byref(cf), _lib.ptr(values), _lib.stream()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_step = ms / args.steps
+    total_el = n_el * world if world == 1 else int(2 * (RES[0] - 1) * (RES[1] - 1) * world)
+    value = total_el / (ms_step * 1e-3)
+
+    # roofline of the fused assembly kernel (one launch per step): algorithmic bytes per SURVEY 8(d)
+    alg_bytes = 4 * 3 * n_el + 8 * 2 * n_nodes + 8 * plan.nnz
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get('k_assemble_pairs_c2_bytes_per_launch')
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': traffic, 'kernel': 'k_assemble_pairs<P1_TRI,ELASTIC,2,2>', 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': alg_bytes, 'bytes_per_element': alg_bytes / n_el,
+                'plan_bytes_read_per_launch': plan.read_bytes}
+
+    # end to end through the C ABI with HOST buffers: H2D coordinates, assemble, D2H values
+    h_coords = torch.as_tensor(mesh.vertices).pin_memory()
+    h_values = torch.empty(plan.nnz, dtype=torch.float64).pin_memory()
+    cf_host = _lib.Coeffs(E, NU, 1.0, None, None)
+
+    def e2e_step():
+        _lib.check(L.fes_assemble_host(plan.handle, _lib.P1_TRI, _lib.FORM_ELASTIC, 2, _lib.ptr(V._en_d),
+                                       C.c_void_p(h_coords.data_ptr()), n_nodes, C.byref(cf_host), None, None,
+                                       C.c_void_p(h_values.data_ptr()), _lib.stream()))
+    e2e_step()
+    barrier()
+    k_e2e = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / k_e2e
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {'value': total_el / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(h_coords.numel() * 8),
+           'd2h_bytes_per_step': int(plan.nnz * 8), 'ms_per_step': e2e_s * 1e3,
+           'api': 'fes_assemble_host (pinned host coordinates in, pinned host CSR values out)'}
+
+    out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+           'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+           'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+           'config': {'workload': 'config 2: 2D P1 linear-elasticity cantilever, create_rect_mesh([[0,0],[4,1]], '
+                                  '(2829,708)) = 3 998 792 triangles, 4 005 864 dofs, E=200 nu=0.3'
+                                  + (f'; {world} slabs side by side, one per GPU, ghost-element owner-computes' if world > 1 else ''),
+                      'n_elements_per_gpu': n_el, 'nnz_per_gpu': plan.nnz,
+                      'l2': 'inputs+outputs per step (0.5 GB) exceed the 126 MB L2; no flush needed'},
+           'roofline': roofline, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks.summary()}
+
+    extra = {'plan_build_s': plan_s, 'plan_device_bytes': plan.bytes}
+    if rank == 0 and world == 1:
+        rate, sample = cpu_assemble_rate()
+        out['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': sample,
+                               'host_cpus': os.cpu_count()}
+        if not args.no_extra:
+            extra.update(extra_metrics(F, V, mesh, dev))
+    out['extra'] = extra
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extra_metrics(F, V, mesh, dev):
+    """Secondary numbers of BASELINE.json: the PCG solve of config 2 and SIMP iterations/sec on
+    config 4 (1201x401 nodes, 960 000 triangles, MBB beam)."""
+    import torch
+    from fes_b200.regions import in_box, intersect, on_plane
+    out = {}
+    bc = F.BoundaryConditions()
+    bc.add(F.BCType.DIRICHLET, on_plane(0, 0.0), [0, 0])
+    bc.add(F.BCType.NEUMANN, on_plane(0, 4.0), [0, -1])
+    prob = F.LinearProblem(V, F.LinearElasticForm(F.LinearElasticMaterial(E, NU)), None, bc)
+    system = F.DiscreteSystem(prob.tangent(None), prob.constraints, F.JacobiPCGBackend(rtol=1e-10))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    system.solve(prob.load_d)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    its = system.solver.last_iterations
+    nnz, n = prob.tangent(None).nnz, V.n_dofs
+    out['pcg_config2'] = {'dofs': n, 'iterations': its, 'seconds': dt, 'us_per_iteration': 1e6 * dt / max(its, 1),
+                          'relres': system.solver.last_relres,
+                          'hbm_frac_of_measured': ((12 * nnz + 4 * (n + 1) + 80 * n) / (dt / max(its, 1)) / 1e9)
+                          / measured_peak()[0]}
+    del system, prob
+    w, h = 3.0, 1.0
+    m4 = F.create_rect_mesh([[0, 0], [w, h]], (1201, 401))
+    bc = F.BoundaryConditions()
+    bottom, top = on_plane(1, 0.0), on_plane(1, h)
+    bc.add(F.BCType.DIRICHLET, intersect(bottom, in_box([None, None], [0.04 * w, None])), [0, 0])
+    bc.add(F.BCType.DIRICHLET, intersect(bottom, in_box([0.96 * w, None], [None, None])), [None, 0])
+    bc.add(F.BCType.NEUMANN, intersect(top, in_box([0.4 * w, None], [0.6 * w, None])), [0, -0.5])
+    topo = F.TopologyOptimizer(m4, F.LinearElastic(200.0, 0.4), bc, iters=5, volume_frac=0.5,
+                               smoothing_radius=0.00625, penalty=3.0, history=None)
+    topo.step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_it = 4
+    comps = [topo.step().total_compliance for _ in range(n_it)]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out['simp_config4'] = {'elements': len(m4.elements), 'iterations_per_s': n_it / dt, 'design_iterations_timed': n_it,
+                           'cg_iterations': topo.cg_iterations, 'total_compliance': comps,
+                           'reference_iterations_per_s_survey': 0.0117}
+    return out
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--no-extra', action='store_true')
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl != 'reference' else a.warmup
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_gpu(a)
