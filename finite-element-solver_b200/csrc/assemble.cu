@@ -10,20 +10,24 @@
 // result is deterministic; element matrices never exist in HBM.
 #include "elements.cuh"
 #include "plan.cuh"
+#include "tma.cuh"
 
 namespace fes {
 namespace {
 
 constexpr int kBlock = 128;
 
+// Lame parameters per unit modulus are computed once on the host (no fp64 divide per element):
+// mu = E * mu1, lam = E * lam1  (ref fem/materials.py:24-28)
 struct Coeffs {
-  double E, nu, factor;
+  double E, mu1, lam1, factor;
   const double* d_E;
   const double* d_scale;
 };
 
 __device__ __forceinline__ void element_coeffs(const Coeffs& c, int64_t e, Material& m, double& w) {
-  m = lame(c.d_E ? __ldg(c.d_E + e) : c.E, c.nu);
+  const double E = c.d_E ? __ldg(c.d_E + e) : c.E;
+  m = Material{E * c.mu1, E * c.lam1};
   w = c.d_scale ? c.factor * __ldg(c.d_scale + e) : c.factor;
 }
 
@@ -99,6 +103,218 @@ k_assemble_pairs(int64_t n_pairs, const uint32_t* __restrict__ pair_start, const
   }
 }
 
+
+// ---- fused assembly, tiled (the production kernel) ------------------------------------------
+// One CTA per tile of consecutive nodes.
+//   phase 1: one thread per (node, incident element) evaluates the element's geometry ONCE --
+//            inverse Jacobian, every node's physical gradient at every quadrature point, and the
+//            element weight(s) -- into a shared-memory record (the fp64 divide lives here).
+//   phase 2: one thread per stored node pair walks its contributions in ascending element id,
+//            reads the two gradients it needs from the records and accumulates the C x C block
+//            in registers with fused multiply-adds; each CSR value is written exactly once.
+// Shared memory holds records only; nothing but the CSR values is written to HBM.
+template <int ELEM, int FORM, int C, int SD>
+struct RecLayout {
+  static constexpr int N = ET<ELEM>::N, NQ = ET<ELEM>::NQ;
+  static constexpr int NG = (FORM == FES_FORM_MASS) ? 0 : NQ * N * SD;  // gradients
+  static constexpr int NW = (FORM == FES_FORM_ELASTIC) ? 2 : 1;         // weights
+  static constexpr int SIZE = NG + NW;
+};
+
+constexpr int kTileThreads = 256;
+constexpr int kRecBatch = 2;  // records a thread evaluates per pass of phase 1 (memory-level parallelism)
+
+// shared-memory carve-up of one tile (bytes); records first, then the TMA-staged plan streams
+template <int ELEM, int FORM, int C, int SD>
+struct TileSmem {
+  using R = RecLayout<ELEM, FORM, C, SD>;
+  static constexpr int N = ET<ELEM>::N;
+  __host__ __device__ static size_t rec_bytes(int gmax) { return (size_t)gmax * R::SIZE * sizeof(double); }
+  __host__ __device__ static size_t contrib_bytes(int gmax) { return ((size_t)gmax * N * 2 + 32 + 15) & ~(size_t)15; }
+  __host__ __device__ static size_t off_bytes(int pmax) { return ((size_t)pmax * 2 + 32 + 15) & ~(size_t)15; }
+  __host__ __device__ static size_t lrow_bytes(int pmax) { return ((size_t)pmax + 32 + 15) & ~(size_t)15; }
+  __host__ __device__ static size_t total(int gmax, int pmax) {
+    return rec_bytes(gmax) + contrib_bytes(gmax) + 2 * off_bytes(pmax) + lrow_bytes(pmax);
+  }
+};
+
+template <int ELEM, int FORM, int C, int SD>
+__global__ void __launch_bounds__(kTileThreads)
+k_assemble_tiles(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__ ne_ptr,
+                 const uint32_t* __restrict__ ne_code, const int32_t* __restrict__ node_ptr,
+                 const uint16_t* __restrict__ pair_off16, const uint8_t* __restrict__ pair_lrow,
+                 const uint16_t* __restrict__ pair_perm16, const uint16_t* __restrict__ contrib16,
+                 const int32_t* __restrict__ en, const double* __restrict__ coords, Coeffs cf, int geo_stride,
+                 int pair_max, double* __restrict__ values) {
+  using R = RecLayout<ELEM, FORM, C, SD>;
+  using TS = TileSmem<ELEM, FORM, C, SD>;
+  constexpr int N = ET<ELEM>::N, NQ = ET<ELEM>::NQ, RD = ET<ELEM>::RD;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int32_t s_node_ptr[257];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_skew[4];
+  const int GS = geo_stride;
+  double* smem = reinterpret_cast<double*>(smem_raw);  // records, field-major: field f of record g at smem[f*GS+g]
+  unsigned char* s_contrib = smem_raw + TS::rec_bytes(GS);
+  unsigned char* s_off = s_contrib + TS::contrib_bytes(GS);
+  unsigned char* s_perm = s_off + TS::off_bytes(pair_max);
+  unsigned char* s_lrow = s_perm + TS::off_bytes(pair_max);
+
+  const int32_t v0 = tile_node0[blockIdx.x], v1 = tile_node0[blockIdx.x + 1];
+  const int32_t g0 = ne_ptr[v0], g1 = ne_ptr[v1];
+  const int32_t p0 = node_ptr[v0], p1 = node_ptr[v1];
+
+  // ---- stage this tile's contiguous plan streams with TMA bulk copies (overlaps phase 1)
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    uint32_t b0, b1, b2;
+    const uint32_t n_contrib = (uint32_t)N * (uint32_t)(g1 - g0), n_pairs = (uint32_t)(p1 - p0);
+    // expect_tx must precede the copies' completion; compute sizes first
+    const uint64_t c_begin = (uint64_t)N * (uint64_t)g0 * 2, o_begin = (uint64_t)p0 * 2, l_begin = (uint64_t)p0;
+    b0 = (uint32_t)(((c_begin & 15) + (uint64_t)n_contrib * 2 + 15) & ~(uint64_t)15);
+    b1 = (uint32_t)(((o_begin & 15) + (uint64_t)n_pairs * 2 + 15) & ~(uint64_t)15);
+    b2 = (uint32_t)(((l_begin & 15) + (uint64_t)n_pairs + 15) & ~(uint64_t)15);
+    mbar_arrive_expect_tx(&s_bar, b0 + 2 * b1 + b2);
+    uint32_t t;
+    s_skew[0] = stage_window<2>(s_contrib, contrib16, (uint32_t)N * (uint32_t)g0, n_contrib, &s_bar, t);
+    s_skew[1] = stage_window<2>(s_off, pair_off16, (uint32_t)p0, n_pairs, &s_bar, t);
+    s_skew[2] = stage_window<1>(s_lrow, pair_lrow, (uint32_t)p0, n_pairs, &s_bar, t);
+    s_skew[3] = stage_window<2>(s_perm, pair_perm16, (uint32_t)p0, n_pairs, &s_bar, t);
+  }
+  for (int l = threadIdx.x; l <= v1 - v0; l += kTileThreads) s_node_ptr[l] = node_ptr[v0 + l];
+
+  // ---- phase 1: geometry records, kRecBatch per thread so the index -> connectivity -> coordinate
+  //      load chain of several records is in flight together
+  for (int32_t base = g0 + threadIdx.x; base < g1; base += kTileThreads * kRecBatch) {
+    uint32_t e[kRecBatch];
+    bool live[kRecBatch];
+#pragma unroll
+    for (int r = 0; r < kRecBatch; ++r) {
+      const int32_t gi = base + r * kTileThreads;
+      live[r] = gi < g1;
+      e[r] = live[r] ? (__ldg(ne_code + gi) >> 3) : 0u;
+    }
+    int32_t ids[kRecBatch][RD + 1];
+#pragma unroll
+    for (int r = 0; r < kRecBatch; ++r)
+#pragma unroll
+      for (int n = 0; n <= RD; ++n) ids[r][n] = live[r] ? __ldg(en + (int64_t)e[r] * N + n) : 0;
+    double X[kRecBatch][RD + 1][SD];
+#pragma unroll
+    for (int r = 0; r < kRecBatch; ++r)
+#pragma unroll
+      for (int n = 0; n <= RD; ++n) {
+        if constexpr (SD == 2) {
+          const double2 xy = __ldg(reinterpret_cast<const double2*>(coords) + ids[r][n]);
+          X[r][n][0] = xy.x; X[r][n][1] = xy.y;
+        } else {
+#pragma unroll
+          for (int s = 0; s < SD; ++s) X[r][n][s] = __ldg(coords + (int64_t)ids[r][n] * SD + s);
+        }
+      }
+#pragma unroll
+    for (int r = 0; r < kRecBatch; ++r) {
+      if (!live[r]) continue;
+      Geom<RD, SD> g;
+      make_geom<RD, SD>(X[r], g);
+      Material m; double w;
+      element_coeffs(cf, e[r], m, w);
+      double* rec = smem + (base + r * kTileThreads - g0);
+      const double vol = g.scale * ref_measure(RD);
+      if constexpr (FORM == FES_FORM_MASS) {
+        rec[0] = w * vol;
+      } else {
+        const double wq = w * vol / (double)NQ;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            double gn[SD];
+            shape_grad<ELEM, SD>(g, q, n, gn);
+#pragma unroll
+            for (int s = 0; s < SD; ++s) rec[((q * N + n) * SD + s) * GS] = gn[s];
+          }
+        if constexpr (FORM == FES_FORM_ELASTIC) {
+          rec[R::NG * GS] = wq * m.lam;
+          rec[(R::NG + 1) * GS] = wq * m.mu;
+        } else {
+          rec[R::NG * GS] = wq;
+        }
+      }
+    }
+  }
+  __syncthreads();          // records + s_node_ptr + s_skew visible
+  mbar_wait(&s_bar, 0);     // staged streams have landed
+
+  // ---- phase 2: one thread per stored pair
+  const uint16_t* codes = reinterpret_cast<const uint16_t*>(s_contrib + s_skew[0]);
+  const uint16_t* offs = reinterpret_cast<const uint16_t*>(s_off + s_skew[1]);
+  const uint8_t* lrows = s_lrow + s_skew[2];
+  const uint16_t* perm = reinterpret_cast<const uint16_t*>(s_perm + s_skew[3]);
+  const int n_pairs = p1 - p0;
+  const uint32_t n_contrib = (uint32_t)N * (uint32_t)(g1 - g0);
+  for (int tt_ = threadIdx.x; tt_ < n_pairs; tt_ += kTileThreads) {
+    const int t = perm[tt_];  // pairs in descending contribution count: uniform trip counts per warp
+    const uint32_t k0 = offs[t];
+    const uint32_t k1 = (t + 1 < n_pairs) ? offs[t + 1] : n_contrib;
+    double acc[C][C];
+#pragma unroll
+    for (int i = 0; i < C; ++i)
+#pragma unroll
+      for (int j = 0; j < C; ++j) acc[i][j] = 0.0;
+    for (uint32_t k = k0; k < k1; ++k) {
+      const uint32_t code = codes[k];
+      const int a = (code >> 3) & 7, b = code & 7;
+      const double* rec = smem + (code >> 6);
+      if constexpr (FORM == FES_FORM_MASS) {
+        acc[0][0] = fma(rec[0], mass_ref<ELEM>(a, b), acc[0][0]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const double* ga = rec + (q * N + a) * SD * GS;
+          const double* gb = rec + (q * N + b) * SD * GS;
+          double A_[SD], B_[SD];
+#pragma unroll
+          for (int s = 0; s < SD; ++s) { A_[s] = ga[s * GS]; B_[s] = gb[s * GS]; }
+          double dot = 0.0;
+#pragma unroll
+          for (int s = 0; s < SD; ++s) dot = fma(A_[s], B_[s], dot);
+          if constexpr (FORM == FES_FORM_LAPLACIAN) {
+            acc[0][0] = fma(rec[R::NG * GS], dot, acc[0][0]);
+          } else {
+            const double wl = rec[R::NG * GS], wm = rec[(R::NG + 1) * GS];
+#pragma unroll
+            for (int i = 0; i < C; ++i)
+#pragma unroll
+              for (int j = 0; j < C; ++j) {
+                double tt = fma(wl, A_[i] * B_[j], acc[i][j]);
+                acc[i][j] = fma(wm, A_[j] * B_[i], tt);
+              }
+#pragma unroll
+            for (int i = 0; i < C; ++i) acc[i][i] = fma(wm, dot, acc[i][i]);
+          }
+        }
+      }
+    }
+    const int l = lrows[t];
+    const int32_t np0 = s_node_ptr[l], deg = s_node_ptr[l + 1] - np0, s = p0 + t - np0;
+    double* out = values + (int64_t)C * C * np0 + (int64_t)C * s;
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+      double* row = out + (int64_t)i * C * deg;
+      if constexpr (FORM == FES_FORM_MASS) {
+#pragma unroll
+        for (int j = 0; j < C; ++j) row[j] = (i == j) ? acc[0][0] : 0.0;
+      } else if constexpr (C == 2) {
+        *reinterpret_cast<double2*>(row) = make_double2(acc[i][0], acc[i][1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < C; ++j) row[j] = acc[i][j];
+      }
+    }
+  }
+}
+
 // PrecomputedForm: gather caller-supplied (n_el, K, K) matrices, optionally scaled per element
 template <int C>
 __global__ void __launch_bounds__(kBlock)
@@ -147,6 +363,7 @@ struct Job {
   Coeffs cf;
   double* out;
   cudaStream_t stream;
+  bool untiled = false;  // force the reference-order (untiled) kernel
 };
 
 template <int ELEM, int FORM, int C, int SD>
@@ -159,9 +376,22 @@ int run(const Job& j) {
   } else {
     const fes_plan* P = j.plan;
     if (P->n_pairs == 0) return FES_OK;
-    k_assemble_pairs<ELEM, FORM, C, SD><<<grid_for(P->n_pairs, kBlock), kBlock, 0, j.stream>>>(
-        P->n_pairs, P->pair_start.p, P->pair_row.p, P->node_ptr.p, P->contrib.p, P->indptr.p, j.en, j.coords, j.cf,
-        j.out);
+    if (P->tiled && !j.untiled) {
+      const size_t smem = TileSmem<ELEM, FORM, C, SD>::total(P->geo_max, P->pair_max);
+      static size_t configured = 0;  // per template instantiation: largest opt-in so far
+      if (smem + 2048 > 48 * 1024 && smem > configured) {  // static smem counts toward the 48 KB default
+        FES_CUDA(cudaFuncSetAttribute(k_assemble_tiles<ELEM, FORM, C, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        configured = smem;
+      }
+      k_assemble_tiles<ELEM, FORM, C, SD><<<(unsigned)P->n_tiles, kTileThreads, smem, j.stream>>>(
+          P->tile_node0.p, P->ne_ptr.p, P->ne_code.p, P->node_ptr.p, P->pair_off16.p, P->pair_lrow.p,
+          P->pair_perm16.p, P->contrib16.p, j.en, j.coords, j.cf, P->geo_max, P->pair_max, j.out);
+    } else {
+      k_assemble_pairs<ELEM, FORM, C, SD><<<grid_for(P->n_pairs, kBlock), kBlock, 0, j.stream>>>(
+          P->n_pairs, P->pair_start.p, P->pair_row.p, P->node_ptr.p, P->contrib.p, P->indptr.p, j.en, j.coords, j.cf,
+          j.out);
+    }
   }
   FES_LAUNCH_CHECK();
   return FES_OK;
@@ -213,7 +443,8 @@ int dispatch(const Job& j, int elem, int form, int c, int sd) {
 
 int check_coeffs(const fes_coeffs* c, Coeffs& out) {
   if (!c) return set_error(FES_ERR_VALUE, "coeffs is NULL");
-  out = Coeffs{c->E, c->nu, c->factor, c->d_E, c->d_scale};
+  out = Coeffs{c->E, 1.0 / (2.0 * (1.0 + c->nu)), c->nu / ((1.0 + c->nu) * (1.0 - 2.0 * c->nu)), c->factor, c->d_E,
+               c->d_scale};
   return FES_OK;
 }
 

@@ -12,6 +12,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
+#include <vector>
+
 #include "plan.cuh"
 
 namespace fes {
@@ -81,6 +84,87 @@ __global__ void k_expand_indices(const int32_t* __restrict__ node_ptr, const int
   }
 }
 
+// incident-element list of node v = the contributions of its diagonal pair (v, v): every element
+// containing v appears there once, in ascending element id, with a == b == v's local index
+__global__ void k_diag_counts(const int32_t* __restrict__ pair_row, const int32_t* __restrict__ node_adj,
+                              const uint32_t* __restrict__ pair_start, int64_t n_pairs,
+                              int32_t* __restrict__ ne_cnt) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  if (pair_row[p] == node_adj[p]) ne_cnt[pair_row[p]] = (int32_t)(pair_start[p + 1] - pair_start[p]);
+}
+
+__global__ void k_fill_ne(const int32_t* __restrict__ pair_row, const int32_t* __restrict__ node_adj,
+                          const uint32_t* __restrict__ pair_start, const uint32_t* __restrict__ contrib,
+                          int64_t n_pairs, int N, const int32_t* __restrict__ ne_ptr,
+                          uint32_t* __restrict__ ne_code) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs || pair_row[p] != node_adj[p]) return;
+  const int N2 = N * N;
+  const int32_t base = ne_ptr[pair_row[p]];
+  const uint32_t k0 = pair_start[p], k1 = pair_start[p + 1];
+  for (uint32_t k = k0; k < k1; ++k) {
+    const uint32_t code = contrib[k], e = code / N2, a = (code - e * N2) / N;
+    ne_code[base + (k - k0)] = e * 8u + a;
+  }
+}
+
+// per pair: tile-relative row and contribution offset; per contribution: the tile-local record
+// index of (row node, element) packed with the local node indices
+__global__ void k_tile_codes(const int32_t* __restrict__ pair_row, const uint32_t* __restrict__ pair_start,
+                             const uint32_t* __restrict__ contrib, int64_t n_pairs, int N,
+                             const int32_t* __restrict__ ne_ptr, const uint32_t* __restrict__ ne_code,
+                             const int32_t* __restrict__ tile_node0, int64_t n_tiles,
+                             uint16_t* __restrict__ contrib16, uint16_t* __restrict__ pair_off16,
+                             uint8_t* __restrict__ pair_lrow) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  const int32_t v = pair_row[p];
+  int64_t lo = 0, hi = n_tiles;  // last tile with tile_node0[t] <= v
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (tile_node0[mid] <= v) lo = mid; else hi = mid;
+  }
+  const int32_t v0 = tile_node0[lo];
+  const int32_t g0 = ne_ptr[v0], gv0 = ne_ptr[v], gv1 = ne_ptr[v + 1];
+  const int N2 = N * N;
+  pair_lrow[p] = (uint8_t)(v - v0);
+  const uint32_t k0 = pair_start[p], k1 = pair_start[p + 1];
+  pair_off16[p] = (uint16_t)(k0 - (uint32_t)N * (uint32_t)g0);
+  for (uint32_t k = k0; k < k1; ++k) {
+    const uint32_t code = contrib[k], e = code / N2, ab = code - e * N2, a = ab / N, b = ab - a * N;
+    int32_t l = gv0, h = gv1;  // lower_bound of e in v's ascending incident list
+    while (l < h) {
+      const int32_t m = (l + h) >> 1;
+      if ((ne_code[m] >> 3) < e) l = m + 1; else h = m;
+    }
+    contrib16[k] = (uint16_t)(((uint32_t)(l - g0) << 6) | (a << 3) | b);
+  }
+}
+
+// Tile-local pair order sorted by contribution count (descending, stable) so the 32 pairs a warp
+// gathers have equal trip counts: a diagonal pair collects one contribution per incident element
+// (4-8 on a triangle mesh, ~24 on a tet mesh), an off-diagonal pair one per element on the edge.
+__global__ void k_tile_perm(const int32_t* __restrict__ tile_node0, int64_t n_tiles,
+                            const int32_t* __restrict__ node_ptr, const uint32_t* __restrict__ pair_start,
+                            uint16_t* __restrict__ perm) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const int32_t p0 = node_ptr[tile_node0[t]], p1 = node_ptr[tile_node0[t + 1]];
+  uint32_t hi = 0;
+  for (int32_t p = p0; p < p1; ++p) hi = max(hi, pair_start[p + 1] - pair_start[p]);
+  int32_t w = p0;
+  while (hi > 0) {
+    uint32_t next = 0;
+    for (int32_t p = p0; p < p1; ++p) {
+      const uint32_t c = pair_start[p + 1] - pair_start[p];
+      if (c == hi) perm[w++] = (uint16_t)(p - p0);
+      else if (c < hi) next = max(next, c);
+    }
+    hi = next;
+  }
+}
+
 __global__ void k_widen(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) out[t] = in[t];
@@ -90,6 +174,72 @@ int bits_for(uint64_t max_value) {
   int b = 1;
   while (b < 64 && (max_value >> b) != 0) ++b;
   return b;
+}
+
+// Tile the node range for the fused assembly kernel.  The greedy split runs on the host over the
+// two prefix arrays (O(n_nodes), once per mesh); everything else stays on the device.
+int build_tiles(fes_plan* P, cudaStream_t stream) {
+  const int64_t nn = P->n_nodes, np_ = P->n_pairs;
+  const int N = P->N;
+  P->tiled = false;
+  if (np_ == 0) return FES_OK;
+  DevBuf<int32_t> ne_cnt;
+  FES_CUDA(ne_cnt.alloc(nn + 1));
+  FES_CUDA(cudaMemsetAsync(ne_cnt.p, 0, ne_cnt.bytes(), stream));
+  k_diag_counts<<<grid_for(np_, kBlock), kBlock, 0, stream>>>(P->pair_row.p, P->node_adj.p, P->pair_start.p, np_, ne_cnt.p);
+  FES_LAUNCH_CHECK();
+  FES_CUDA(P->ne_ptr.alloc(nn + 1));
+  size_t tb = 0;
+  FES_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, ne_cnt.p, P->ne_ptr.p, nn + 1, stream));
+  DevBuf<uint8_t> tmp;
+  FES_CUDA(tmp.alloc(tb));
+  FES_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, ne_cnt.p, P->ne_ptr.p, nn + 1, stream));
+  count_launch(2);
+  std::vector<int32_t> h_ne(nn + 1), h_np(nn + 1);
+  FES_CUDA(cudaMemcpyAsync(h_ne.data(), P->ne_ptr.p, (nn + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  FES_CUDA(cudaMemcpyAsync(h_np.data(), P->node_ptr.p, (nn + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  FES_CUDA(cudaStreamSynchronize(stream));
+  P->n_geo = h_ne[nn];
+  if (P->n_geo != P->n_el * N) return FES_OK;  // degenerate elements (repeated nodes): keep the untiled kernel
+  if (P->n_el >= ((int64_t)1 << 29)) return FES_OK;
+  const int gmax = tile_geo_budget(N);
+  P->geo_max = gmax;
+  std::vector<int32_t> tiles;
+  tiles.push_back(0);
+  int64_t v0 = 0;
+  for (int64_t v = 0; v < nn; ++v) {
+    const int64_t geo = h_ne[v + 1] - h_ne[v0];
+    if (h_ne[v + 1] - h_ne[v] > gmax) return FES_OK;  // one node alone overflows a tile: untiled kernel
+    if (geo > gmax || v - v0 >= 255) {
+      tiles.push_back((int32_t)v);
+      v0 = v;
+    }
+  }
+  tiles.push_back((int32_t)nn);
+  P->n_tiles = (int64_t)tiles.size() - 1;
+  int pmax = 0;
+  for (size_t t = 0; t + 1 < tiles.size(); ++t) pmax = std::max(pmax, (int)(h_np[tiles[t + 1]] - h_np[tiles[t]]));
+  P->pair_max = pmax;
+  FES_CUDA(P->tile_node0.alloc(tiles.size()));
+  FES_CUDA(cudaMemcpyAsync(P->tile_node0.p, tiles.data(), tiles.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  FES_CUDA(P->ne_code.alloc(P->n_geo));
+  k_fill_ne<<<grid_for(np_, kBlock), kBlock, 0, stream>>>(P->pair_row.p, P->node_adj.p, P->pair_start.p, P->contrib.p, np_,
+                                                          N, P->ne_ptr.p, P->ne_code.p);
+  FES_LAUNCH_CHECK();
+  FES_CUDA(P->contrib16.alloc(P->n_contrib + 16));
+  FES_CUDA(P->pair_off16.alloc(np_ + 16));
+  FES_CUDA(P->pair_lrow.alloc(np_ + 32));
+  k_tile_codes<<<grid_for(np_, kBlock), kBlock, 0, stream>>>(P->pair_row.p, P->pair_start.p, P->contrib.p, np_, N,
+                                                             P->ne_ptr.p, P->ne_code.p, P->tile_node0.p, P->n_tiles,
+                                                             P->contrib16.p, P->pair_off16.p, P->pair_lrow.p);
+  FES_LAUNCH_CHECK();
+  FES_CUDA(P->pair_perm16.alloc(np_ + 16));
+  k_tile_perm<<<grid_for(P->n_tiles, 64), 64, 0, stream>>>(P->tile_node0.p, P->n_tiles, P->node_ptr.p, P->pair_start.p,
+                                                         P->pair_perm16.p);
+  FES_LAUNCH_CHECK();
+  FES_CUDA(cudaStreamSynchronize(stream));
+  P->tiled = true;
+  return FES_OK;
 }
 
 }  // namespace
@@ -198,6 +348,7 @@ extern "C" int fes_plan_create(const int32_t* d_elem_nodes, int64_t n_el, int N,
                                                                      n_pairs, n_comp, P->indices.p);
   FES_LAUNCH_CHECK();
   FES_CUDA(cudaStreamSynchronize(stream));
+  FES_TRY(build_tiles(P, stream));
   guard.p = nullptr;
   *out = P;
   return FES_OK;
@@ -213,12 +364,17 @@ extern "C" const int32_t* fes_plan_indices(const fes_plan* p) { return p ? p->in
 extern "C" int64_t fes_plan_bytes(const fes_plan* p) {
   if (!p) return 0;
   return (int64_t)(p->node_ptr.bytes() + p->node_adj.bytes() + p->pair_row.bytes() + p->pair_start.bytes() +
-                   p->contrib.bytes() + p->indptr.bytes() + p->indices.bytes());
+                   p->contrib.bytes() + p->indptr.bytes() + p->indices.bytes() + p->ne_ptr.bytes() +
+                   p->ne_code.bytes() + p->tile_node0.bytes() + p->contrib16.bytes() + p->pair_off16.bytes() +
+                   p->pair_lrow.bytes() + p->pair_perm16.bytes());
 }
 
-// what one fused assembly streams from the plan: pair_row + pair_start + contrib + node_ptr + indptr
+// what one fused assembly streams from the plan (overhead on top of the algorithmic bytes)
 extern "C" int64_t fes_plan_read_bytes(const fes_plan* p) {
   if (!p) return 0;
+  if (p->tiled)
+    return (int64_t)(p->ne_ptr.bytes() + p->ne_code.bytes() + p->tile_node0.bytes() + p->contrib16.bytes() +
+                     p->pair_off16.bytes() + p->pair_lrow.bytes() + p->pair_perm16.bytes() + p->node_ptr.bytes());
   return (int64_t)(p->pair_row.bytes() + p->pair_start.bytes() + p->contrib.bytes() + p->node_ptr.bytes() +
                    p->indptr.bytes());
 }

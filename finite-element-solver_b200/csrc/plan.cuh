@@ -16,4 +16,32 @@ struct fes_plan {
   // scalar CSR, bit-identical to the reference's _ScatterPlan.indptr / .indices
   fes::DevBuf<int32_t> indptr;   // n_dofs + 1
   fes::DevBuf<int32_t> indices;  // nnz
+
+  // ---- tiled layout for the fused assembly kernel ------------------------------------------
+  // A tile is a run of consecutive nodes whose (node, incident element) records fit in shared
+  // memory.  Phase 1 of the kernel evaluates one geometry record per (node, element); phase 2
+  // gathers each pair's contributions from those records.
+  bool tiled = false;
+  int64_t n_tiles = 0, n_geo = 0;
+  int geo_max = 0;                     // records per tile upper bound
+  int pair_max = 0;                    // stored pairs per tile upper bound
+  fes::DevBuf<int32_t> ne_ptr;         // n_nodes + 1 : incident-element ranges per node
+  fes::DevBuf<uint32_t> ne_code;       // n_geo : e*8 + a, ascending e per node
+  fes::DevBuf<int32_t> tile_node0;     // n_tiles + 1
+  fes::DevBuf<uint16_t> contrib16;     // n_contrib : (record index in tile)<<6 | a<<3 | b
+  fes::DevBuf<uint16_t> pair_off16;    // n_pairs : first contribution, relative to the tile's first
+  fes::DevBuf<uint8_t> pair_lrow;      // n_pairs : row node, relative to the tile's first node
+  fes::DevBuf<uint16_t> pair_perm16;   // n_pairs : tile-local pair order, by contribution count descending
 };
+
+namespace fes {
+// records per tile for an element with N nodes (sized for the largest record, elasticity)
+inline int tile_geo_budget(int N) {
+  switch (N) {
+    case 2: return 512;
+    case 3: return 512;    // 3-node: P1 triangle (8 doubles -> 32 KB) or P2 line
+    case 4: return 384;    // P1 tet (14 doubles -> 42 KB)
+    default: return 160;   // P2 triangle (38 doubles -> 48 KB)
+  }
+}
+}  // namespace fes
