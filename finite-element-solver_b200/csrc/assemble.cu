@@ -23,6 +23,8 @@ struct Coeffs {
   double E, mu1, lam1, factor;
   const double* d_E;
   const double* d_scale;
+  double lam_over_mu;  // = 2 nu / (1 - 2 nu)
+  double sign;         // sign of the global factor; the tiled kernel works with |factor|
 };
 
 __device__ __forceinline__ void element_coeffs(const Coeffs& c, int64_t e, Material& m, double& w) {
@@ -116,8 +118,10 @@ k_assemble_pairs(int64_t n_pairs, const uint32_t* __restrict__ pair_start, const
 template <int ELEM, int FORM, int C, int SD>
 struct RecLayout {
   static constexpr int N = ET<ELEM>::N, NQ = ET<ELEM>::NQ;
-  static constexpr int NG = (FORM == FES_FORM_MASS) ? 0 : NQ * N * SD;  // gradients
-  static constexpr int NW = (FORM == FES_FORM_ELASTIC) ? 2 : 1;         // weights
+  // gradient forms store sqrt(weight)-scaled gradients, so no separate weight is needed;
+  // the mass form stores the weighted measure only
+  static constexpr int NG = (FORM == FES_FORM_MASS) ? 0 : NQ * N * SD;
+  static constexpr int NW = (FORM == FES_FORM_MASS) ? 1 : 0;
   static constexpr int SIZE = NG + NW;
 };
 
@@ -224,7 +228,11 @@ k_assemble_tiles(const int32_t* __restrict__ tile_node0, const int32_t* __restri
       if constexpr (FORM == FES_FORM_MASS) {
         rec[0] = w * vol;
       } else {
-        const double wq = w * vol / (double)NQ;
+        // g~ = sqrt(w_q E_e) g: the element's weight and modulus ride on the gradients, so phase 2
+        // accumulates plain outer products and applies the (uniform) Lame factors once per pair
+        double wq = w * vol / (double)NQ;
+        if constexpr (FORM == FES_FORM_ELASTIC) wq *= m.mu;  // m.mu carries E_e (mu1 is divided out below)
+        const double sq = sqrt(wq);
 #pragma unroll
         for (int q = 0; q < NQ; ++q)
 #pragma unroll
@@ -232,14 +240,8 @@ k_assemble_tiles(const int32_t* __restrict__ tile_node0, const int32_t* __restri
             double gn[SD];
             shape_grad<ELEM, SD>(g, q, n, gn);
 #pragma unroll
-            for (int s = 0; s < SD; ++s) rec[((q * N + n) * SD + s) * GS] = gn[s];
+            for (int s = 0; s < SD; ++s) rec[((q * N + n) * SD + s) * GS] = sq * gn[s];
           }
-        if constexpr (FORM == FES_FORM_ELASTIC) {
-          rec[R::NG * GS] = wq * m.lam;
-          rec[(R::NG + 1) * GS] = wq * m.mu;
-        } else {
-          rec[R::NG * GS] = wq;
-        }
       }
     }
   }
@@ -272,29 +274,45 @@ k_assemble_tiles(const int32_t* __restrict__ tile_node0, const int32_t* __restri
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
           const double* ga = rec + (q * N + a) * SD * GS;
-          const double* gb = rec + (q * N + b) * SD * GS;
           double A_[SD], B_[SD];
 #pragma unroll
-          for (int s = 0; s < SD; ++s) { A_[s] = ga[s * GS]; B_[s] = gb[s * GS]; }
-          double dot = 0.0;
+          for (int s = 0; s < SD; ++s) A_[s] = ga[s * GS];
+          if (a == b) {  // a diagonal pair: one gradient serves both sides
 #pragma unroll
-          for (int s = 0; s < SD; ++s) dot = fma(A_[s], B_[s], dot);
-          if constexpr (FORM == FES_FORM_LAPLACIAN) {
-            acc[0][0] = fma(rec[R::NG * GS], dot, acc[0][0]);
+            for (int s = 0; s < SD; ++s) B_[s] = A_[s];
           } else {
-            const double wl = rec[R::NG * GS], wm = rec[(R::NG + 1) * GS];
+            const double* gb = rec + (q * N + b) * SD * GS;
+#pragma unroll
+            for (int s = 0; s < SD; ++s) B_[s] = gb[s * GS];
+          }
+          if constexpr (FORM == FES_FORM_LAPLACIAN) {
+#pragma unroll
+            for (int s = 0; s < SD; ++s) acc[0][0] = fma(A_[s], B_[s], acc[0][0]);
+          } else {
 #pragma unroll
             for (int i = 0; i < C; ++i)
 #pragma unroll
-              for (int j = 0; j < C; ++j) {
-                double tt = fma(wl, A_[i] * B_[j], acc[i][j]);
-                acc[i][j] = fma(wm, A_[j] * B_[i], tt);
-              }
-#pragma unroll
-            for (int i = 0; i < C; ++i) acc[i][i] = fma(wm, dot, acc[i][i]);
+              for (int j = 0; j < C; ++j) acc[i][j] = fma(A_[i], B_[j], acc[i][j]);  // S += g~_a (x) g~_b
           }
         }
       }
+    }
+    if constexpr (FORM == FES_FORM_ELASTIC) {
+      // K = (lam/mu) S + S^T + tr(S) I, in units where the stored gradients carry mu_e w_q
+      double tr = 0.0;
+#pragma unroll
+      for (int i = 0; i < C; ++i) tr += acc[i][i];
+      double K[C][C];
+#pragma unroll
+      for (int i = 0; i < C; ++i)
+#pragma unroll
+        for (int j = 0; j < C; ++j) K[i][j] = fma(cf.lam_over_mu, acc[i][j], acc[j][i]) + (i == j ? tr : 0.0);
+#pragma unroll
+      for (int i = 0; i < C; ++i)
+#pragma unroll
+        for (int j = 0; j < C; ++j) acc[i][j] = cf.sign * K[i][j];
+    } else if constexpr (FORM == FES_FORM_LAPLACIAN) {
+      acc[0][0] *= cf.sign;
     }
     const int l = lrows[t];
     const int32_t np0 = s_node_ptr[l], deg = s_node_ptr[l + 1] - np0, s = p0 + t - np0;
@@ -384,9 +402,11 @@ int run(const Job& j) {
                                       (int)smem));
         configured = smem;
       }
+      Coeffs cf = j.cf;
+      if (FORM != FES_FORM_MASS && cf.factor < 0.0) { cf.factor = -cf.factor; cf.sign = -1.0; }
       k_assemble_tiles<ELEM, FORM, C, SD><<<(unsigned)P->n_tiles, kTileThreads, smem, j.stream>>>(
           P->tile_node0.p, P->ne_ptr.p, P->ne_code.p, P->node_ptr.p, P->pair_off16.p, P->pair_lrow.p,
-          P->pair_perm16.p, P->contrib16.p, j.en, j.coords, j.cf, P->geo_max, P->pair_max, j.out);
+          P->pair_perm16.p, P->contrib16.p, j.en, j.coords, cf, P->geo_max, P->pair_max, j.out);
     } else {
       k_assemble_pairs<ELEM, FORM, C, SD><<<grid_for(P->n_pairs, kBlock), kBlock, 0, j.stream>>>(
           P->n_pairs, P->pair_start.p, P->pair_row.p, P->node_ptr.p, P->contrib.p, P->indptr.p, j.en, j.coords, j.cf,
@@ -444,7 +464,7 @@ int dispatch(const Job& j, int elem, int form, int c, int sd) {
 int check_coeffs(const fes_coeffs* c, Coeffs& out) {
   if (!c) return set_error(FES_ERR_VALUE, "coeffs is NULL");
   out = Coeffs{c->E, 1.0 / (2.0 * (1.0 + c->nu)), c->nu / ((1.0 + c->nu) * (1.0 - 2.0 * c->nu)), c->factor, c->d_E,
-               c->d_scale};
+               c->d_scale, 2.0 * c->nu / (1.0 - 2.0 * c->nu), 1.0};
   return FES_OK;
 }
 

@@ -32,7 +32,11 @@ def _per_element(values, n_el, device, what):
     t = values if isinstance(values, torch.Tensor) else torch.as_tensor(np.asarray(values, dtype=np.float64))
     if t.numel() != n_el:
         raise ValueError(f'{what} has {t.numel()} entries but the mesh has {n_el} elements')
-    return t.to(device=device, dtype=torch.float64).contiguous()
+    t = t.to(device=device, dtype=torch.float64).contiguous()
+    if t.numel() and float(t.min()) < 0.0:
+        # the fused kernel folds sqrt(weight) into the stored gradients
+        raise ValueError(f'{what} must be nonnegative')
+    return t
 
 
 class _Form:
