@@ -90,7 +90,11 @@ class JacobiPCGBackend:
                 raise ValueError(f'operator must be square, got {A.shape}')
             _lib.check(L.fes_solver_create(A.shape[0], _lib.ptr(A.indptr_d), _lib.ptr(A.indices_d),
                                            _lib.ptr(A.data_d), _lib.ptr(free_mask), _lib.stream(), C.byref(handle)))
-            return PCGSolver(handle, A.shape[0], self.rtol, self.maxiter, keepalive=(A, free_mask), device=A.device)
+            plan = getattr(A, '_plan', None)
+            if plan is not None and A.indptr_d.data_ptr() == plan.indptr_d.data_ptr():
+                _lib.check(L.fes_solver_use_plan(handle, plan.handle))
+            return PCGSolver(handle, A.shape[0], self.rtol, self.maxiter, keepalive=(A, free_mask, plan),
+                             device=A.device)
         _lib.require_cuda()
         if free_mask is not None:
             raise ValueError('a free mask needs a DeviceCSR operator')

@@ -13,6 +13,7 @@ class DeviceCSR:
         self.shape = tuple(shape)
         self.indptr_d, self.indices_d, self.data_d = indptr, indices, data
         self._host_pattern = host_pattern   # callable -> (indptr int64, indices int64), cached by the plan
+        self._plan = None                   # the ScatterPlan owning indptr/indices, when there is one
 
     @property
     def nnz(self):
@@ -57,8 +58,13 @@ class DeviceCSR:
 
     __matmul__ = matvec
 
+    def _like(self, data):
+        out = DeviceCSR(self.shape, self.indptr_d, self.indices_d, data, self._host_pattern)
+        out._plan = self._plan
+        return out
+
     def scaled(self, alpha):
-        return DeviceCSR(self.shape, self.indptr_d, self.indices_d, self.data_d * alpha, self._host_pattern)
+        return self._like(self.data_d * alpha)
 
     def add_subpattern(self, other, alpha=1.0):
         """self + alpha*other where other's pattern is a subset of self's; returns a new DeviceCSR."""
@@ -66,7 +72,7 @@ class DeviceCSR:
         _lib.check(_lib.lib().fes_csr_add_subpattern(
             self.shape[0], _lib.ptr(self.indptr_d), _lib.ptr(self.indices_d), _lib.ptr(out),
             _lib.ptr(other.indptr_d), _lib.ptr(other.indices_d), _lib.ptr(other.data_d), float(alpha), _lib.stream()))
-        return DeviceCSR(self.shape, self.indptr_d, self.indices_d, out, self._host_pattern)
+        return self._like(out)
 
     @classmethod
     def from_scipy(cls, A, device):

@@ -16,6 +16,7 @@
 #include <cooperative_groups.h>
 
 #include "gridsum.cuh"
+#include "plan.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -37,6 +38,10 @@ struct fes_solver {
   fes::DevBuf<double> dinv, r, p, q, partials, hb, hx;
   fes::DevBuf<PcgState> state;
   int lanes = 8, grid = 0, block = 0;
+  int block_c = 0;  // 0 = scalar CSR rows; 2 / 3 = node-block rows
+  int64_t n_nodes = 0;
+  const int32_t* node_ptr = nullptr;
+  const int32_t* node_adj = nullptr;
 };
 
 namespace fes {
@@ -61,6 +66,11 @@ struct PcgArgs {
   double rtol;
   long long maxiter;
   int warm;
+  // node-block mode (operators assembled from a plan): row c*v+i holds, for each neighbour node
+  // w = node_adj[node_ptr[v]+s], the c values at c*c*node_ptr[v] + i*c*deg + c*s .. +c-1
+  int64_t n_nodes;
+  const int32_t* node_ptr;
+  const int32_t* node_adj;
 };
 
 __device__ __forceinline__ bool is_free(const uint8_t* mask, int64_t i) { return mask == nullptr || mask[i] != 0; }
@@ -84,27 +94,127 @@ __device__ __forceinline__ double row_dot(const PcgArgs& A, bool active, int64_t
   return s;
 }
 
-template <int G>
+
+// Node-block row product: G lanes share node v and stride over its neighbour blocks; one column
+// index and one C-wide gather of `vec` serve C*C matrix values.  All lanes of the warp call this
+// together.  out[i] is the full row sum for dof C*v+i (valid in every lane of the group).
+template <int G, int C, bool MASKED_X>
+__device__ __forceinline__ void node_row_dot(const PcgArgs& A, bool active, int64_t v, int lane, const double* vec,
+                                             double (&out)[C]) {
+#pragma unroll
+  for (int i = 0; i < C; ++i) out[i] = 0.0;
+  if (active) {
+    const int32_t np0 = __ldg(A.node_ptr + v), deg = __ldg(A.node_ptr + v + 1) - np0;
+    const double* base = A.data + (int64_t)C * C * np0;
+    for (int32_t s = lane; s < deg; s += G) {
+      const int64_t w = __ldg(A.node_adj + np0 + s);
+      double pw[C];
+      if constexpr (C == 2) {
+        const double2 t = *reinterpret_cast<const double2*>(vec + 2 * w);
+        pw[0] = t.x; pw[1] = t.y;
+      } else {
+#pragma unroll
+        for (int j = 0; j < C; ++j) pw[j] = vec[C * w + j];
+      }
+      if (MASKED_X) {
+#pragma unroll
+        for (int j = 0; j < C; ++j) pw[j] = is_free(A.mask, C * w + j) ? pw[j] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < C; ++i) {
+        const double* row = base + (int64_t)i * C * deg + C * s;
+        if constexpr (C == 2) {
+          const double2 a = __ldg(reinterpret_cast<const double2*>(row));
+          out[i] = fma(a.x, pw[0], fma(a.y, pw[1], out[i]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < C; ++j) out[i] = fma(__ldg(row + j), pw[j], out[i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < C; ++i)
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) out[i] += __shfl_xor_sync(0xffffffffu, out[i], o);
+}
+
+// One sparse product y = A vec restricted to the free rows, with the optional dot partial
+// sum_i vec2[i] * y[i].  Rows are walked in warp-convergent strides; UNROLL independent rows per
+// group are in flight together.
+template <int G, int C, bool MASKED_X, bool RESIDUAL>
+__device__ __forceinline__ double sparse_product(const PcgArgs& A, int64_t tid, int64_t nth, const double* vec,
+                                                 double* y) {
+  constexpr int GPW = 32 / G, UNROLL = 2;
+  const int64_t ngrp = nth / G;
+  const int lane = (int)(tid % G), sub = (int)((tid / G) % GPW);
+  const int64_t rbase0 = tid / G - sub;
+  double partial = 0.0;
+  if constexpr (C == 0) {
+    for (int64_t rbase = rbase0; rbase < A.n; rbase += ngrp * UNROLL) {
+      double acc[UNROLL];
+      bool act[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int64_t row = rbase + u * ngrp + sub;
+        act[u] = row < A.n && is_free(A.mask, row);
+        acc[u] = row_dot<G, MASKED_X>(A, act[u], row, lane, vec);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int64_t row = rbase + u * ngrp + sub;
+        if (act[u] && lane == 0) {
+          if (RESIDUAL) y[row] = A.b[row] - acc[u];
+          else { y[row] = acc[u]; partial += vec[row] * acc[u]; }
+        }
+      }
+    }
+  } else {
+    constexpr int CC = C == 0 ? 1 : C;
+    for (int64_t vbase = rbase0; vbase < A.n_nodes; vbase += ngrp * UNROLL) {
+      double acc[UNROLL][CC];
+      bool act[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int64_t v = vbase + u * ngrp + sub;
+        bool any = false;
+        if (v < A.n_nodes) {
+#pragma unroll
+          for (int i = 0; i < CC; ++i) any = any || is_free(A.mask, CC * v + i);
+        }
+        act[u] = any;
+        node_row_dot<G, CC, MASKED_X>(A, any, v, lane, vec, acc[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int64_t v = vbase + u * ngrp + sub;
+        if (act[u] && lane < CC) {
+          // lane i of the group finishes dof C*v+i (every lane holds all C sums after the shuffles)
+          double mine = acc[u][0];
+#pragma unroll
+          for (int i = 1; i < CC; ++i) mine = (lane == i) ? acc[u][i] : mine;
+          const int64_t row = CC * v + lane;
+          if (is_free(A.mask, row)) {
+            if (RESIDUAL) y[row] = A.b[row] - mine;
+            else { y[row] = mine; partial += vec[row] * mine; }
+          }
+        }
+      }
+    }
+  }
+  return partial;
+}
+
+template <int G, int C>
 __global__ void __launch_bounds__(kPcgBlock) k_pcg(PcgArgs A) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sm[33];
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
-  // G lanes share a row; the 32/G row groups of a warp walk rows rbase+sub together so the
-  // warp-wide shuffles stay convergent
-  constexpr int GPW = 32 / G;
-  const int64_t ngrp = nth / G;
-  const int lane = (int)(tid % G), sub = (int)((tid / G) % GPW);
-  const int64_t rbase0 = tid / G - sub;
 
   // ---- r0 = b - A x0 on the free rows (x0 = 0 unless warm), p = 0 everywhere
   if (A.warm) {
-    for (int64_t rbase = rbase0; rbase < A.n; rbase += ngrp) {
-      const int64_t row = rbase + sub;
-      const bool active = row < A.n && is_free(A.mask, row);
-      const double ax = row_dot<G, true>(A, active, row, lane, A.x);
-      if (active && lane == 0) A.r[row] = A.b[row] - ax;
-    }
+    sparse_product<G, C, true, true>(A, tid, nth, A.x, A.r);
     grid.sync();
   }
   double v3[3] = {0.0, 0.0, 0.0};  // b.b, r.r, r.z
@@ -137,16 +247,7 @@ __global__ void __launch_bounds__(kPcgBlock) k_pcg(PcgArgs A) {
         if (is_free(A.mask, i)) A.p[i] = A.dinv[i] * A.r[i] + beta * A.p[i];
       grid.sync();
 
-      double v1[1] = {0.0};
-      for (int64_t rbase = rbase0; rbase < A.n; rbase += ngrp) {
-        const int64_t row = rbase + sub;
-        const bool active = row < A.n && is_free(A.mask, row);
-        const double qi = row_dot<G, false>(A, active, row, lane, A.p);
-        if (active && lane == 0) {
-          A.q[row] = qi;
-          v1[0] += A.p[row] * qi;
-        }
-      }
+      double v1[1] = {sparse_product<G, C, false, false>(A, tid, nth, A.p, A.q)};
       grid_sum<1>(grid, v1, A.partials, 3, sm);
       const double pq = v1[0];
       if (!(pq > 0.0)) { status = 2; break; }
@@ -235,21 +336,20 @@ int pick_lanes(int64_t n, int64_t nnz) {
   return 32;
 }
 
-template <int G>
+template <int G, int C>
 int launch_pcg(fes_solver* s, PcgArgs& args, cudaStream_t st) {
   if (s->grid == 0) {
     int dev = 0, sms = 0, per_sm = 0;
     FES_CUDA(cudaGetDevice(&dev));
     FES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    FES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<G>, kPcgBlock, 0));
+    FES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<G, C>, kPcgBlock, 0));
     if (per_sm < 1) return set_error(FES_ERR_CUDA, "PCG kernel does not fit on an SM");
-    if (per_sm > 2) per_sm = 2;
     s->grid = sms * per_sm;
     if (s->grid > kMaxGrid) s->grid = kMaxGrid;
     s->block = kPcgBlock;
   }
   void* params[] = {&args};
-  FES_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<G>, dim3(s->grid), dim3(s->block), params, 0, st));
+  FES_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<G, C>, dim3(s->grid), dim3(s->block), params, 0, st));
   count_launch();
   return FES_OK;
 }
@@ -361,6 +461,20 @@ extern "C" int fes_solver_create_host(int64_t n, const int64_t* h_indptr, const 
 
 extern "C" void fes_solver_destroy(fes_solver* s) { delete s; }
 
+extern "C" int fes_solver_use_plan(fes_solver* s, const fes_plan* plan) {
+  if (!s || !plan) return set_error(FES_ERR_VALUE, "fes_solver_use_plan: NULL argument");
+  if (plan->n_dofs != s->n || s->indptr != plan->indptr.p)
+    return set_error(FES_ERR_VALUE, "fes_solver_use_plan: the operator was not assembled from this plan");
+  if (plan->c == 2 || plan->c == 3) {
+    s->block_c = plan->c;
+    s->n_nodes = plan->n_nodes;
+    s->node_ptr = plan->node_ptr.p;
+    s->node_adj = plan->node_adj.p;
+    s->grid = 0;  // occupancy of the block-mode kernel differs
+  }
+  return FES_OK;
+}
+
 extern "C" int fes_solver_solve(fes_solver* s, const double* d_b, double* d_x, double rtol, int64_t maxiter,
                                 int warm_start, int64_t* iters_out, double* relres_out, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
@@ -370,10 +484,17 @@ extern "C" int fes_solver_solve(fes_solver* s, const double* d_b, double* d_x, d
   if (s->n == 0 || s->n_free == 0) return FES_OK;
   if (maxiter <= 0) maxiter = 10 * s->n_free;
   PcgArgs a{s->n, s->indptr, s->indices, s->data, s->mask, s->dinv.p, d_b, d_x, s->r.p, s->p.p, s->q.p,
-            s->partials.p, s->state.p, rtol, (long long)maxiter, warm_start ? 1 : 0};
-#define FES_PCG(G) FES_TRY(launch_pcg<G>(s, a, st))
-  FES_BY_LANES(s->lanes, FES_PCG)
+            s->partials.p, s->state.p, rtol, (long long)maxiter, warm_start ? 1 : 0, s->n_nodes, s->node_ptr,
+            s->node_adj};
+  if (s->block_c == 2) {
+    FES_TRY((launch_pcg<8, 2>(s, a, st)));
+  } else if (s->block_c == 3) {
+    FES_TRY((launch_pcg<16, 3>(s, a, st)));
+  } else {
+#define FES_PCG(G) FES_TRY((launch_pcg<G, 0>(s, a, st)))
+    FES_BY_LANES(s->lanes, FES_PCG)
 #undef FES_PCG
+  }
   PcgState h;
   FES_CUDA(cudaMemcpyAsync(&h, s->state.p, sizeof(h), cudaMemcpyDeviceToHost, st));
   FES_CUDA(cudaStreamSynchronize(st));

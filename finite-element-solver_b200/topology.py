@@ -150,6 +150,7 @@ class TopologyOptimizer:
         plan = self.space.plan()
         self._values = torch.zeros(plan.nnz, dtype=torch.float64, device=dev)
         self._A = DeviceCSR((self.space.n_dofs,) * 2, plan.indptr_d, plan.indices_d, self._values, plan.host_pattern)
+        self._A._plan = plan
         self._mask = torch.zeros(self.space.n_dofs, dtype=torch.uint8, device=dev)
         self._mask[torch.as_tensor(free, device=dev)] = 1
         self._x_fixed = torch.zeros(self.space.n_dofs, dtype=torch.float64, device=dev)

@@ -148,6 +148,9 @@ int fes_solver_create(int64_t n, const int32_t* d_indptr, const int32_t* d_indic
 int fes_solver_create_host(int64_t n, const int64_t* h_indptr, const int64_t* h_indices,
                            const double* h_data, fes_solver** out);
 void fes_solver_destroy(fes_solver* s);
+/* The operator's indptr/indices/data are the plan's CSR (values from fes_assemble): let the
+ * SpMV walk node blocks (one column index and one c-wide gather per c x c block). */
+int fes_solver_use_plan(fes_solver* s, const fes_plan* plan);
 /* re-read d_data (same pattern) and refresh the Jacobi diagonal: a new SIMP iteration */
 int fes_solver_refresh(fes_solver* s, void* stream);
 /* Solve A_ff x_f = b_f.  d_b, d_x are full length n; entries at fixed dofs of d_x are left
