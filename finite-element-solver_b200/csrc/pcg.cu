@@ -6,14 +6,23 @@
 // residual, and the failure semantics mirror scipy.sparse.linalg.cg(A, b, rtol, atol=0,
 // maxiter, M=diag(A)^-1).
 //
-// Device design: the whole solve is one cooperative launch (grid = resident CTAs on all SMs).
-// Each iteration is three phases separated by grid barriers: p = z + beta p | q = A p with the
-// p.q partials | x += alpha p, r -= alpha q with the r.z and r.r partials.  alpha, beta and the
-// convergence test are computed redundantly by every CTA from per-CTA partial sums reduced in a
-// fixed order (warp shuffle tree -> shared memory -> global partials -> same tree again), so
-// no scalar ever visits the host and results are bit-reproducible run to run.  A 0/1 free mask
-// restricts the iteration to the free-free block without forming A[free][:, free].
-#include <cooperative_groups.h>
+// Device design
+//   * The whole solve is one cooperative launch (grid = resident CTAs on all SMs).  Each
+//     iteration is three phases separated by grid barriers: p = z + beta p | q = A p with the p.q
+//     partials | x += alpha p, r -= alpha q with the r.z and r.r partials.  alpha, beta and the
+//     convergence test are computed redundantly by every CTA from per-CTA partial sums reduced
+//     in a fixed order (warp shuffle tree -> shared memory -> global partials -> same tree), so no
+//     scalar visits the host and results are bit-reproducible run to run.
+//   * The operator is re-laid out once per refresh into SELL-32-sigma over BLOCK rows: a node's
+//     c dofs form one block row whose entries are c x c blocks sharing one column index.  A thread
+//     owns one block row; the 32 lanes of a warp read one slice column by column, so every load
+//     is lane-contiguous and all of a row's loads are independent (no shuffles, no dependent
+//     index chain beyond column -> gather).  Rows are sorted by length inside windows of 256 so
+//     slices carry almost no padding.
+//   * A 0/1 free mask restricts the iteration to the free-free block without forming
+//     A[free][:, free]: fixed rows carry dinv = r = p = q = 0, so the vector phases need no mask.
+#include <algorithm>
+#include <vector>
 
 #include "gridsum.cuh"
 #include "plan.cuh"
@@ -38,22 +47,25 @@ struct fes_solver {
   fes::DevBuf<double> dinv, r, p, q, partials, hb, hx;
   fes::DevBuf<PcgState> state;
   int lanes = 8, grid = 0, block = 0;
-  int block_c = 0;  // 0 = scalar CSR rows; 2 / 3 = node-block rows
-  int64_t n_nodes = 0;
-  const int32_t* node_ptr = nullptr;
-  const int32_t* node_adj = nullptr;
+  // block-row source layout: c = 1 means plain CSR rows (row_ptr = indptr, cols = indices)
+  int c = 1;
+  int64_t n_brow = 0;
+  const int32_t* row_ptr = nullptr;
+  const int32_t* row_col = nullptr;
+  // SELL-32-sigma copy of the operator
+  int64_t n_slices = 0, sell_entries = 0;
+  fes::DevBuf<int32_t> sell_row, sell_slice_ptr, sell_cols;
+  fes::DevBuf<double> sell_vals;
 };
 
 namespace fes {
 namespace {
 
 constexpr int kPcgBlock = 512;
+constexpr int kSigma = 256;  // rows sorted by length inside windows of this many block rows
 
 struct PcgArgs {
   int64_t n;
-  const int32_t* indptr;
-  const int32_t* indices;
-  const double* data;
   const uint8_t* mask;
   const double* dinv;
   const double* b;
@@ -66,138 +78,64 @@ struct PcgArgs {
   double rtol;
   long long maxiter;
   int warm;
-  // node-block mode (operators assembled from a plan): row c*v+i holds, for each neighbour node
-  // w = node_adj[node_ptr[v]+s], the c values at c*c*node_ptr[v] + i*c*deg + c*s .. +c-1
-  int64_t n_nodes;
-  const int32_t* node_ptr;
-  const int32_t* node_adj;
+  int64_t n_slots;  // n_slices * 32
+  const int32_t* sell_row;
+  const int32_t* sell_slice_ptr;
+  const int32_t* sell_cols;
+  const double* sell_vals;
 };
 
 __device__ __forceinline__ bool is_free(const uint8_t* mask, int64_t i) { return mask == nullptr || mask[i] != 0; }
 
-// Row sum over G cooperating lanes.  Every lane of the warp must call this together (the shuffle
-// tree spans the warp), so inactive rows pass active = false instead of skipping the call.
-template <int G, bool MASKED_X>
-__device__ __forceinline__ double row_dot(const PcgArgs& A, bool active, int64_t row, int lane, const double* vec) {
-  double s = 0.0;
-  if (active) {
-    const int32_t k1 = __ldg(A.indptr + row + 1);
-    for (int32_t k = __ldg(A.indptr + row) + lane; k < k1; k += G) {
-      const int32_t j = __ldg(A.indices + k);
-      double xv = vec[j];
-      if (MASKED_X) xv = is_free(A.mask, j) ? xv : 0.0;
-      s += __ldg(A.data + k) * xv;
-    }
-  }
+// y = A vec on the free rows (0 on fixed rows); returns this thread's share of vec . y.
+// RESIDUAL writes b - A vec instead.  MASKED_X treats vec as zero on fixed dofs (warm start).
+template <int C, bool MASKED_X, bool RESIDUAL>
+__device__ __forceinline__ double sparse_product(const PcgArgs& A, int64_t tid, int64_t nth, const double* vec,
+                                                 double* y) {
+  double partial = 0.0;
+  for (int64_t slot = tid; slot < A.n_slots; slot += nth) {
+    const int lane = (int)(slot & 31);
+    const int64_t slice = slot >> 5;
+    const int32_t brow = __ldg(A.sell_row + slot);
+    const int32_t base = __ldg(A.sell_slice_ptr + slice);
+    const int32_t width = (__ldg(A.sell_slice_ptr + slice + 1) - base) >> 5;
+    uint8_t fr[C];
 #pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  return s;
-}
-
-
-// Node-block row product: G lanes share node v and stride over its neighbour blocks; one column
-// index and one C-wide gather of `vec` serve C*C matrix values.  All lanes of the warp call this
-// together.  out[i] is the full row sum for dof C*v+i (valid in every lane of the group).
-template <int G, int C, bool MASKED_X>
-__device__ __forceinline__ void node_row_dot(const PcgArgs& A, bool active, int64_t v, int lane, const double* vec,
-                                             double (&out)[C]) {
+    for (int i = 0; i < C; ++i) fr[i] = (brow >= 0 && is_free(A.mask, (int64_t)C * brow + i)) ? 1 : 0;
+    const int32_t* cp = A.sell_cols + base + lane;
+    const double* vp = A.sell_vals + (int64_t)base * (C * C) + lane;
+    double acc[C];
 #pragma unroll
-  for (int i = 0; i < C; ++i) out[i] = 0.0;
-  if (active) {
-    const int32_t np0 = __ldg(A.node_ptr + v), deg = __ldg(A.node_ptr + v + 1) - np0;
-    const double* base = A.data + (int64_t)C * C * np0;
-    for (int32_t s = lane; s < deg; s += G) {
-      const int64_t w = __ldg(A.node_adj + np0 + s);
+    for (int i = 0; i < C; ++i) acc[i] = 0.0;
+#pragma unroll 4
+    for (int32_t s = 0; s < width; ++s) {
+      const int32_t col = __ldg(cp + s * 32);
       double pw[C];
       if constexpr (C == 2) {
-        const double2 t = *reinterpret_cast<const double2*>(vec + 2 * w);
+        const double2 t = *reinterpret_cast<const double2*>(vec + 2 * (int64_t)col);
         pw[0] = t.x; pw[1] = t.y;
       } else {
 #pragma unroll
-        for (int j = 0; j < C; ++j) pw[j] = vec[C * w + j];
+        for (int j = 0; j < C; ++j) pw[j] = vec[(int64_t)C * col + j];
       }
       if (MASKED_X) {
 #pragma unroll
-        for (int j = 0; j < C; ++j) pw[j] = is_free(A.mask, C * w + j) ? pw[j] : 0.0;
+        for (int j = 0; j < C; ++j) pw[j] = is_free(A.mask, (int64_t)C * col + j) ? pw[j] : 0.0;
       }
+      const double* a = vp + (int64_t)s * (C * C * 32);
+#pragma unroll
+      for (int i = 0; i < C; ++i)
+#pragma unroll
+        for (int j = 0; j < C; ++j) acc[i] = fma(__ldg(a + (i * C + j) * 32), pw[j], acc[i]);
+    }
+    if (brow >= 0) {
 #pragma unroll
       for (int i = 0; i < C; ++i) {
-        const double* row = base + (int64_t)i * C * deg + C * s;
-        if constexpr (C == 2) {
-          const double2 a = __ldg(reinterpret_cast<const double2*>(row));
-          out[i] = fma(a.x, pw[0], fma(a.y, pw[1], out[i]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < C; ++j) out[i] = fma(__ldg(row + j), pw[j], out[i]);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < C; ++i)
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) out[i] += __shfl_xor_sync(0xffffffffu, out[i], o);
-}
-
-// One sparse product y = A vec restricted to the free rows, with the optional dot partial
-// sum_i vec2[i] * y[i].  Rows are walked in warp-convergent strides; UNROLL independent rows per
-// group are in flight together.
-template <int G, int C, bool MASKED_X, bool RESIDUAL>
-__device__ __forceinline__ double sparse_product(const PcgArgs& A, int64_t tid, int64_t nth, const double* vec,
-                                                 double* y) {
-  constexpr int GPW = 32 / G, UNROLL = 2;
-  const int64_t ngrp = nth / G;
-  const int lane = (int)(tid % G), sub = (int)((tid / G) % GPW);
-  const int64_t rbase0 = tid / G - sub;
-  double partial = 0.0;
-  if constexpr (C == 0) {
-    for (int64_t rbase = rbase0; rbase < A.n; rbase += ngrp * UNROLL) {
-      double acc[UNROLL];
-      bool act[UNROLL];
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int64_t row = rbase + u * ngrp + sub;
-        act[u] = row < A.n && is_free(A.mask, row);
-        acc[u] = row_dot<G, MASKED_X>(A, act[u], row, lane, vec);
-      }
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int64_t row = rbase + u * ngrp + sub;
-        if (act[u] && lane == 0) {
-          if (RESIDUAL) y[row] = A.b[row] - acc[u];
-          else { y[row] = acc[u]; partial += vec[row] * acc[u]; }
-        }
-      }
-    }
-  } else {
-    constexpr int CC = C == 0 ? 1 : C;
-    for (int64_t vbase = rbase0; vbase < A.n_nodes; vbase += ngrp * UNROLL) {
-      double acc[UNROLL][CC];
-      bool act[UNROLL];
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int64_t v = vbase + u * ngrp + sub;
-        bool any = false;
-        if (v < A.n_nodes) {
-#pragma unroll
-          for (int i = 0; i < CC; ++i) any = any || is_free(A.mask, CC * v + i);
-        }
-        act[u] = any;
-        node_row_dot<G, CC, MASKED_X>(A, any, v, lane, vec, acc[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int64_t v = vbase + u * ngrp + sub;
-        if (act[u] && lane < CC) {
-          // lane i of the group finishes dof C*v+i (every lane holds all C sums after the shuffles)
-          double mine = acc[u][0];
-#pragma unroll
-          for (int i = 1; i < CC; ++i) mine = (lane == i) ? acc[u][i] : mine;
-          const int64_t row = CC * v + lane;
-          if (is_free(A.mask, row)) {
-            if (RESIDUAL) y[row] = A.b[row] - mine;
-            else { y[row] = mine; partial += vec[row] * mine; }
-          }
+        const int64_t row = (int64_t)C * brow + i;
+        if (RESIDUAL) y[row] = fr[i] ? A.b[row] - acc[i] : 0.0;
+        else {
+          y[row] = fr[i] ? acc[i] : 0.0;
+          partial += fr[i] ? vec[row] * acc[i] : 0.0;
         }
       }
     }
@@ -205,7 +143,7 @@ __device__ __forceinline__ double sparse_product(const PcgArgs& A, int64_t tid, 
   return partial;
 }
 
-template <int G, int C>
+template <int C>
 __global__ void __launch_bounds__(kPcgBlock) k_pcg(PcgArgs A) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sm[33];
@@ -214,17 +152,20 @@ __global__ void __launch_bounds__(kPcgBlock) k_pcg(PcgArgs A) {
 
   // ---- r0 = b - A x0 on the free rows (x0 = 0 unless warm), p = 0 everywhere
   if (A.warm) {
-    sparse_product<G, C, true, true>(A, tid, nth, A.x, A.r);
+    sparse_product<C, true, true>(A, tid, nth, A.x, A.r);
     grid.sync();
   }
+  // Fixed rows carry dinv = 0 and r = p = q = 0 from here on, so the vector phases below need no
+  // mask: every update leaves them at zero and x untouched.
   double v3[3] = {0.0, 0.0, 0.0};  // b.b, r.r, r.z
   for (int64_t i = tid; i < A.n; i += nth) {
-    A.p[i] = 0.0;
-    if (!is_free(A.mask, i)) continue;
-    const double bi = A.b[i];
+    const bool fr = is_free(A.mask, i);
+    const double bi = fr ? A.b[i] : 0.0;
     double ri = bi;
-    if (A.warm) ri = A.r[i];
-    else { A.r[i] = bi; A.x[i] = 0.0; }
+    if (A.warm) ri = A.r[i];  // the residual product already wrote 0 on fixed rows
+    else { A.r[i] = bi; if (fr) A.x[i] = 0.0; }
+    A.p[i] = 0.0;
+    A.q[i] = 0.0;
     v3[0] += bi * bi;
     v3[1] += ri * ri;
     v3[2] += ri * ri * A.dinv[i];
@@ -243,11 +184,10 @@ __global__ void __launch_bounds__(kPcgBlock) k_pcg(PcgArgs A) {
       if (sqrt(rr) < A.rtol * sqrt(bb)) break;
       if (it >= A.maxiter) { status = 1; break; }
       const double beta = (it == 0) ? 0.0 : rho / rho_prev;
-      for (int64_t i = tid; i < A.n; i += nth)
-        if (is_free(A.mask, i)) A.p[i] = A.dinv[i] * A.r[i] + beta * A.p[i];
+      for (int64_t i = tid; i < A.n; i += nth) A.p[i] = fma(beta, A.p[i], A.dinv[i] * A.r[i]);
       grid.sync();
 
-      double v1[1] = {sparse_product<G, C, false, false>(A, tid, nth, A.p, A.q)};
+      double v1[1] = {sparse_product<C, false, false>(A, tid, nth, A.p, A.q)};
       grid_sum<1>(grid, v1, A.partials, 3, sm);
       const double pq = v1[0];
       if (!(pq > 0.0)) { status = 2; break; }
@@ -255,8 +195,8 @@ __global__ void __launch_bounds__(kPcgBlock) k_pcg(PcgArgs A) {
 
       double v2[2] = {0.0, 0.0};
       for (int64_t i = tid; i < A.n; i += nth) {
-        if (!is_free(A.mask, i)) continue;
-        A.x[i] += alpha * A.p[i];
+        const double pi = A.p[i];
+        if (pi != 0.0) A.x[i] = fma(alpha, pi, A.x[i]);  // fixed rows (p = 0) keep their prescribed value
         const double ri = A.r[i] - alpha * A.q[i];
         A.r[i] = ri;
         v2[0] += ri * ri;
@@ -274,6 +214,33 @@ __global__ void __launch_bounds__(kPcgBlock) k_pcg(PcgArgs A) {
     A.state->status = status;
     A.state->bnorm = sqrt(bb);
     A.state->relres = bb > 0.0 ? sqrt(rr) / sqrt(bb) : 0.0;
+  }
+}
+
+// one thread per SELL row slot: column index and the c x c values of block (brow, s), zero padding
+template <int C>
+__global__ void k_sell_fill(int64_t n_slots, const int32_t* __restrict__ sell_row,
+                            const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ row_ptr,
+                            const int32_t* __restrict__ row_col, const double* __restrict__ data,
+                            int32_t* __restrict__ cols, double* __restrict__ vals, int fill_cols) {
+  const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_slots) return;
+  const int lane = (int)(slot & 31);
+  const int64_t slice = slot >> 5;
+  const int32_t base = slice_ptr[slice], width = (slice_ptr[slice + 1] - base) >> 5;
+  const int32_t brow = sell_row[slot];
+  int32_t p0 = 0, deg = 0;
+  if (brow >= 0) { p0 = row_ptr[brow]; deg = row_ptr[brow + 1] - p0; }
+  for (int32_t s = 0; s < width; ++s) {
+    const int64_t e = (int64_t)base + (int64_t)s * 32 + lane;
+    const bool live = s < deg;
+    if (fill_cols) cols[e] = live ? row_col[p0 + s] : (brow >= 0 ? brow : 0);
+    double* v = vals + ((int64_t)base + (int64_t)s * 32) * (C * C) + lane;
+#pragma unroll
+    for (int i = 0; i < C; ++i)
+#pragma unroll
+      for (int j = 0; j < C; ++j)
+        v[(i * C + j) * 32] = live ? data[(int64_t)C * C * p0 + ((int64_t)i * deg + s) * C + j] : 0.0;
   }
 }
 
@@ -336,21 +303,81 @@ int pick_lanes(int64_t n, int64_t nnz) {
   return 32;
 }
 
-template <int G, int C>
+template <int C>
 int launch_pcg(fes_solver* s, PcgArgs& args, cudaStream_t st) {
   if (s->grid == 0) {
     int dev = 0, sms = 0, per_sm = 0;
     FES_CUDA(cudaGetDevice(&dev));
     FES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    FES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<G, C>, kPcgBlock, 0));
+    FES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<C>, kPcgBlock, 0));
     if (per_sm < 1) return set_error(FES_ERR_CUDA, "PCG kernel does not fit on an SM");
     s->grid = sms * per_sm;
     if (s->grid > kMaxGrid) s->grid = kMaxGrid;
     s->block = kPcgBlock;
   }
   void* params[] = {&args};
-  FES_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<G, C>, dim3(s->grid), dim3(s->block), params, 0, st));
+  FES_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<C>, dim3(s->grid), dim3(s->block), params, 0, st));
   count_launch();
+  return FES_OK;
+}
+
+// SELL-32-sigma structure over block rows: the row order and slice offsets are computed on the
+// host from the row lengths (O(rows), once per operator); columns and values are filled on the
+// device.
+int build_sell(fes_solver* s, cudaStream_t st) {
+  const int64_t nb = s->n_brow;
+  std::vector<int32_t> ptr(nb + 1);
+  FES_CUDA(cudaMemcpyAsync(ptr.data(), s->row_ptr, (nb + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  FES_CUDA(cudaStreamSynchronize(st));
+  const int64_t n_slices = (nb + 31) / 32;
+  std::vector<int32_t> row(n_slices * 32, -1), slice_ptr(n_slices + 1, 0);
+  std::vector<int32_t> order;
+  for (int64_t w0 = 0; w0 < nb; w0 += kSigma) {
+    const int64_t w1 = std::min<int64_t>(nb, w0 + kSigma);
+    order.resize(w1 - w0);
+    for (int64_t i = w0; i < w1; ++i) order[i - w0] = (int32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+      return ptr[a + 1] - ptr[a] > ptr[b + 1] - ptr[b];
+    });
+    for (int64_t i = w0; i < w1; ++i) row[i] = order[i - w0];
+  }
+  int64_t total = 0;
+  for (int64_t sl = 0; sl < n_slices; ++sl) {
+    int32_t width = 0;
+    for (int l = 0; l < 32; ++l) {
+      const int32_t r = row[sl * 32 + l];
+      if (r >= 0) width = std::max(width, ptr[r + 1] - ptr[r]);
+    }
+    slice_ptr[sl] = (int32_t)total;
+    total += (int64_t)width * 32;
+    if (total >= ((int64_t)1 << 31)) return set_error(FES_ERR_VALUE, "operator too large for int32 SELL offsets");
+  }
+  slice_ptr[n_slices] = (int32_t)total;
+  s->n_slices = n_slices;
+  s->sell_entries = total;
+  FES_CUDA(s->sell_row.alloc(row.size()));
+  FES_CUDA(s->sell_slice_ptr.alloc(slice_ptr.size()));
+  FES_CUDA(s->sell_cols.alloc(total));
+  FES_CUDA(s->sell_vals.alloc((size_t)total * s->c * s->c));
+  FES_CUDA(cudaMemcpyAsync(s->sell_row.p, row.data(), row.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  FES_CUDA(cudaMemcpyAsync(s->sell_slice_ptr.p, slice_ptr.data(), slice_ptr.size() * sizeof(int32_t),
+                           cudaMemcpyHostToDevice, st));
+  FES_CUDA(cudaStreamSynchronize(st));
+  return FES_OK;
+}
+
+int fill_sell(fes_solver* s, int fill_cols, cudaStream_t st) {
+  const int64_t n_slots = s->n_slices * 32;
+  if (n_slots == 0) return FES_OK;
+  const int g = grid_for(n_slots, 256);
+#define FES_FILL(C_)                                                                                         \
+  k_sell_fill<C_><<<g, 256, 0, st>>>(n_slots, s->sell_row.p, s->sell_slice_ptr.p, s->row_ptr, s->row_col, s->data, \
+                                     s->sell_cols.p, s->sell_vals.p, fill_cols)
+  if (s->c == 1) FES_FILL(1);
+  else if (s->c == 2) FES_FILL(2);
+  else FES_FILL(3);
+#undef FES_FILL
+  FES_LAUNCH_CHECK();
   return FES_OK;
 }
 
@@ -374,7 +401,18 @@ int init_solver(fes_solver* s, cudaStream_t st) {
     FES_CUDA(cudaStreamSynchronize(st));
     s->n_free = (int64_t)h;
   }
-  return fes_solver_refresh(s, st);
+  s->c = 1; s->n_brow = s->n; s->row_ptr = s->indptr; s->row_col = s->indices;
+  return FES_OK;
+}
+
+// (re)build the SELL copy lazily: structure on first use, values whenever the operator changed
+int ensure_sell(fes_solver* s, cudaStream_t st) {
+  if (s->n == 0) return FES_OK;
+  if (s->sell_row.p == nullptr) {
+    FES_TRY(build_sell(s, st));
+    FES_TRY(fill_sell(s, 1, st));
+  }
+  return FES_OK;
 }
 
 }  // namespace
@@ -395,6 +433,7 @@ extern "C" int fes_solver_refresh(fes_solver* s, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (!s) return set_error(FES_ERR_VALUE, "fes_solver_refresh: NULL solver");
   if (s->n == 0) return FES_OK;
+  if (s->sell_row.p != nullptr) FES_TRY(fill_sell(s, 0, st));  // same structure, new values
   DevBuf<int> bad;
   FES_CUDA(bad.alloc(1));
   FES_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
@@ -423,7 +462,8 @@ extern "C" int fes_solver_create(int64_t n, const int32_t* d_indptr, const int32
     return set_error(FES_ERR_CUDA, "fes_solver_create: cannot read indptr");
   }
   s->nnz = last;
-  const int rc = init_solver(s, (cudaStream_t)stream);
+  int rc = init_solver(s, (cudaStream_t)stream);
+  if (rc == FES_OK) rc = fes_solver_refresh(s, stream);
   if (rc != FES_OK) { delete s; return rc; }
   *out = s;
   return FES_OK;
@@ -443,17 +483,16 @@ extern "C" int fes_solver_create_host(int64_t n, const int64_t* h_indptr, const 
   FES_CUDA(s->own_indices.alloc(nnz));
   FES_CUDA(s->own_data.alloc(nnz));
   {  // narrow the reference's int64 index arrays on the host, then one copy each
-    int32_t* tmp = new int32_t[(size_t)(nnz > n + 1 ? nnz : n + 1)];
+    std::vector<int32_t> tmp((size_t)std::max<int64_t>(nnz, n + 1));
     for (int64_t i = 0; i <= n; ++i) tmp[i] = (int32_t)h_indptr[i];
-    cudaError_t e = cudaMemcpy(s->own_indptr.p, tmp, (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice);
+    FES_CUDA(cudaMemcpy(s->own_indptr.p, tmp.data(), (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
     for (int64_t i = 0; i < nnz; ++i) tmp[i] = (int32_t)h_indices[i];
-    if (e == cudaSuccess && nnz) e = cudaMemcpy(s->own_indices.p, tmp, nnz * sizeof(int32_t), cudaMemcpyHostToDevice);
-    delete[] tmp;
-    FES_CUDA(e);
+    if (nnz) FES_CUDA(cudaMemcpy(s->own_indices.p, tmp.data(), nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
   if (nnz) FES_CUDA(cudaMemcpy(s->own_data.p, h_data, nnz * sizeof(double), cudaMemcpyHostToDevice));
   s->indptr = s->own_indptr.p; s->indices = s->own_indices.p; s->data = s->own_data.p; s->mask = nullptr;
   FES_TRY(init_solver(s, nullptr));
+  FES_TRY(fes_solver_refresh(s, nullptr));
   guard.p = nullptr;
   *out = s;
   return FES_OK;
@@ -465,12 +504,12 @@ extern "C" int fes_solver_use_plan(fes_solver* s, const fes_plan* plan) {
   if (!s || !plan) return set_error(FES_ERR_VALUE, "fes_solver_use_plan: NULL argument");
   if (plan->n_dofs != s->n || s->indptr != plan->indptr.p)
     return set_error(FES_ERR_VALUE, "fes_solver_use_plan: the operator was not assembled from this plan");
-  if (plan->c == 2 || plan->c == 3) {
-    s->block_c = plan->c;
-    s->n_nodes = plan->n_nodes;
-    s->node_ptr = plan->node_ptr.p;
-    s->node_adj = plan->node_adj.p;
-    s->grid = 0;  // occupancy of the block-mode kernel differs
+  if ((plan->c == 2 || plan->c == 3) && s->sell_row.p == nullptr) {
+    s->c = plan->c;
+    s->n_brow = plan->n_nodes;
+    s->row_ptr = plan->node_ptr.p;
+    s->row_col = plan->node_adj.p;
+    s->grid = 0;  // occupancy of the block-row kernel differs
   }
   return FES_OK;
 }
@@ -483,18 +522,13 @@ extern "C" int fes_solver_solve(fes_solver* s, const double* d_b, double* d_x, d
   if (relres_out) *relres_out = 0.0;
   if (s->n == 0 || s->n_free == 0) return FES_OK;
   if (maxiter <= 0) maxiter = 10 * s->n_free;
-  PcgArgs a{s->n, s->indptr, s->indices, s->data, s->mask, s->dinv.p, d_b, d_x, s->r.p, s->p.p, s->q.p,
-            s->partials.p, s->state.p, rtol, (long long)maxiter, warm_start ? 1 : 0, s->n_nodes, s->node_ptr,
-            s->node_adj};
-  if (s->block_c == 2) {
-    FES_TRY((launch_pcg<8, 2>(s, a, st)));
-  } else if (s->block_c == 3) {
-    FES_TRY((launch_pcg<16, 3>(s, a, st)));
-  } else {
-#define FES_PCG(G) FES_TRY((launch_pcg<G, 0>(s, a, st)))
-    FES_BY_LANES(s->lanes, FES_PCG)
-#undef FES_PCG
-  }
+  FES_TRY(ensure_sell(s, st));
+  PcgArgs a{s->n, s->mask, s->dinv.p, d_b, d_x, s->r.p, s->p.p, s->q.p, s->partials.p, s->state.p, rtol,
+            (long long)maxiter, warm_start ? 1 : 0, s->n_slices * 32, s->sell_row.p, s->sell_slice_ptr.p,
+            s->sell_cols.p, s->sell_vals.p};
+  if (s->c == 2) FES_TRY(launch_pcg<2>(s, a, st));
+  else if (s->c == 3) FES_TRY(launch_pcg<3>(s, a, st));
+  else FES_TRY(launch_pcg<1>(s, a, st));
   PcgState h;
   FES_CUDA(cudaMemcpyAsync(&h, s->state.p, sizeof(h), cudaMemcpyDeviceToHost, st));
   FES_CUDA(cudaStreamSynchronize(st));

@@ -34,4 +34,21 @@ if what in ('all', 'tet'):
     for _ in range(4):
         A = V.assemble_device(form)
     torch.cuda.synchronize()
+if what in ('simp',):
+    from fes_b200.regions import in_box, intersect
+    w, h = 3.0, 1.0
+    m4 = F.create_rect_mesh([[0, 0], [w, h]], (1201, 401))
+    bc = F.BoundaryConditions()
+    bottom, top = on_plane(1, 0.0), on_plane(1, h)
+    bc.add(F.BCType.DIRICHLET, intersect(bottom, in_box([None, None], [0.04 * w, None])), [0, 0])
+    bc.add(F.BCType.DIRICHLET, intersect(bottom, in_box([0.96 * w, None], [None, None])), [None, 0])
+    bc.add(F.BCType.NEUMANN, intersect(top, in_box([0.4 * w, None], [0.6 * w, None])), [0, -0.5])
+    topo = F.TopologyOptimizer(m4, F.LinearElastic(200.0, 0.4), bc, iters=1, volume_frac=0.5,
+                               smoothing_radius=0.00625, penalty=3.0, history=None,
+                               backend=F.JacobiPCGBackend(rtol=1e-10, maxiter=int(sys.argv[2]) if len(sys.argv) > 2 else 200))
+    try:
+        topo.step()
+    except RuntimeError as e:
+        print('expected:', str(e)[:60])
+    torch.cuda.synchronize()
 print('done')
