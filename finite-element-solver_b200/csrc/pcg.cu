@@ -144,9 +144,9 @@ __device__ __forceinline__ double sparse_product(const PcgArgs& A, int64_t tid, 
 }
 
 template <int C>
-__global__ void __launch_bounds__(kPcgBlock) k_pcg(PcgArgs A) {
+__global__ void __launch_bounds__(kPcgBlock, C == 3 ? 2 : 3) k_pcg(PcgArgs A) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double sm[33];
+  __shared__ double sm[3 * 33];
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
 

@@ -276,7 +276,7 @@ __device__ __forceinline__ double oc_candidate(double rho, double s, double m, d
 
 __global__ void __launch_bounds__(512) k_oc(OcArgs A) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double sm[33];
+  __shared__ double sm[3 * 33];
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   double v2[2] = {0.0, 0.0};  // sum of volumes, count of negative sensitivities
   for (int64_t e = tid; e < A.n; e += nth) {
