@@ -200,9 +200,9 @@ def run_gpu(args):
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get('k_assemble_pairs_c2_bytes_per_launch')
+        traffic = json.load(open(tpath)).get('k_assemble_tiles_c2_bytes_per_launch')
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': traffic, 'kernel': 'k_assemble_pairs<P1_TRI,ELASTIC,2,2>', 'peak_source': peak_src,
+                'traffic': traffic, 'kernel': 'k_assemble_tiles<P1_TRI,ELASTIC,2,2>', 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg_bytes, 'bytes_per_element': alg_bytes / n_el,
                 'plan_bytes_read_per_launch': plan.read_bytes}
 

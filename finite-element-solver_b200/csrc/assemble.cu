@@ -536,18 +536,21 @@ extern "C" int fes_assemble_host(const fes_plan* plan, int elem_kind, int form, 
   if (!plan || !coeffs) return set_error(FES_ERR_VALUE, "fes_assemble_host: NULL argument");
   if (coeffs->d_E || coeffs->d_scale)
     return set_error(FES_ERR_VALUE, "fes_assemble_host: pass per-element coefficients through h_E / h_scale");
-  DevBuf<double> coords, E, scale, values;
-  FES_CUDA(coords.alloc((size_t)n_nodes * spatial_dim));
-  FES_CUDA(values.alloc(plan->nnz));
+  // device staging lives with the plan: repeated assemblies (a SIMP loop, a time stepper
+  // rebuilding its operator) pay the copies, not an allocation
+  DevBuf<double>&coords = plan->stage_coords, &E = plan->stage_E, &scale = plan->stage_scale,
+                &values = plan->stage_values;
+  if (coords.n != (size_t)n_nodes * spatial_dim) FES_CUDA(coords.alloc((size_t)n_nodes * spatial_dim));
+  if (values.n != (size_t)plan->nnz) FES_CUDA(values.alloc(plan->nnz));
   FES_CUDA(cudaMemcpyAsync(coords.p, h_coords, coords.bytes(), cudaMemcpyHostToDevice, st));
   fes_coeffs c = *coeffs;
   if (h_E) {
-    FES_CUDA(E.alloc(plan->n_el));
+    if (E.n != (size_t)plan->n_el) FES_CUDA(E.alloc(plan->n_el));
     FES_CUDA(cudaMemcpyAsync(E.p, h_E, E.bytes(), cudaMemcpyHostToDevice, st));
     c.d_E = E.p;
   }
   if (h_scale) {
-    FES_CUDA(scale.alloc(plan->n_el));
+    if (scale.n != (size_t)plan->n_el) FES_CUDA(scale.alloc(plan->n_el));
     FES_CUDA(cudaMemcpyAsync(scale.p, h_scale, scale.bytes(), cudaMemcpyHostToDevice, st));
     c.d_scale = scale.p;
   }

@@ -32,6 +32,9 @@ struct fes_plan {
   fes::DevBuf<uint16_t> pair_off16;    // n_pairs : first contribution, relative to the tile's first
   fes::DevBuf<uint8_t> pair_lrow;      // n_pairs : row node, relative to the tile's first node
   fes::DevBuf<uint16_t> pair_perm16;   // n_pairs : tile-local pair order, by contribution count descending
+
+  // staging for the host-buffer entry point (fes_assemble_host), allocated on first use
+  mutable fes::DevBuf<double> stage_coords, stage_values, stage_E, stage_scale;
 };
 
 namespace fes {
