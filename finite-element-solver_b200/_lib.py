@@ -56,6 +56,11 @@ SIGNATURES = {
     'fes_solver_solve': (_int, [_p, _p, _p, _dbl, _i64, _int, C.POINTER(_i64), C.POINTER(_dbl), _p]),
     'fes_solver_solve_host': (_int, [_p, _p, _p, _dbl, _i64, C.POINTER(_i64), C.POINTER(_dbl)]),
     'fes_lift_rhs': (_int, [_p, _p, _p, _p, _p]),
+    'fes_comm_create': (_int, [_int, _int, _i64, C.POINTER(_p)]),
+    'fes_comm_handle': (_int, [_p, _p]),
+    'fes_comm_connect': (_int, [_p, _p]),
+    'fes_comm_destroy': (None, [_p]),
+    'fes_solver_set_dist': (_int, [_p, _p, _i64, _i64, _p, _p, _p]),
     'fes_filter_create': (_int, [_p, _i64, _int, _p, _int, _dbl, _p, C.POINTER(_p)]),
     'fes_filter_destroy': (None, [_p]),
     'fes_filter_nnz': (_i64, [_p]),

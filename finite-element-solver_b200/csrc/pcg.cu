@@ -21,6 +21,8 @@
 //     slices carry almost no padding.
 //   * A 0/1 free mask restricts the iteration to the free-free block without forming
 //     A[free][:, free]: fixed rows carry dinv = r = p = q = 0, so the vector phases need no mask.
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -34,6 +36,25 @@ struct PcgState {
   int status;  // 0 converged, 1 not converged in maxiter, 2 breakdown (p.Ap <= 0 or NaN)
   double relres;
   double bnorm;
+};
+
+// Peer-memory communicator: one cudaMalloc'd region per rank, exported over CUDA IPC.
+//   [0,128)      u64 halo_flag[16]   peer r stores its halo epoch here after writing my ghosts
+//   [128,256)    u64 red_flag[16]    peer r stores the reduction step here after filling its box
+//   [256,2304)   double red_box[4][16][4]   ring of reduction mailboxes, [step & 3][src rank][value]
+//   [2304,2320)  u64 counters[2]     this rank's halo epoch / reduction step (persist across solves)
+//   [4096,...)   double p[max_dofs]  the CG direction vector; peers write its ghost entries
+constexpr int kCommMaxWorld = 16;
+constexpr size_t kCommHaloFlag = 0, kCommRedFlag = 128, kCommRedBox = 256, kCommCounters = 2304, kCommVec = 4096;
+
+struct fes_comm {
+  int rank = 0, world = 1;
+  int64_t max_dofs = 0;
+  size_t bytes = 0;
+  unsigned char* base = nullptr;                 // this rank's region
+  unsigned char* peer[kCommMaxWorld] = {};       // every rank's region in this process' address space
+  fes::DevBuf<unsigned char*> d_peer;            // the same table on the device
+  bool connected = false;
 };
 
 struct fes_solver {
@@ -56,6 +77,11 @@ struct fes_solver {
   int64_t n_slices = 0, sell_entries = 0;
   fes::DevBuf<int32_t> sell_row, sell_slice_ptr, sell_cols;
   fes::DevBuf<double> sell_vals;
+  // distributed mode: rows [row_begin, row_end) are owned; the rest of the local vector is ghost
+  fes_comm* comm = nullptr;
+  int64_t row_begin = 0, row_end = 0;
+  fes::DevBuf<int32_t> send_ptr, send_src, send_dst;
+  unsigned recv_mask = 0, send_mask = 0;
 };
 
 namespace fes {
@@ -83,7 +109,81 @@ struct PcgArgs {
   const int32_t* sell_slice_ptr;
   const int32_t* sell_cols;
   const double* sell_vals;
+  // owned row range (the whole vector on one GPU) and the peer-memory communicator
+  int64_t row_begin, row_end;
+  int world, rank;
+  unsigned char* comm;               // this rank's region (NULL on one GPU)
+  unsigned char* const* comm_peer;   // device table of every rank's region
+  const int32_t* send_ptr;           // [world+1] into send_src / send_dst (dof level)
+  const int32_t* send_src;           // local dof to read
+  const int32_t* send_dst;           // dof index in the receiver's local numbering
+  unsigned recv_mask, send_mask;     // bit r: this rank receives from / sends to rank r
 };
+
+constexpr long long kSpinLimit = 40000000000LL;  // ~20 s of SM clocks: a lost peer traps instead of hanging
+
+__device__ __forceinline__ void spin_until(const volatile unsigned long long* flag, unsigned long long want) {
+  const long long t0 = clock64();
+  while (*flag < want) {
+    if (clock64() - t0 > kSpinLimit) {
+      printf("fes_b200: peer wait timed out (flag %llu, want %llu)\n", (unsigned long long)*flag, want);
+      __trap();
+    }
+  }
+}
+
+// Write this rank's owned boundary values of `vec` straight into the ghost entries of every
+// neighbour's vector (NVLink peer stores), publish the epoch, then wait for the neighbours'.
+__device__ __forceinline__ void halo_exchange(const PcgArgs& A, cg::grid_group& grid, const double* vec,
+                                              unsigned long long epoch, int64_t tid, int64_t nth) {
+  const int32_t total = A.send_ptr[A.world];
+  for (int64_t k = tid; k < total; k += nth) {
+    int r = 0;
+    while (k >= A.send_ptr[r + 1]) ++r;
+    double* peer_vec = reinterpret_cast<double*>(A.comm_peer[r] + kCommVec);
+    peer_vec[A.send_dst[k]] = vec[A.send_src[k]];
+  }
+  __threadfence_system();
+  grid.sync();
+  if (blockIdx.x == 0 && (int)threadIdx.x < A.world && ((A.send_mask >> threadIdx.x) & 1u)) {
+    volatile unsigned long long* f =
+        reinterpret_cast<volatile unsigned long long*>(A.comm_peer[threadIdx.x] + kCommHaloFlag) + A.rank;
+    *f = epoch;
+  }
+  if (threadIdx.x == 0) {
+    for (int r = 0; r < A.world; ++r)
+      if ((A.recv_mask >> r) & 1u)
+        spin_until(reinterpret_cast<volatile unsigned long long*>(A.comm + kCommHaloFlag) + r, epoch);
+  }
+  __syncthreads();
+  __threadfence_system();  // drop stale L1 lines of the ghost entries before the gathers
+}
+
+// Sum NV values over all ranks through the peers' mailboxes; fixed rank order, so every rank and
+// every CTA computes the same bits.  v holds this rank's totals on entry (valid in every thread).
+template <int NV>
+__device__ __forceinline__ void rank_sum(const PcgArgs& A, double (&v)[NV], unsigned long long step) {
+  if (blockIdx.x == 0 && (int)threadIdx.x < A.world) {
+    unsigned char* peer = A.comm_peer[threadIdx.x];
+    volatile double* box = reinterpret_cast<volatile double*>(peer + kCommRedBox) + ((step & 3) * kCommMaxWorld + A.rank) * 4;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) box[k] = v[k];
+    __threadfence_system();
+    *(reinterpret_cast<volatile unsigned long long*>(peer + kCommRedFlag) + A.rank) = step;
+  }
+  if (threadIdx.x == 0) {
+    for (int r = 0; r < A.world; ++r)
+      spin_until(reinterpret_cast<volatile unsigned long long*>(A.comm + kCommRedFlag) + r, step);
+  }
+  __syncthreads();
+  const volatile double* mine = reinterpret_cast<const volatile double*>(A.comm + kCommRedBox) + (step & 3) * kCommMaxWorld * 4;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double t = 0.0;
+    for (int r = 0; r < A.world; ++r) t += mine[r * 4 + k];
+    v[k] = t;
+  }
+}
 
 __device__ __forceinline__ bool is_free(const uint8_t* mask, int64_t i) { return mask == nullptr || mask[i] != 0; }
 
@@ -143,22 +243,38 @@ __device__ __forceinline__ double sparse_product(const PcgArgs& A, int64_t tid, 
   return partial;
 }
 
-template <int C>
-__global__ void __launch_bounds__(kPcgBlock, C == 3 ? 2 : 3) k_pcg(PcgArgs A) {
+template <int C, bool DIST>
+__global__ void __launch_bounds__(kPcgBlock, (C == 3 || DIST) ? 2 : 3) k_pcg(PcgArgs A) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sm[3 * 33];
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
 
-  // ---- r0 = b - A x0 on the free rows (x0 = 0 unless warm), p = 0 everywhere
+  constexpr bool dist = DIST;  // the single-GPU instantiation carries none of the peer code
+  unsigned long long halo_epoch = 0, red_step = 0;
+  if (dist) {
+    const volatile unsigned long long* ctr = reinterpret_cast<const volatile unsigned long long*>(A.comm + kCommCounters);
+    halo_epoch = ctr[0];
+    red_step = ctr[1];
+  }
+  const int64_t lo = A.row_begin, hi = A.row_end;
+
+  // ---- r0 = b - A x0 on the owned free rows (x0 = 0 unless warm), p = 0
   if (A.warm) {
-    sparse_product<C, true, true>(A, tid, nth, A.x, A.r);
+    const double* x_all = A.x;
+    if (dist) {  // the product needs x on the ghost nodes: ship it through the shared vector
+      for (int64_t i = lo + tid; i < hi; i += nth) A.p[i] = A.x[i];
+      grid.sync();
+      halo_exchange(A, grid, A.p, ++halo_epoch, tid, nth);
+      x_all = A.p;
+    }
+    sparse_product<C, true, true>(A, tid, nth, x_all, A.r);
     grid.sync();
   }
   // Fixed rows carry dinv = 0 and r = p = q = 0 from here on, so the vector phases below need no
   // mask: every update leaves them at zero and x untouched.
   double v3[3] = {0.0, 0.0, 0.0};  // b.b, r.r, r.z
-  for (int64_t i = tid; i < A.n; i += nth) {
+  for (int64_t i = lo + tid; i < hi; i += nth) {
     const bool fr = is_free(A.mask, i);
     const double bi = fr ? A.b[i] : 0.0;
     double ri = bi;
@@ -171,12 +287,13 @@ __global__ void __launch_bounds__(kPcgBlock, C == 3 ? 2 : 3) k_pcg(PcgArgs A) {
     v3[2] += ri * ri * A.dinv[i];
   }
   grid_sum<3>(grid, v3, A.partials, 0, sm);
+  if (dist) rank_sum<3>(A, v3, ++red_step);
   const double bb = v3[0];
   double rr = v3[1], rho = v3[2], rho_prev = 1.0;
   long long it = 0;
   int status = 0;
   if (bb == 0.0) {  // scipy returns x = 0 for a zero right-hand side
-    for (int64_t i = tid; i < A.n; i += nth)
+    for (int64_t i = lo + tid; i < hi; i += nth)
       if (is_free(A.mask, i)) A.x[i] = 0.0;
     rr = 0.0;
   } else {
@@ -184,17 +301,19 @@ __global__ void __launch_bounds__(kPcgBlock, C == 3 ? 2 : 3) k_pcg(PcgArgs A) {
       if (sqrt(rr) < A.rtol * sqrt(bb)) break;
       if (it >= A.maxiter) { status = 1; break; }
       const double beta = (it == 0) ? 0.0 : rho / rho_prev;
-      for (int64_t i = tid; i < A.n; i += nth) A.p[i] = fma(beta, A.p[i], A.dinv[i] * A.r[i]);
+      for (int64_t i = lo + tid; i < hi; i += nth) A.p[i] = fma(beta, A.p[i], A.dinv[i] * A.r[i]);
       grid.sync();
+      if (dist) halo_exchange(A, grid, A.p, ++halo_epoch, tid, nth);
 
       double v1[1] = {sparse_product<C, false, false>(A, tid, nth, A.p, A.q)};
       grid_sum<1>(grid, v1, A.partials, 3, sm);
+      if (dist) rank_sum<1>(A, v1, ++red_step);
       const double pq = v1[0];
       if (!(pq > 0.0)) { status = 2; break; }
       const double alpha = rho / pq;
 
       double v2[2] = {0.0, 0.0};
-      for (int64_t i = tid; i < A.n; i += nth) {
+      for (int64_t i = lo + tid; i < hi; i += nth) {
         const double pi = A.p[i];
         if (pi != 0.0) A.x[i] = fma(alpha, pi, A.x[i]);  // fixed rows (p = 0) keep their prescribed value
         const double ri = A.r[i] - alpha * A.q[i];
@@ -203,6 +322,7 @@ __global__ void __launch_bounds__(kPcgBlock, C == 3 ? 2 : 3) k_pcg(PcgArgs A) {
         v2[1] += ri * ri * A.dinv[i];
       }
       grid_sum<2>(grid, v2, A.partials, 1, sm);
+      if (dist) rank_sum<2>(A, v2, ++red_step);
       rr = v2[0];
       rho_prev = rho;
       rho = v2[1];
@@ -214,6 +334,11 @@ __global__ void __launch_bounds__(kPcgBlock, C == 3 ? 2 : 3) k_pcg(PcgArgs A) {
     A.state->status = status;
     A.state->bnorm = sqrt(bb);
     A.state->relres = bb > 0.0 ? sqrt(rr) / sqrt(bb) : 0.0;
+    if (dist) {
+      volatile unsigned long long* ctr = reinterpret_cast<volatile unsigned long long*>(A.comm + kCommCounters);
+      ctr[0] = halo_epoch;
+      ctr[1] = red_step;
+    }
   }
 }
 
@@ -303,20 +428,20 @@ int pick_lanes(int64_t n, int64_t nnz) {
   return 32;
 }
 
-template <int C>
+template <int C, bool DIST>
 int launch_pcg(fes_solver* s, PcgArgs& args, cudaStream_t st) {
   if (s->grid == 0) {
     int dev = 0, sms = 0, per_sm = 0;
     FES_CUDA(cudaGetDevice(&dev));
     FES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    FES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<C>, kPcgBlock, 0));
+    FES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<C, DIST>, kPcgBlock, 0));
     if (per_sm < 1) return set_error(FES_ERR_CUDA, "PCG kernel does not fit on an SM");
     s->grid = sms * per_sm;
     if (s->grid > kMaxGrid) s->grid = kMaxGrid;
     s->block = kPcgBlock;
   }
   void* params[] = {&args};
-  FES_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<C>, dim3(s->grid), dim3(s->block), params, 0, st));
+  FES_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<C, DIST>, dim3(s->grid), dim3(s->block), params, 0, st));
   count_launch();
   return FES_OK;
 }
@@ -325,17 +450,19 @@ int launch_pcg(fes_solver* s, PcgArgs& args, cudaStream_t st) {
 // host from the row lengths (O(rows), once per operator); columns and values are filled on the
 // device.
 int build_sell(fes_solver* s, cudaStream_t st) {
-  const int64_t nb = s->n_brow;
-  std::vector<int32_t> ptr(nb + 1);
-  FES_CUDA(cudaMemcpyAsync(ptr.data(), s->row_ptr, (nb + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  const int64_t nb_all = s->n_brow;
+  std::vector<int32_t> ptr(nb_all + 1);
+  FES_CUDA(cudaMemcpyAsync(ptr.data(), s->row_ptr, (nb_all + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   FES_CUDA(cudaStreamSynchronize(st));
+  // only the owned block rows are multiplied (all of them on one GPU)
+  const int64_t b0 = s->row_begin / s->c, b1 = s->row_end / s->c, nb = b1 - b0;
   const int64_t n_slices = (nb + 31) / 32;
   std::vector<int32_t> row(n_slices * 32, -1), slice_ptr(n_slices + 1, 0);
   std::vector<int32_t> order;
   for (int64_t w0 = 0; w0 < nb; w0 += kSigma) {
     const int64_t w1 = std::min<int64_t>(nb, w0 + kSigma);
     order.resize(w1 - w0);
-    for (int64_t i = w0; i < w1; ++i) order[i - w0] = (int32_t)i;
+    for (int64_t i = w0; i < w1; ++i) order[i - w0] = (int32_t)(b0 + i);
     std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
       return ptr[a + 1] - ptr[a] > ptr[b + 1] - ptr[b];
     });
@@ -402,6 +529,7 @@ int init_solver(fes_solver* s, cudaStream_t st) {
     s->n_free = (int64_t)h;
   }
   s->c = 1; s->n_brow = s->n; s->row_ptr = s->indptr; s->row_col = s->indices;
+  s->row_begin = 0; s->row_end = s->n;
   return FES_OK;
 }
 
@@ -514,6 +642,84 @@ extern "C" int fes_solver_use_plan(fes_solver* s, const fes_plan* plan) {
   return FES_OK;
 }
 
+extern "C" int fes_comm_create(int rank, int world, int64_t max_local_dofs, fes_comm** out) {
+  if (!out) return set_error(FES_ERR_VALUE, "fes_comm_create: out is NULL");
+  *out = nullptr;
+  if (world < 1 || world > kCommMaxWorld || rank < 0 || rank >= world || max_local_dofs < 0)
+    return set_error(FES_ERR_VALUE, "fes_comm_create: bad rank/world (%d/%d; at most %d ranks)", rank, world, kCommMaxWorld);
+  fes_comm* c = new fes_comm();
+  c->rank = rank; c->world = world; c->max_dofs = max_local_dofs;
+  c->bytes = kCommVec + (size_t)max_local_dofs * sizeof(double);
+  if (cudaMalloc((void**)&c->base, c->bytes) != cudaSuccess || cudaMemset(c->base, 0, c->bytes) != cudaSuccess) {
+    delete c;
+    return set_error(FES_ERR_CUDA, "fes_comm_create: cannot allocate %zu bytes", c->bytes);
+  }
+  c->peer[rank] = c->base;
+  *out = c;
+  return FES_OK;
+}
+
+extern "C" int fes_comm_handle(const fes_comm* c, void* out64) {
+  if (!c || !out64) return set_error(FES_ERR_VALUE, "fes_comm_handle: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  FES_CUDA(cudaIpcGetMemHandle(&h, c->base));
+  memcpy(out64, &h, 64);
+  return FES_OK;
+}
+
+extern "C" int fes_comm_connect(fes_comm* c, const void* handles) {
+  if (!c || !handles) return set_error(FES_ERR_VALUE, "fes_comm_connect: NULL argument");
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + 64 * r, 64);
+    void* p = nullptr;
+    FES_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer[r] = (unsigned char*)p;
+  }
+  FES_CUDA(c->d_peer.alloc(kCommMaxWorld));
+  FES_CUDA(cudaMemcpy(c->d_peer.p, c->peer, sizeof(c->peer), cudaMemcpyHostToDevice));
+  c->connected = true;
+  return FES_OK;
+}
+
+extern "C" void fes_comm_destroy(fes_comm* c) {
+  if (!c) return;
+  for (int r = 0; r < c->world; ++r)
+    if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+  if (c->base) cudaFree(c->base);
+  delete c;
+}
+
+extern "C" int fes_solver_set_dist(fes_solver* s, fes_comm* comm, int64_t row_begin, int64_t row_end,
+                                   const int32_t* h_send_ptr, const int32_t* h_send_src, const int32_t* h_send_dst) {
+  if (!s || !comm || !h_send_ptr) return set_error(FES_ERR_VALUE, "fes_solver_set_dist: NULL argument");
+  if (row_begin < 0 || row_end > s->n || row_begin > row_end || row_begin % s->c || row_end % s->c)
+    return set_error(FES_ERR_VALUE, "fes_solver_set_dist: bad owned row range [%lld, %lld)", (long long)row_begin,
+                     (long long)row_end);
+  if (s->n > comm->max_dofs) return set_error(FES_ERR_VALUE, "fes_solver_set_dist: communicator vector too small");
+  if (s->sell_row.p != nullptr) return set_error(FES_ERR_VALUE, "fes_solver_set_dist: call before the first solve");
+  s->comm = comm;
+  s->row_begin = row_begin; s->row_end = row_end;
+  const int world = comm->world;
+  const int32_t total = h_send_ptr[world];
+  FES_CUDA(s->send_ptr.alloc(world + 1));
+  FES_CUDA(s->send_src.alloc(total > 0 ? total : 1));
+  FES_CUDA(s->send_dst.alloc(total > 0 ? total : 1));
+  FES_CUDA(cudaMemcpy(s->send_ptr.p, h_send_ptr, (world + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (total > 0) {
+    FES_CUDA(cudaMemcpy(s->send_src.p, h_send_src, total * sizeof(int32_t), cudaMemcpyHostToDevice));
+    FES_CUDA(cudaMemcpy(s->send_dst.p, h_send_dst, total * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  s->send_mask = 0;
+  for (int r = 0; r < world; ++r)
+    if (h_send_ptr[r + 1] > h_send_ptr[r]) s->send_mask |= 1u << r;
+  // the halo is symmetric for a symmetric pattern: whoever needs my nodes owns nodes I need
+  s->recv_mask = s->send_mask;
+  return FES_OK;
+}
+
 extern "C" int fes_solver_solve(fes_solver* s, const double* d_b, double* d_x, double rtol, int64_t maxiter,
                                 int warm_start, int64_t* iters_out, double* relres_out, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
@@ -523,12 +729,23 @@ extern "C" int fes_solver_solve(fes_solver* s, const double* d_b, double* d_x, d
   if (s->n == 0 || s->n_free == 0) return FES_OK;
   if (maxiter <= 0) maxiter = 10 * s->n_free;
   FES_TRY(ensure_sell(s, st));
-  PcgArgs a{s->n, s->mask, s->dinv.p, d_b, d_x, s->r.p, s->p.p, s->q.p, s->partials.p, s->state.p, rtol,
+  const bool dist = s->comm != nullptr && s->comm->world > 1;
+  if (dist && !s->comm->connected) return set_error(FES_ERR_VALUE, "fes_solver_solve: communicator is not connected");
+  double* pvec = dist ? reinterpret_cast<double*>(s->comm->base + kCommVec) : s->p.p;
+  PcgArgs a{s->n, s->mask, s->dinv.p, d_b, d_x, s->r.p, pvec, s->q.p, s->partials.p, s->state.p, rtol,
             (long long)maxiter, warm_start ? 1 : 0, s->n_slices * 32, s->sell_row.p, s->sell_slice_ptr.p,
-            s->sell_cols.p, s->sell_vals.p};
-  if (s->c == 2) FES_TRY(launch_pcg<2>(s, a, st));
-  else if (s->c == 3) FES_TRY(launch_pcg<3>(s, a, st));
-  else FES_TRY(launch_pcg<1>(s, a, st));
+            s->sell_cols.p, s->sell_vals.p, s->row_begin, s->row_end, dist ? s->comm->world : 1,
+            dist ? s->comm->rank : 0, dist ? s->comm->base : nullptr, dist ? s->comm->d_peer.p : nullptr,
+            s->send_ptr.p, s->send_src.p, s->send_dst.p, s->recv_mask, s->send_mask};
+  if (dist) {
+    if (s->c == 2) FES_TRY((launch_pcg<2, true>(s, a, st)));
+    else if (s->c == 3) FES_TRY((launch_pcg<3, true>(s, a, st)));
+    else FES_TRY((launch_pcg<1, true>(s, a, st)));
+  } else {
+    if (s->c == 2) FES_TRY((launch_pcg<2, false>(s, a, st)));
+    else if (s->c == 3) FES_TRY((launch_pcg<3, false>(s, a, st)));
+    else FES_TRY((launch_pcg<1, false>(s, a, st)));
+  }
   PcgState h;
   FES_CUDA(cudaMemcpyAsync(&h, s->state.p, sizeof(h), cudaMemcpyDeviceToHost, st));
   FES_CUDA(cudaStreamSynchronize(st));

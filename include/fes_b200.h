@@ -50,6 +50,7 @@ extern "C" {
 typedef struct fes_plan fes_plan;     /* CSR pattern + scatter plan of one (connectivity, n_comp)  */
 typedef struct fes_solver fes_solver; /* Jacobi-PCG bound to one operator                          */
 typedef struct fes_filter fes_filter; /* SIMP cone filter (row-normalised CSR over elements)       */
+typedef struct fes_comm fes_comm;     /* peer-memory communicator of the distributed PCG           */
 
 /* Coefficients of a form.  ScaledForm(factor, form) sets `factor`; per-element modulus
  * (LinearElasticMaterial(E=array)) sets d_E; MaskedMassForm's 0/1 mask and SIMP's rho^p go in
@@ -163,6 +164,22 @@ int fes_solver_solve_host(fes_solver* s, const double* h_b, double* h_x, double 
 /* b_f - A_fx x_fixed: d_rhs = d_b - A * d_xfixed on free rows (ref fem/system.py:49-50) */
 int fes_lift_rhs(const fes_solver* s, const double* d_b, const double* d_xfixed, double* d_rhs,
                  void* stream);
+
+/* ---- multi-GPU (one process per GPU) -------------------------------------------
+ * The operator is sharded by contiguous node blocks with ghost elements; assembly needs no
+ * exchange.  The distributed PCG keeps ONE persistent kernel per rank: the halo of the direction
+ * vector is written by its owners straight into the neighbours' vectors over NVLink peer memory
+ * (CUDA IPC), and the dot products are summed through per-rank mailboxes in fixed rank order, so
+ * every rank computes bit-identical alpha/beta.  The host only exchanges the 64-byte IPC handles
+ * and the halo index lists (torch.distributed). */
+int fes_comm_create(int rank, int world, int64_t max_local_dofs, fes_comm** out);
+int fes_comm_handle(const fes_comm* comm, void* out64);         /* cudaIpcMemHandle_t of this rank   */
+int fes_comm_connect(fes_comm* comm, const void* handles);      /* world x 64 bytes, rank order      */
+void fes_comm_destroy(fes_comm* comm);
+/* Rows [row_begin,row_end) of the local numbering are owned; h_send_* (dof level) list, per peer
+ * rank, the owned dofs it needs and their index in ITS numbering.  Call before the first solve. */
+int fes_solver_set_dist(fes_solver* s, fes_comm* comm, int64_t row_begin, int64_t row_end,
+                        const int32_t* h_send_ptr, const int32_t* h_send_src, const int32_t* h_send_dst);
 
 /* ---- SIMP inner loop ----------------------------------------------------------------------
  * Replaces calculate_smoothing_matrix (ref fem/topology.py:39-77), DensityField.gradient /
