@@ -248,11 +248,108 @@ def run_gpu(args):
                                'host_cpus': os.cpu_count()}
         if not args.no_extra:
             extra.update(extra_metrics(F, V, mesh, dev))
+    if not args.no_extra:
+        del values
+        torch.cuda.empty_cache()
+        try:
+            extra['config5_tets'] = config5_metrics(F, world, rank, dev, n=args.tet_n)
+        except Exception as exc:   # reported, never silently dropped
+            extra['config5_tets'] = {'error': f'{type(exc).__name__}: {exc}'[:300]}
     out['extra'] = extra
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def config5_metrics(F, world, rank, dev, n=151, pcg_iters=300):
+    """Config 5: 3D P1 elasticity on create_box_mesh(n^3 nodes) = 6(n-1)^3 tets, sharded by node
+    blocks over `world` GPUs (strong scaling).  Times the owner-computes assembly (no collective)
+    and the distributed Jacobi-PCG (halo + reductions inside the persistent kernel)."""
+    import torch
+    import torch.distributed as dist
+    from fes_b200 import _lib
+    from fes_b200.dist import (Communicator, DistributedSystem, NodePartition, all_to_all_objects,
+                               halo_schedule)
+    from fes_b200.mesh import boundary_facets, box_arrays
+    t0 = time.perf_counter()
+    verts, elems = box_arrays([[0, 0, 0], [1, 1, 1]], (n, n, n))
+    part = NodePartition(elems, len(verts), rank, world)
+    # only the two loaded/clamped faces matter for the boundary data: facets of the first and last
+    # cell layers lying in the planes x = 0 and x = 1
+    plane = n * n
+    faces = []
+    for layer, lo in ((slice(0, 6 * (n - 1) ** 2), 0), (slice(len(elems) - 6 * (n - 1) ** 2, len(elems)), len(verts) - plane)):
+        f = boundary_facets(elems[layer])
+        faces.append(f[((f >= lo) & (f < lo + plane)).all(axis=1)])
+    mesh_l = part.local_mesh(verts, np.concatenate(faces))
+    host_s = time.perf_counter() - t0
+    n_el_global, n_el_local = len(elems), len(part.local_elements)
+    del elems
+    Vl = F.FunctionSpace(mesh_l, n_components=3)
+    form = F.LinearElasticForm(F.LinearElasticMaterial(200.0, 0.3))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    plan = Vl.plan()
+    torch.cuda.synchronize()
+    plan_s = time.perf_counter() - t0
+    A = Vl.assemble_device(form)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    reps = 5
+    ev0.record()
+    for _ in range(reps):
+        Vl.assemble_device(form, out=A.data_d)
+    ev1.record()
+    torch.cuda.synchronize()
+    asm_ms = torch.tensor([ev0.elapsed_time(ev1) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(asm_ms, op=dist.ReduceOp.MAX)
+    asm_ms = float(asm_ms.item())
+    alg = 4 * 4 * n_el_local + 8 * 3 * len(mesh_l.vertices) + 8 * plan.nnz
+    # cantilever: clamp x = 0, traction [0,-5,0] on x = 1 (ref tests/test_backends.py:109-113)
+    from fes_b200.regions import on_plane
+    bc = F.BoundaryConditions()
+    bc.add(F.BCType.DIRICHLET, on_plane(0, 0.0), [0, 0, 0])
+    bc.add(F.BCType.NEUMANN, on_plane(0, 1.0), [0, -5, 0])
+    prob = F.LinearProblem(Vl, form, None, bc)
+    free, fixed, vals = prob.constraints
+    mask = torch.zeros(Vl.n_dofs, dtype=torch.uint8, device=dev)
+    mask[torch.as_tensor(free, device=dev)] = 1
+    backend = F.JacobiPCGBackend(rtol=1e-30, maxiter=pcg_iters)
+    x = torch.zeros(Vl.n_dofs, dtype=torch.float64, device=dev)
+    if world > 1:
+        md = torch.tensor([Vl.n_dofs], device=dev)
+        dist.all_reduce(md, op=dist.ReduceOp.MAX)
+        comm = Communicator(int(md.item()))
+        system = DistributedSystem(part, A, 3, mask, comm, halo_schedule(part, all_to_all_objects), backend)
+        solve = lambda: system.solve(prob.load_d, x)
+    else:
+        solver = backend.prepare(A, mask)
+        solve = lambda: solver.solve_device(prob.load_d, x)
+    best = float('inf')
+    for _ in range(2):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        try:
+            solve()
+        except RuntimeError:
+            pass                      # capped iteration count: "CG failed" is expected here
+        torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    t = torch.tensor([best], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    us_iter = 1e6 * float(t.item()) / pcg_iters
+    return {'n_nodes_per_side': n, 'elements': n_el_global, 'elements_per_gpu': n_el_local, 'dofs': 3 * n ** 3,
+            'nnz_per_gpu': plan.nnz, 'assembly_ms': asm_ms, 'elements_per_s': n_el_global / (asm_ms * 1e-3),
+            'assembly_hbm_frac_of_measured': alg / (asm_ms * 1e-3) / 1e9 / measured_peak()[0],
+            'plan_build_s': plan_s, 'host_mesh_partition_s': host_s, 'pcg_us_per_iteration': us_iter,
+            'pcg_iterations_timed': pcg_iters, 'scaling': 'strong'}
 
 
 def extra_metrics(F, V, mesh, dev):
@@ -307,6 +404,7 @@ if __name__ == '__main__':
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-extra', action='store_true')
+    ap.add_argument('--tet-n', type=int, default=151, help='nodes per side of the config-5 tet box')
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != 'reference' else a.warmup
     if a.impl == 'reference':

@@ -21,6 +21,7 @@
 //     slices carry almost no padding.
 //   * A 0/1 free mask restricts the iteration to the free-free block without forming
 //     A[free][:, free]: fixed rows carry dinv = r = p = q = 0, so the vector phases need no mask.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -36,6 +37,7 @@ struct PcgState {
   int status;  // 0 converged, 1 not converged in maxiter, 2 breakdown (p.Ap <= 0 or NaN)
   double relres;
   double bnorm;
+  long long cycles[6];  // CTA 0 / thread 0: p update, halo, product, product reduce, x/r update, update reduce
 };
 
 // Peer-memory communicator: one cudaMalloc'd region per rank, exported over CUDA IPC.
@@ -292,6 +294,7 @@ __global__ void __launch_bounds__(kPcgBlock, (C == 3 || DIST) ? 2 : 3) k_pcg(Pcg
   double rr = v3[1], rho = v3[2], rho_prev = 1.0;
   long long it = 0;
   int status = 0;
+  long long cyc[6] = {0, 0, 0, 0, 0, 0};
   if (bb == 0.0) {  // scipy returns x = 0 for a zero right-hand side
     for (int64_t i = lo + tid; i < hi; i += nth)
       if (is_free(A.mask, i)) A.x[i] = 0.0;
@@ -301,13 +304,18 @@ __global__ void __launch_bounds__(kPcgBlock, (C == 3 || DIST) ? 2 : 3) k_pcg(Pcg
       if (sqrt(rr) < A.rtol * sqrt(bb)) break;
       if (it >= A.maxiter) { status = 1; break; }
       const double beta = (it == 0) ? 0.0 : rho / rho_prev;
+      long long c0 = clock64();
       for (int64_t i = lo + tid; i < hi; i += nth) A.p[i] = fma(beta, A.p[i], A.dinv[i] * A.r[i]);
       grid.sync();
+      long long c1 = clock64(); cyc[0] += c1 - c0;
       if (dist) halo_exchange(A, grid, A.p, ++halo_epoch, tid, nth);
+      c0 = clock64(); cyc[1] += c0 - c1;
 
       double v1[1] = {sparse_product<C, false, false>(A, tid, nth, A.p, A.q)};
+      c1 = clock64(); cyc[2] += c1 - c0;
       grid_sum<1>(grid, v1, A.partials, 3, sm);
       if (dist) rank_sum<1>(A, v1, ++red_step);
+      c0 = clock64(); cyc[3] += c0 - c1;
       const double pq = v1[0];
       if (!(pq > 0.0)) { status = 2; break; }
       const double alpha = rho / pq;
@@ -321,8 +329,10 @@ __global__ void __launch_bounds__(kPcgBlock, (C == 3 || DIST) ? 2 : 3) k_pcg(Pcg
         v2[0] += ri * ri;
         v2[1] += ri * ri * A.dinv[i];
       }
+      c1 = clock64(); cyc[4] += c1 - c0;
       grid_sum<2>(grid, v2, A.partials, 1, sm);
       if (dist) rank_sum<2>(A, v2, ++red_step);
+      cyc[5] += clock64() - c1;
       rr = v2[0];
       rho_prev = rho;
       rho = v2[1];
@@ -334,6 +344,7 @@ __global__ void __launch_bounds__(kPcgBlock, (C == 3 || DIST) ? 2 : 3) k_pcg(Pcg
     A.state->status = status;
     A.state->bnorm = sqrt(bb);
     A.state->relres = bb > 0.0 ? sqrt(rr) / sqrt(bb) : 0.0;
+    for (int k = 0; k < 6; ++k) A.state->cycles[k] = cyc[k];
     if (dist) {
       volatile unsigned long long* ctr = reinterpret_cast<volatile unsigned long long*>(A.comm + kCommCounters);
       ctr[0] = halo_epoch;
@@ -751,6 +762,12 @@ extern "C" int fes_solver_solve(fes_solver* s, const double* d_b, double* d_x, d
   FES_CUDA(cudaStreamSynchronize(st));
   if (iters_out) *iters_out = h.iters;
   if (relres_out) *relres_out = h.relres;
+  if (getenv("FES_PCG_TIMERS") && h.iters > 0) {
+    const char* names[6] = {"p-update", "halo", "product", "product-reduce", "xr-update", "update-reduce"};
+    fprintf(stderr, "[fes pcg] rank %d, %lld iterations, SM cycles per iteration:", dist ? s->comm->rank : 0, h.iters);
+    for (int k = 0; k < 6; ++k) fprintf(stderr, " %s=%lld", names[k], h.cycles[k] / h.iters);
+    fprintf(stderr, "\n");
+  }
   if (h.status == 1)
     return set_error(FES_ERR_CG, "CG failed to solve the free-free block: did not converge in %lld iterations "
                      "(relative residual %.3e). The operator must be symmetric positive-definite for CG.",
