@@ -8,6 +8,8 @@
 // order np.bincount(group, weights=Ke.ravel()[order]) adds them -- evaluates each
 // element block in registers and writes every CSR value exactly once.  No atomics, so the
 // result is deterministic; element matrices never exist in HBM.
+#include <stdlib.h>
+
 #include "elements.cuh"
 #include "plan.cuh"
 #include "tma.cuh"
@@ -107,88 +109,82 @@ k_assemble_pairs(int64_t n_pairs, const uint32_t* __restrict__ pair_start, const
 
 
 // ---- fused assembly, tiled (the production kernel) ------------------------------------------
-// One CTA per tile of consecutive nodes.
-//   phase 1: one thread per (node, incident element) evaluates the element's geometry ONCE --
-//            inverse Jacobian, every node's physical gradient at every quadrature point, and the
-//            element weight(s) -- into a shared-memory record (the fp64 divide lives here).
-//   phase 2: one thread per stored node pair walks its contributions in ascending element id,
-//            reads the two gradients it needs from the records and accumulates the C x C block
-//            in registers with fused multiply-adds; each CSR value is written exactly once.
-// Shared memory holds records only; nothing but the CSR values is written to HBM.
+// One CTA (128 threads) per tile of consecutive nodes.
+//   staging: thread 0 arms an mbarrier and issues two 1-D TMA bulk copies (cp.async.bulk, SASS
+//            UBLKCP) of the tile's contiguous plan streams -- the packed metadata of its active
+//            pairs and their contribution codes -- which land while phase 1 runs.
+//   phase 1: one thread per (node, incident element) record, two records per thread in flight,
+//            evaluates the element's geometry ONCE -- inverse Jacobian (the only fp64 divide) and
+//            every node's physical gradient at every quadrature point, pre-multiplied by
+//            sqrt(w_q mu_e) -- into shared memory, double2-packed and record-minor so both the
+//            writes and the LDS.128 reads of phase 2 are as wide as they can be.
+//   phase 2: one thread per ACTIVE pair (v, w >= v), taken in descending contribution count so a
+//            warp's trip counts agree.  It walks the pair's contributions in ascending element id
+//            (np.bincount's order), accumulates the raw outer products S += g~_a (x) g~_b in
+//            registers, applies K = (lam/mu) S + S^T + tr(S) I once, and writes the block of (v, w)
+//            and -- K being symmetric, bit for bit -- its transpose as the block of (w, v).
+// Every CSR value is written exactly once; no atomics, so results are reproducible.
 template <int ELEM, int FORM, int C, int SD>
 struct RecLayout {
   static constexpr int N = ET<ELEM>::N, NQ = ET<ELEM>::NQ;
-  // gradient forms store sqrt(weight)-scaled gradients, so no separate weight is needed;
-  // the mass form stores the weighted measure only
-  static constexpr int NG = (FORM == FES_FORM_MASS) ? 0 : NQ * N * SD;
-  static constexpr int NW = (FORM == FES_FORM_MASS) ? 1 : 0;
-  static constexpr int SIZE = NG + NW;
+  // per (quadrature point, node): SD/2 double2 planes + (SD & 1) double plane; mass: one weight
+  static constexpr int NV2 = (FORM == FES_FORM_MASS) ? 0 : NQ * N * (SD / 2);
+  static constexpr int NV1 = (FORM == FES_FORM_MASS) ? 1 : NQ * N * (SD & 1);
+  static constexpr int DOUBLES = 2 * NV2 + NV1;
 };
 
-constexpr int kTileThreads = 256;
+constexpr int kTileThreads = 128;
 constexpr int kRecBatch = 2;  // records a thread evaluates per pass of phase 1 (memory-level parallelism)
 
-// shared-memory carve-up of one tile (bytes); records first, then the TMA-staged plan streams
 template <int ELEM, int FORM, int C, int SD>
 struct TileSmem {
   using R = RecLayout<ELEM, FORM, C, SD>;
-  static constexpr int N = ET<ELEM>::N;
-  __host__ __device__ static size_t rec_bytes(int gmax) { return (size_t)gmax * R::SIZE * sizeof(double); }
-  __host__ __device__ static size_t contrib_bytes(int gmax) { return ((size_t)gmax * N * 2 + 32 + 15) & ~(size_t)15; }
-  __host__ __device__ static size_t off_bytes(int pmax) { return ((size_t)pmax * 2 + 32 + 15) & ~(size_t)15; }
-  __host__ __device__ static size_t lrow_bytes(int pmax) { return ((size_t)pmax + 32 + 15) & ~(size_t)15; }
-  __host__ __device__ static size_t total(int gmax, int pmax) {
-    return rec_bytes(gmax) + contrib_bytes(gmax) + 2 * off_bytes(pmax) + lrow_bytes(pmax);
+  __host__ __device__ static size_t rec_bytes(int gmax) { return ((size_t)gmax * R::DOUBLES * 8 + 15) & ~(size_t)15; }
+  __host__ __device__ static size_t meta_bytes(int amax) { return (size_t)amax * 16 + 16; }
+  __host__ __device__ static size_t code_bytes(int cmax) { return ((size_t)cmax * 2 + 32 + 15) & ~(size_t)15; }
+  __host__ __device__ static size_t total(int gmax, int amax, int cmax) {
+    return rec_bytes(gmax) + meta_bytes(amax) + code_bytes(cmax);
   }
 };
 
 template <int ELEM, int FORM, int C, int SD>
 __global__ void __launch_bounds__(kTileThreads)
 k_assemble_tiles(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__ ne_ptr,
-                 const uint32_t* __restrict__ ne_code, const int32_t* __restrict__ node_ptr,
-                 const uint16_t* __restrict__ pair_off16, const uint8_t* __restrict__ pair_lrow,
-                 const uint16_t* __restrict__ pair_perm16, const uint16_t* __restrict__ contrib16,
-                 const int32_t* __restrict__ en, const double* __restrict__ coords, Coeffs cf, int geo_stride,
-                 int pair_max, double* __restrict__ values) {
+                 const uint32_t* __restrict__ ne_code, const int32_t* __restrict__ tile_act0,
+                 const int32_t* __restrict__ tile_con0, const uint4* __restrict__ act_meta,
+                 const uint16_t* __restrict__ act_codes, const int32_t* __restrict__ en,
+                 const double* __restrict__ coords, Coeffs cf, int geo_stride, int act_max,
+                 double* __restrict__ values) {
   using R = RecLayout<ELEM, FORM, C, SD>;
   using TS = TileSmem<ELEM, FORM, C, SD>;
   constexpr int N = ET<ELEM>::N, NQ = ET<ELEM>::NQ, RD = ET<ELEM>::RD;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int32_t s_node_ptr[257];
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ uint32_t s_skew[4];
+  __shared__ uint32_t s_skew;
   const int GS = geo_stride;
-  double* smem = reinterpret_cast<double*>(smem_raw);  // records, field-major: field f of record g at smem[f*GS+g]
-  unsigned char* s_contrib = smem_raw + TS::rec_bytes(GS);
-  unsigned char* s_off = s_contrib + TS::contrib_bytes(GS);
-  unsigned char* s_perm = s_off + TS::off_bytes(pair_max);
-  unsigned char* s_lrow = s_perm + TS::off_bytes(pair_max);
+  // planes: v2[plane * GS + record] (double2), then v1[plane * GS + record] (double)
+  double2* v2 = reinterpret_cast<double2*>(smem_raw);
+  double* v1 = reinterpret_cast<double*>(smem_raw) + (size_t)2 * R::NV2 * GS;
+  const uint4* s_meta = reinterpret_cast<const uint4*>(smem_raw + TS::rec_bytes(GS));
+  unsigned char* s_code = smem_raw + TS::rec_bytes(GS) + TS::meta_bytes(act_max);
 
-  const int32_t v0 = tile_node0[blockIdx.x], v1 = tile_node0[blockIdx.x + 1];
-  const int32_t g0 = ne_ptr[v0], g1 = ne_ptr[v1];
-  const int32_t p0 = node_ptr[v0], p1 = node_ptr[v1];
+  const int32_t v0 = tile_node0[blockIdx.x], v1n = tile_node0[blockIdx.x + 1];
+  const int32_t g0 = ne_ptr[v0], g1 = ne_ptr[v1n];
+  const int32_t a0 = tile_act0[blockIdx.x], n_act = tile_act0[blockIdx.x + 1] - a0;
 
-  // ---- stage this tile's contiguous plan streams with TMA bulk copies (overlaps phase 1)
   if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
-    uint32_t b0, b1, b2;
-    const uint32_t n_contrib = (uint32_t)N * (uint32_t)(g1 - g0), n_pairs = (uint32_t)(p1 - p0);
-    // expect_tx must precede the copies' completion; compute sizes first
-    const uint64_t c_begin = (uint64_t)N * (uint64_t)g0 * 2, o_begin = (uint64_t)p0 * 2, l_begin = (uint64_t)p0;
-    b0 = (uint32_t)(((c_begin & 15) + (uint64_t)n_contrib * 2 + 15) & ~(uint64_t)15);
-    b1 = (uint32_t)(((o_begin & 15) + (uint64_t)n_pairs * 2 + 15) & ~(uint64_t)15);
-    b2 = (uint32_t)(((l_begin & 15) + (uint64_t)n_pairs + 15) & ~(uint64_t)15);
-    mbar_arrive_expect_tx(&s_bar, b0 + 2 * b1 + b2);
+    const int32_t c0 = tile_con0[blockIdx.x], n_con = tile_con0[blockIdx.x + 1] - c0;
+    const uint64_t c_begin = (uint64_t)c0 * 2;
+    const uint32_t b_meta = (uint32_t)n_act * 16u;
+    const uint32_t b_code = (uint32_t)(((c_begin & 15) + (uint64_t)n_con * 2 + 15) & ~(uint64_t)15);
+    mbar_arrive_expect_tx(&s_bar, b_meta + b_code);
+    if (b_meta) bulk_g2s(const_cast<uint4*>(s_meta), act_meta + a0, b_meta, &s_bar);
     uint32_t t;
-    s_skew[0] = stage_window<2>(s_contrib, contrib16, (uint32_t)N * (uint32_t)g0, n_contrib, &s_bar, t);
-    s_skew[1] = stage_window<2>(s_off, pair_off16, (uint32_t)p0, n_pairs, &s_bar, t);
-    s_skew[2] = stage_window<1>(s_lrow, pair_lrow, (uint32_t)p0, n_pairs, &s_bar, t);
-    s_skew[3] = stage_window<2>(s_perm, pair_perm16, (uint32_t)p0, n_pairs, &s_bar, t);
+    s_skew = stage_window<2>(s_code, act_codes, (uint32_t)c0, (uint32_t)n_con, &s_bar, t);
   }
-  for (int l = threadIdx.x; l <= v1 - v0; l += kTileThreads) s_node_ptr[l] = node_ptr[v0 + l];
 
-  // ---- phase 1: geometry records, kRecBatch per thread so the index -> connectivity -> coordinate
-  //      load chain of several records is in flight together
+  // ---- phase 1: geometry records
   for (int32_t base = g0 + threadIdx.x; base < g1; base += kTileThreads * kRecBatch) {
     uint32_t e[kRecBatch];
     bool live[kRecBatch];
@@ -223,15 +219,15 @@ k_assemble_tiles(const int32_t* __restrict__ tile_node0, const int32_t* __restri
       make_geom<RD, SD>(X[r], g);
       Material m; double w;
       element_coeffs(cf, e[r], m, w);
-      double* rec = smem + (base + r * kTileThreads - g0);
+      const int rec = base + r * kTileThreads - g0;
       const double vol = g.scale * ref_measure(RD);
       if constexpr (FORM == FES_FORM_MASS) {
-        rec[0] = w * vol;
+        v1[rec] = w * vol;
       } else {
-        // g~ = sqrt(w_q E_e) g: the element's weight and modulus ride on the gradients, so phase 2
-        // accumulates plain outer products and applies the (uniform) Lame factors once per pair
+        // g~ = sqrt(w_q mu_e) g: weight and modulus ride on the gradients (mu1 is divided out by
+        // using lam/mu below), so phase 2 accumulates plain outer products
         double wq = w * vol / (double)NQ;
-        if constexpr (FORM == FES_FORM_ELASTIC) wq *= m.mu;  // m.mu carries E_e (mu1 is divided out below)
+        if constexpr (FORM == FES_FORM_ELASTIC) wq *= m.mu;
         const double sq = sqrt(wq);
 #pragma unroll
         for (int q = 0; q < NQ; ++q)
@@ -240,50 +236,53 @@ k_assemble_tiles(const int32_t* __restrict__ tile_node0, const int32_t* __restri
             double gn[SD];
             shape_grad<ELEM, SD>(g, q, n, gn);
 #pragma unroll
-            for (int s = 0; s < SD; ++s) rec[((q * N + n) * SD + s) * GS] = sq * gn[s];
+            for (int h = 0; h < SD / 2; ++h)
+              v2[((q * N + n) * (SD / 2) + h) * GS + rec] = make_double2(sq * gn[2 * h], sq * gn[2 * h + 1]);
+            if constexpr (SD & 1) v1[(q * N + n) * GS + rec] = sq * gn[SD - 1];
           }
       }
     }
   }
-  __syncthreads();          // records + s_node_ptr + s_skew visible
-  mbar_wait(&s_bar, 0);     // staged streams have landed
+  __syncthreads();        // records and s_skew visible
+  mbar_wait(&s_bar, 0);   // staged streams have landed
 
-  // ---- phase 2: one thread per stored pair
-  const uint16_t* codes = reinterpret_cast<const uint16_t*>(s_contrib + s_skew[0]);
-  const uint16_t* offs = reinterpret_cast<const uint16_t*>(s_off + s_skew[1]);
-  const uint8_t* lrows = s_lrow + s_skew[2];
-  const uint16_t* perm = reinterpret_cast<const uint16_t*>(s_perm + s_skew[3]);
-  const int n_pairs = p1 - p0;
-  const uint32_t n_contrib = (uint32_t)N * (uint32_t)(g1 - g0);
-  for (int tt_ = threadIdx.x; tt_ < n_pairs; tt_ += kTileThreads) {
-    const int t = perm[tt_];  // pairs in descending contribution count: uniform trip counts per warp
-    const uint32_t k0 = offs[t];
-    const uint32_t k1 = (t + 1 < n_pairs) ? offs[t + 1] : n_contrib;
+  // ---- phase 2: one thread per active pair
+  const uint16_t* codes = reinterpret_cast<const uint16_t*>(s_code + s_skew);
+  for (int t = threadIdx.x; t < n_act; t += kTileThreads) {
+    const uint4 mt = s_meta[t];
+    const uint32_t k0 = mt.x & 0xffffu, cnt = (mt.x >> 16) & 0xffu;
+    const bool diag = (mt.x >> 24) & 1u;
     double acc[C][C];
 #pragma unroll
     for (int i = 0; i < C; ++i)
 #pragma unroll
       for (int j = 0; j < C; ++j) acc[i][j] = 0.0;
-    for (uint32_t k = k0; k < k1; ++k) {
+    for (uint32_t k = k0; k < k0 + cnt; ++k) {
       const uint32_t code = codes[k];
       const int a = (code >> 3) & 7, b = code & 7;
-      const double* rec = smem + (code >> 6);
+      const int rec = code >> 6;
       if constexpr (FORM == FES_FORM_MASS) {
-        acc[0][0] = fma(rec[0], mass_ref<ELEM>(a, b), acc[0][0]);
+        acc[0][0] = fma(v1[rec], mass_ref<ELEM>(a, b), acc[0][0]);
       } else {
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-          const double* ga = rec + (q * N + a) * SD * GS;
           double A_[SD], B_[SD];
 #pragma unroll
-          for (int s = 0; s < SD; ++s) A_[s] = ga[s * GS];
-          if (a == b) {  // a diagonal pair: one gradient serves both sides
+          for (int h = 0; h < SD / 2; ++h) {
+            const double2 t2 = v2[((q * N + a) * (SD / 2) + h) * GS + rec];
+            A_[2 * h] = t2.x; A_[2 * h + 1] = t2.y;
+          }
+          if constexpr (SD & 1) A_[SD - 1] = v1[(q * N + a) * GS + rec];
+          if (a == b) {
 #pragma unroll
             for (int s = 0; s < SD; ++s) B_[s] = A_[s];
           } else {
-            const double* gb = rec + (q * N + b) * SD * GS;
 #pragma unroll
-            for (int s = 0; s < SD; ++s) B_[s] = gb[s * GS];
+            for (int h = 0; h < SD / 2; ++h) {
+              const double2 t2 = v2[((q * N + b) * (SD / 2) + h) * GS + rec];
+              B_[2 * h] = t2.x; B_[2 * h + 1] = t2.y;
+            }
+            if constexpr (SD & 1) B_[SD - 1] = v1[(q * N + b) * GS + rec];
           }
           if constexpr (FORM == FES_FORM_LAPLACIAN) {
 #pragma unroll
@@ -297,37 +296,47 @@ k_assemble_tiles(const int32_t* __restrict__ tile_node0, const int32_t* __restri
         }
       }
     }
+    double K[C][C];
     if constexpr (FORM == FES_FORM_ELASTIC) {
-      // K = (lam/mu) S + S^T + tr(S) I, in units where the stored gradients carry mu_e w_q
       double tr = 0.0;
 #pragma unroll
       for (int i = 0; i < C; ++i) tr += acc[i][i];
-      double K[C][C];
 #pragma unroll
       for (int i = 0; i < C; ++i)
 #pragma unroll
-        for (int j = 0; j < C; ++j) K[i][j] = fma(cf.lam_over_mu, acc[i][j], acc[j][i]) + (i == j ? tr : 0.0);
-#pragma unroll
-      for (int i = 0; i < C; ++i)
-#pragma unroll
-        for (int j = 0; j < C; ++j) acc[i][j] = cf.sign * K[i][j];
+        for (int j = 0; j < C; ++j)
+          K[i][j] = cf.sign * (fma(cf.lam_over_mu, acc[i][j], acc[j][i]) + (i == j ? tr : 0.0));
     } else if constexpr (FORM == FES_FORM_LAPLACIAN) {
-      acc[0][0] *= cf.sign;
+      K[0][0] = cf.sign * acc[0][0];
+    } else {
+#pragma unroll
+      for (int i = 0; i < C; ++i)
+#pragma unroll
+        for (int j = 0; j < C; ++j) K[i][j] = (i == j) ? acc[0][0] : 0.0;
     }
-    const int l = lrows[t];
-    const int32_t np0 = s_node_ptr[l], deg = s_node_ptr[l + 1] - np0, s = p0 + t - np0;
-    double* out = values + (int64_t)C * C * np0 + (int64_t)C * s;
+    // row i of a block starts at C * (q0 + i * deg); the block of (w, v) is K^T
+    const int64_t q_own = mt.y, q_mir = mt.z;
+    const int64_t deg_own = mt.w & 0xffffu, deg_mir = mt.w >> 16;
 #pragma unroll
     for (int i = 0; i < C; ++i) {
-      double* row = out + (int64_t)i * C * deg;
-      if constexpr (FORM == FES_FORM_MASS) {
-#pragma unroll
-        for (int j = 0; j < C; ++j) row[j] = (i == j) ? acc[0][0] : 0.0;
-      } else if constexpr (C == 2) {
-        *reinterpret_cast<double2*>(row) = make_double2(acc[i][0], acc[i][1]);
+      double* row = values + (int64_t)C * (q_own + i * deg_own);
+      if constexpr (C == 2) {
+        *reinterpret_cast<double2*>(row) = make_double2(K[i][0], K[i][1]);
       } else {
 #pragma unroll
-        for (int j = 0; j < C; ++j) row[j] = acc[i][j];
+        for (int j = 0; j < C; ++j) row[j] = K[i][j];
+      }
+    }
+    if (!diag) {
+#pragma unroll
+      for (int i = 0; i < C; ++i) {
+        double* row = values + (int64_t)C * (q_mir + i * deg_mir);
+        if constexpr (C == 2) {
+          *reinterpret_cast<double2*>(row) = make_double2(K[0][i], K[1][i]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < C; ++j) row[j] = K[j][i];
+        }
       }
     }
   }
@@ -395,9 +404,9 @@ int run(const Job& j) {
     const fes_plan* P = j.plan;
     if (P->n_pairs == 0) return FES_OK;
     if (P->tiled && !j.untiled) {
-      const size_t smem = TileSmem<ELEM, FORM, C, SD>::total(P->geo_max, P->pair_max);
+      const size_t smem = TileSmem<ELEM, FORM, C, SD>::total(P->geo_max, P->act_max, P->con_max);
       static size_t configured = 0;  // per template instantiation: largest opt-in so far
-      if (smem + 2048 > 48 * 1024 && smem > configured) {  // static smem counts toward the 48 KB default
+      if (smem + 1024 > 48 * 1024 && smem > configured) {  // static smem counts toward the 48 KB default
         FES_CUDA(cudaFuncSetAttribute(k_assemble_tiles<ELEM, FORM, C, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
         configured = smem;
@@ -405,8 +414,8 @@ int run(const Job& j) {
       Coeffs cf = j.cf;
       if (FORM != FES_FORM_MASS && cf.factor < 0.0) { cf.factor = -cf.factor; cf.sign = -1.0; }
       k_assemble_tiles<ELEM, FORM, C, SD><<<(unsigned)P->n_tiles, kTileThreads, smem, j.stream>>>(
-          P->tile_node0.p, P->ne_ptr.p, P->ne_code.p, P->node_ptr.p, P->pair_off16.p, P->pair_lrow.p,
-          P->pair_perm16.p, P->contrib16.p, j.en, j.coords, cf, P->geo_max, P->pair_max, j.out);
+          P->tile_node0.p, P->ne_ptr.p, P->ne_code.p, P->tile_act0.p, P->tile_con0.p, P->act_meta.p, P->act_codes.p,
+          j.en, j.coords, cf, P->geo_max, P->act_max, j.out);
     } else {
       k_assemble_pairs<ELEM, FORM, C, SD><<<grid_for(P->n_pairs, kBlock), kBlock, 0, j.stream>>>(
           P->n_pairs, P->pair_start.p, P->pair_row.p, P->node_ptr.p, P->contrib.p, P->indptr.p, j.en, j.coords, j.cf,

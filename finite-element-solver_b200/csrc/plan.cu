@@ -12,6 +12,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -115,8 +117,7 @@ __global__ void k_tile_codes(const int32_t* __restrict__ pair_row, const uint32_
                              const uint32_t* __restrict__ contrib, int64_t n_pairs, int N,
                              const int32_t* __restrict__ ne_ptr, const uint32_t* __restrict__ ne_code,
                              const int32_t* __restrict__ tile_node0, int64_t n_tiles,
-                             uint16_t* __restrict__ contrib16, uint16_t* __restrict__ pair_off16,
-                             uint8_t* __restrict__ pair_lrow) {
+                             uint16_t* __restrict__ contrib16, uint8_t* __restrict__ pair_lrow) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_pairs) return;
   const int32_t v = pair_row[p];
@@ -130,7 +131,6 @@ __global__ void k_tile_codes(const int32_t* __restrict__ pair_row, const uint32_
   const int N2 = N * N;
   pair_lrow[p] = (uint8_t)(v - v0);
   const uint32_t k0 = pair_start[p], k1 = pair_start[p + 1];
-  pair_off16[p] = (uint16_t)(k0 - (uint32_t)N * (uint32_t)g0);
   for (uint32_t k = k0; k < k1; ++k) {
     const uint32_t code = contrib[k], e = code / N2, ab = code - e * N2, a = ab / N, b = ab - a * N;
     int32_t l = gv0, h = gv1;  // lower_bound of e in v's ascending incident list
@@ -142,24 +142,70 @@ __global__ void k_tile_codes(const int32_t* __restrict__ pair_row, const uint32_
   }
 }
 
-// Tile-local pair order sorted by contribution count (descending, stable) so the 32 pairs a warp
-// gathers have equal trip counts: a diagonal pair collects one contribution per incident element
-// (4-8 on a triangle mesh, ~24 on a tet mesh), an off-diagonal pair one per element on the edge.
-__global__ void k_tile_perm(const int32_t* __restrict__ tile_node0, int64_t n_tiles,
-                            const int32_t* __restrict__ node_ptr, const uint32_t* __restrict__ pair_start,
-                            uint16_t* __restrict__ perm) {
+// Active pairs of a tile (w >= v): count them and their contributions; flag anything the packed
+// metadata cannot hold.
+__global__ void k_tile_count(const int32_t* __restrict__ tile_node0, int64_t n_tiles,
+                             const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ node_adj,
+                             const int32_t* __restrict__ pair_row, const uint32_t* __restrict__ pair_start,
+                             int32_t* __restrict__ act_cnt, int32_t* __restrict__ con_cnt, int* __restrict__ bad) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const int32_t p0 = node_ptr[tile_node0[t]], p1 = node_ptr[tile_node0[t + 1]];
+  int32_t na = 0, nc = 0;
+  for (int32_t p = p0; p < p1; ++p) {
+    if (node_adj[p] < pair_row[p]) continue;
+    const uint32_t c = pair_start[p + 1] - pair_start[p];
+    if (c > 255u) atomicExch(bad, 1);
+    ++na;
+    nc += (int32_t)c;
+  }
+  if (nc > 65535) atomicExch(bad, 1);
+  act_cnt[t] = na;
+  con_cnt[t] = nc;
+}
+
+// Emit a tile's active pairs in descending contribution count (stable), so the 32 pairs a warp
+// gathers have equal trip counts, with their packed metadata and their contribution codes.
+__global__ void k_tile_active(const int32_t* __restrict__ tile_node0, int64_t n_tiles,
+                              const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ node_adj,
+                              const int32_t* __restrict__ pair_row, const uint32_t* __restrict__ pair_start,
+                              const uint16_t* __restrict__ contrib16, const int32_t* __restrict__ tile_act0,
+                              const int32_t* __restrict__ tile_con0, int c, uint4* __restrict__ meta,
+                              uint16_t* __restrict__ codes) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
   const int32_t p0 = node_ptr[tile_node0[t]], p1 = node_ptr[tile_node0[t + 1]];
   uint32_t hi = 0;
-  for (int32_t p = p0; p < p1; ++p) hi = max(hi, pair_start[p + 1] - pair_start[p]);
-  int32_t w = p0;
+  for (int32_t p = p0; p < p1; ++p)
+    if (node_adj[p] >= pair_row[p]) hi = max(hi, pair_start[p + 1] - pair_start[p]);
+  int32_t wa = tile_act0[t];
+  const int32_t con_base = tile_con0[t];
+  uint32_t off = 0;
   while (hi > 0) {
     uint32_t next = 0;
     for (int32_t p = p0; p < p1; ++p) {
-      const uint32_t c = pair_start[p + 1] - pair_start[p];
-      if (c == hi) perm[w++] = (uint16_t)(p - p0);
-      else if (c < hi) next = max(next, c);
+      const int32_t v = pair_row[p], w = node_adj[p];
+      if (w < v) continue;
+      const uint32_t k0 = pair_start[p], cnt = pair_start[p + 1] - k0;
+      if (cnt == hi) {
+        const int32_t npv = node_ptr[v], degv = node_ptr[v + 1] - npv;
+        const int32_t npw = node_ptr[w], degw = node_ptr[w + 1] - npw;
+        int32_t lo_ = npw, hi_ = npw + degw;  // slot of v in row w (the pattern is symmetric)
+        while (lo_ < hi_) {
+          const int32_t m = (lo_ + hi_) >> 1;
+          if (node_adj[m] < v) lo_ = m + 1; else hi_ = m;
+        }
+        uint4 mt;
+        mt.x = off | (cnt << 16) | ((w == v ? 1u : 0u) << 24);
+        mt.y = (uint32_t)c * (uint32_t)npv + (uint32_t)(p - npv);
+        mt.z = (uint32_t)c * (uint32_t)npw + (uint32_t)(lo_ - npw);
+        mt.w = (uint32_t)degv | ((uint32_t)degw << 16);
+        meta[wa++] = mt;
+        for (uint32_t k = 0; k < cnt; ++k) codes[con_base + off + k] = contrib16[k0 + k];
+        off += cnt;
+      } else if (cnt < hi) {
+        next = max(next, cnt);
+      }
     }
     hi = next;
   }
@@ -178,7 +224,7 @@ int bits_for(uint64_t max_value) {
 
 // Tile the node range for the fused assembly kernel.  The greedy split runs on the host over the
 // two prefix arrays (O(n_nodes), once per mesh); everything else stays on the device.
-int build_tiles(fes_plan* P, cudaStream_t stream) {
+int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream) {
   const int64_t nn = P->n_nodes, np_ = P->n_pairs;
   const int N = P->N;
   P->tiled = false;
@@ -217,9 +263,6 @@ int build_tiles(fes_plan* P, cudaStream_t stream) {
   }
   tiles.push_back((int32_t)nn);
   P->n_tiles = (int64_t)tiles.size() - 1;
-  int pmax = 0;
-  for (size_t t = 0; t + 1 < tiles.size(); ++t) pmax = std::max(pmax, (int)(h_np[tiles[t + 1]] - h_np[tiles[t]]));
-  P->pair_max = pmax;
   FES_CUDA(P->tile_node0.alloc(tiles.size()));
   FES_CUDA(cudaMemcpyAsync(P->tile_node0.p, tiles.data(), tiles.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
   FES_CUDA(P->ne_code.alloc(P->n_geo));
@@ -227,15 +270,53 @@ int build_tiles(fes_plan* P, cudaStream_t stream) {
                                                           N, P->ne_ptr.p, P->ne_code.p);
   FES_LAUNCH_CHECK();
   FES_CUDA(P->contrib16.alloc(P->n_contrib + 16));
-  FES_CUDA(P->pair_off16.alloc(np_ + 16));
   FES_CUDA(P->pair_lrow.alloc(np_ + 32));
   k_tile_codes<<<grid_for(np_, kBlock), kBlock, 0, stream>>>(P->pair_row.p, P->pair_start.p, P->contrib.p, np_, N,
                                                              P->ne_ptr.p, P->ne_code.p, P->tile_node0.p, P->n_tiles,
-                                                             P->contrib16.p, P->pair_off16.p, P->pair_lrow.p);
+                                                             P->contrib16.p, P->pair_lrow.p);
   FES_LAUNCH_CHECK();
-  FES_CUDA(P->pair_perm16.alloc(np_ + 16));
-  k_tile_perm<<<grid_for(P->n_tiles, 64), 64, 0, stream>>>(P->tile_node0.p, P->n_tiles, P->node_ptr.p, P->pair_start.p,
-                                                         P->pair_perm16.p);
+
+  // active pairs (w >= v) per tile: counts -> offsets -> sorted emission with packed metadata
+  const int64_t nt = P->n_tiles;
+  DevBuf<int32_t> act_cnt, con_cnt;
+  DevBuf<int> bad;
+  FES_CUDA(act_cnt.alloc(nt + 1)); FES_CUDA(con_cnt.alloc(nt + 1)); FES_CUDA(bad.alloc(1));
+  FES_CUDA(cudaMemsetAsync(act_cnt.p, 0, act_cnt.bytes(), stream));
+  FES_CUDA(cudaMemsetAsync(con_cnt.p, 0, con_cnt.bytes(), stream));
+  FES_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), stream));
+  k_tile_count<<<grid_for(nt, 64), 64, 0, stream>>>(P->tile_node0.p, nt, P->node_ptr.p, P->node_adj.p, P->pair_row.p,
+                                                    P->pair_start.p, act_cnt.p, con_cnt.p, bad.p);
+  FES_LAUNCH_CHECK();
+  FES_CUDA(P->tile_act0.alloc(nt + 1));
+  FES_CUDA(P->tile_con0.alloc(nt + 1));
+  size_t sb = 0;
+  FES_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, sb, act_cnt.p, P->tile_act0.p, nt + 1, stream));
+  if (sb > tmp.bytes()) FES_CUDA(tmp.alloc(sb));
+  FES_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, sb, act_cnt.p, P->tile_act0.p, nt + 1, stream));
+  FES_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, sb, con_cnt.p, P->tile_con0.p, nt + 1, stream));
+  count_launch(4);
+  std::vector<int32_t> h_act(nt + 1), h_con(nt + 1);
+  int h_bad = 0;
+  FES_CUDA(cudaMemcpyAsync(h_act.data(), P->tile_act0.p, (nt + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  FES_CUDA(cudaMemcpyAsync(h_con.data(), P->tile_con0.p, (nt + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  FES_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  FES_CUDA(cudaStreamSynchronize(stream));
+  if (h_bad) return FES_OK;  // a pair shared by > 255 elements: keep the untiled kernel
+  P->n_active = h_act[nt];
+  P->n_act_contrib = h_con[nt];
+  int amax = 0, cmax = 0, dmax = 0;
+  for (int64_t t = 0; t < nt; ++t) {
+    amax = std::max(amax, h_act[t + 1] - h_act[t]);
+    cmax = std::max(cmax, h_con[t + 1] - h_con[t]);
+  }
+  for (int64_t v = 0; v < nn; ++v) dmax = std::max(dmax, h_np[v + 1] - h_np[v]);
+  if (dmax > 65535) return FES_OK;
+  P->act_max = amax; P->con_max = cmax;
+  FES_CUDA(P->act_meta.alloc(P->n_active + 4));
+  FES_CUDA(P->act_codes.alloc(P->n_act_contrib + 16));
+  k_tile_active<<<grid_for(nt, 64), 64, 0, stream>>>(P->tile_node0.p, nt, P->node_ptr.p, P->node_adj.p, P->pair_row.p,
+                                                     P->pair_start.p, P->contrib16.p, P->tile_act0.p, P->tile_con0.p,
+                                                     P->c, P->act_meta.p, P->act_codes.p);
   FES_LAUNCH_CHECK();
   FES_CUDA(cudaStreamSynchronize(stream));
   P->tiled = true;
@@ -348,7 +429,7 @@ extern "C" int fes_plan_create(const int32_t* d_elem_nodes, int64_t n_el, int N,
                                                                      n_pairs, n_comp, P->indices.p);
   FES_LAUNCH_CHECK();
   FES_CUDA(cudaStreamSynchronize(stream));
-  FES_TRY(build_tiles(P, stream));
+  FES_TRY(build_tiles(P, d_elem_nodes, stream));
   guard.p = nullptr;
   *out = P;
   return FES_OK;
@@ -365,16 +446,16 @@ extern "C" int64_t fes_plan_bytes(const fes_plan* p) {
   if (!p) return 0;
   return (int64_t)(p->node_ptr.bytes() + p->node_adj.bytes() + p->pair_row.bytes() + p->pair_start.bytes() +
                    p->contrib.bytes() + p->indptr.bytes() + p->indices.bytes() + p->ne_ptr.bytes() +
-                   p->ne_code.bytes() + p->tile_node0.bytes() + p->contrib16.bytes() + p->pair_off16.bytes() +
-                   p->pair_lrow.bytes() + p->pair_perm16.bytes());
+                   p->ne_code.bytes() + p->tile_node0.bytes() + p->tile_act0.bytes() + p->tile_con0.bytes() +
+                   p->act_meta.bytes() + p->act_codes.bytes() + p->contrib16.bytes() + p->pair_lrow.bytes());
 }
 
 // what one fused assembly streams from the plan (overhead on top of the algorithmic bytes)
 extern "C" int64_t fes_plan_read_bytes(const fes_plan* p) {
   if (!p) return 0;
   if (p->tiled)
-    return (int64_t)(p->ne_ptr.bytes() + p->ne_code.bytes() + p->tile_node0.bytes() + p->contrib16.bytes() +
-                     p->pair_off16.bytes() + p->pair_lrow.bytes() + p->pair_perm16.bytes() + p->node_ptr.bytes());
+    return (int64_t)(p->ne_ptr.bytes() + p->ne_code.bytes() + p->tile_node0.bytes() + p->tile_act0.bytes() +
+                     p->tile_con0.bytes() + p->act_meta.bytes() + p->act_codes.bytes() + p->node_ptr.bytes());
   return (int64_t)(p->pair_row.bytes() + p->pair_start.bytes() + p->contrib.bytes() + p->node_ptr.bytes() +
                    p->indptr.bytes());
 }

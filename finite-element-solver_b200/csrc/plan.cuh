@@ -20,18 +20,24 @@ struct fes_plan {
   // ---- tiled layout for the fused assembly kernel ------------------------------------------
   // A tile is a run of consecutive nodes whose (node, incident element) records fit in shared
   // memory.  Phase 1 of the kernel evaluates one geometry record per (node, element); phase 2
-  // gathers each pair's contributions from those records.
+  // gathers the contributions of the tile's ACTIVE pairs -- pairs (v, w) with w >= v; the block of
+  // (w, v) is the transpose and is written by the same thread.
   bool tiled = false;
-  int64_t n_tiles = 0, n_geo = 0;
+  int64_t n_tiles = 0, n_geo = 0, n_active = 0, n_act_contrib = 0;
   int geo_max = 0;                     // records per tile upper bound
-  int pair_max = 0;                    // stored pairs per tile upper bound
+  int act_max = 0, con_max = 0;        // active pairs / their contributions per tile, upper bounds
   fes::DevBuf<int32_t> ne_ptr;         // n_nodes + 1 : incident-element ranges per node
   fes::DevBuf<uint32_t> ne_code;       // n_geo : e*8 + a, ascending e per node
   fes::DevBuf<int32_t> tile_node0;     // n_tiles + 1
-  fes::DevBuf<uint16_t> contrib16;     // n_contrib : (record index in tile)<<6 | a<<3 | b
-  fes::DevBuf<uint16_t> pair_off16;    // n_pairs : first contribution, relative to the tile's first
-  fes::DevBuf<uint8_t> pair_lrow;      // n_pairs : row node, relative to the tile's first node
-  fes::DevBuf<uint16_t> pair_perm16;   // n_pairs : tile-local pair order, by contribution count descending
+  fes::DevBuf<int32_t> tile_act0;      // n_tiles + 1 : active-pair ranges
+  fes::DevBuf<int32_t> tile_con0;      // n_tiles + 1 : ranges in act_codes
+  fes::DevBuf<uint4> act_meta;         // n_active : per active pair, in descending contribution count per tile:
+                                       //   x = off16 | cnt8<<16 | diag<<24, y = q0 own, z = q0 mirror,
+                                       //   w = deg own | deg mirror<<16;  row i of a block starts at C*(q0 + i*deg)
+  fes::DevBuf<uint16_t> act_codes;     // n_act_contrib : (record index in tile)<<6 | a<<3 | b, ascending element id
+  // build-time only (kept for k_assemble_precomputed and the untiled fallback): see above
+  fes::DevBuf<uint16_t> contrib16;     // n_contrib : tile-relative codes in pair order
+  fes::DevBuf<uint8_t> pair_lrow;      // n_pairs : row node relative to the tile's first node
 
   // staging for the host-buffer entry point (fes_assemble_host), allocated on first use
   mutable fes::DevBuf<double> stage_coords, stage_values, stage_E, stage_scale;
@@ -41,10 +47,10 @@ namespace fes {
 // records per tile for an element with N nodes (sized for the largest record, elasticity)
 inline int tile_geo_budget(int N) {
   switch (N) {
-    case 2: return 512;
-    case 3: return 512;    // 3-node: P1 triangle (8 doubles -> 32 KB) or P2 line
-    case 4: return 384;    // P1 tet (14 doubles -> 42 KB)
-    default: return 160;   // P2 triangle (38 doubles -> 48 KB)
+    case 2: return 256;
+    case 3: return 256;    // 3-node: P1 triangle (6 doubles -> 12 KB) or P2 line
+    case 4: return 256;    // P1 tet (12 doubles -> 24 KB)
+    default: return 128;   // P2 triangle (36 doubles -> 36 KB)
   }
 }
 }  // namespace fes

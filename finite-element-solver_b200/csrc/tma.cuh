@@ -39,6 +39,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// shared -> global bulk copy (SASS UBLKCP.G.S); both 16-byte aligned, bytes a multiple of 16.  The
+// generic-proxy writes to shared memory must be fenced into the async proxy first.
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // A stream of `count` elements of size ES starting at element i0 of `base`, staged with one bulk
 // copy from the enclosing 16-byte aligned window.  Returns the byte skew of element i0 inside
 // the window; the caller reads dst + skew.  Arrays are allocated with 32 bytes of tail padding.
