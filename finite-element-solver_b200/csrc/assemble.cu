@@ -10,6 +10,8 @@
 // result is deterministic; element matrices never exist in HBM.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "elements.cuh"
 #include "plan.cuh"
 #include "tma.cuh"
@@ -136,82 +138,131 @@ struct RecLayout {
 constexpr int kTileThreads = 128;
 constexpr int kRecBatch = 2;  // records a thread evaluates per pass of phase 1 (memory-level parallelism)
 
+// shared-memory carve-up: geometry records and node coordinates (one copy), then two copies of
+// the TMA-staged plan streams (double buffering across tiles)
 template <int ELEM, int FORM, int C, int SD>
 struct TileSmem {
   using R = RecLayout<ELEM, FORM, C, SD>;
   __host__ __device__ static size_t rec_bytes(int gmax) { return ((size_t)gmax * R::DOUBLES * 8 + 15) & ~(size_t)15; }
+  __host__ __device__ static size_t xyz_bytes() { return (size_t)256 * SD * 8; }   // distinct-node coordinates
   __host__ __device__ static size_t meta_bytes(int amax) { return (size_t)amax * 16 + 16; }
   __host__ __device__ static size_t code_bytes(int cmax) { return ((size_t)cmax * 2 + 32 + 15) & ~(size_t)15; }
+  __host__ __device__ static size_t nod_bytes() { return (size_t)256 * 4; }        // distinct-node ids
+  __host__ __device__ static size_t loc_bytes(int gmax) { return ((size_t)gmax * 4 + 32 + 15) & ~(size_t)15; }
+  __host__ __device__ static size_t stage_bytes(int gmax, int amax, int cmax) {
+    return meta_bytes(amax) + code_bytes(cmax) + nod_bytes() + loc_bytes(gmax);
+  }
   __host__ __device__ static size_t total(int gmax, int amax, int cmax) {
-    return rec_bytes(gmax) + meta_bytes(amax) + code_bytes(cmax);
+    return rec_bytes(gmax) + xyz_bytes() + 2 * stage_bytes(gmax, amax, cmax);
   }
 };
 
 template <int ELEM, int FORM, int C, int SD>
 __global__ void __launch_bounds__(kTileThreads)
-k_assemble_tiles(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__ ne_ptr,
-                 const uint32_t* __restrict__ ne_code, const int32_t* __restrict__ tile_act0,
-                 const int32_t* __restrict__ tile_con0, const uint4* __restrict__ act_meta,
-                 const uint16_t* __restrict__ act_codes, const int32_t* __restrict__ en,
-                 const double* __restrict__ coords, Coeffs cf, int geo_stride, int act_max,
+k_assemble_tiles(const int4* __restrict__ tile_hdr, int n_tiles, const uint32_t* __restrict__ ne_code,
+                 const uint4* __restrict__ act_meta, const uint16_t* __restrict__ act_codes,
+                 const int32_t* __restrict__ tile_nodes, const uint32_t* __restrict__ rec_local,
+                 const double* __restrict__ coords, Coeffs cf, int geo_stride, int act_max, int con_max,
                  double* __restrict__ values) {
   using R = RecLayout<ELEM, FORM, C, SD>;
   using TS = TileSmem<ELEM, FORM, C, SD>;
   constexpr int N = ET<ELEM>::N, NQ = ET<ELEM>::NQ, RD = ET<ELEM>::RD;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ uint32_t s_skew;
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ uint32_t s_skew[2][2];
   const int GS = geo_stride;
   // planes: v2[plane * GS + record] (double2), then v1[plane * GS + record] (double)
   double2* v2 = reinterpret_cast<double2*>(smem_raw);
   double* v1 = reinterpret_cast<double*>(smem_raw) + (size_t)2 * R::NV2 * GS;
-  const uint4* s_meta = reinterpret_cast<const uint4*>(smem_raw + TS::rec_bytes(GS));
-  unsigned char* s_code = smem_raw + TS::rec_bytes(GS) + TS::meta_bytes(act_max);
+  double* s_xyz = reinterpret_cast<double*>(smem_raw + TS::rec_bytes(GS));
+  unsigned char* stage0 = smem_raw + TS::rec_bytes(GS) + TS::xyz_bytes();
+  const size_t stage_sz = TS::stage_bytes(GS, act_max, con_max);
 
-  const int32_t v0 = tile_node0[blockIdx.x], v1n = tile_node0[blockIdx.x + 1];
-  const int32_t g0 = ne_ptr[v0], g1 = ne_ptr[v1n];
-  const int32_t a0 = tile_act0[blockIdx.x], n_act = tile_act0[blockIdx.x + 1] - a0;
-
-  if (threadIdx.x == 0) {
-    mbar_init(&s_bar, 1);
-    const int32_t c0 = tile_con0[blockIdx.x], n_con = tile_con0[blockIdx.x + 1] - c0;
-    const uint64_t c_begin = (uint64_t)c0 * 2;
-    const uint32_t b_meta = (uint32_t)n_act * 16u;
-    const uint32_t b_code = (uint32_t)(((c_begin & 15) + (uint64_t)n_con * 2 + 15) & ~(uint64_t)15);
-    mbar_arrive_expect_tx(&s_bar, b_meta + b_code);
-    if (b_meta) bulk_g2s(const_cast<uint4*>(s_meta), act_meta + a0, b_meta, &s_bar);
+  // One thread arms the stage's mbarrier and issues four 1-D TMA bulk copies of the tile's
+  // contiguous plan streams; they land while the previous tile is still being computed.
+  auto issue = [&](const int4& h0, const int4& h1, int tile, int buf) {
+    unsigned char* st = stage0 + buf * stage_sz;
+    unsigned char* s_code = st + TS::meta_bytes(act_max);
+    unsigned char* s_nod = s_code + TS::code_bytes(con_max);
+    unsigned char* s_loc = s_nod + TS::nod_bytes();
+    const uint32_t n_rec = (uint32_t)(h0.y - h0.x);
+    const uint32_t b_meta = (uint32_t)h0.w * 16u;
+    const uint32_t b_code = (uint32_t)(((((uint64_t)h1.x * 2) & 15) + (uint64_t)h1.y * 2 + 15) & ~(uint64_t)15);
+    const uint32_t b_nod = ((uint32_t)h1.z * 4u + 15u) & ~15u;
+    const uint32_t b_loc = (uint32_t)(((((uint64_t)h0.x * 4) & 15) + (uint64_t)n_rec * 4 + 15) & ~(uint64_t)15);
+    mbar_arrive_expect_tx(&s_bar[buf], b_meta + b_code + b_nod + b_loc);
     uint32_t t;
-    s_skew = stage_window<2>(s_code, act_codes, (uint32_t)c0, (uint32_t)n_con, &s_bar, t);
-  }
+    if (b_nod) bulk_g2s(s_nod, tile_nodes + (int64_t)tile * fes_plan::kTileNodeStride, b_nod, &s_bar[buf]);
+    s_skew[buf][1] = stage_window<4>(s_loc, rec_local, (uint32_t)h0.x, n_rec, &s_bar[buf], t);
+    if (b_meta) bulk_g2s(st, act_meta + h0.z, b_meta, &s_bar[buf]);
+    s_skew[buf][0] = stage_window<2>(s_code, act_codes, (uint32_t)h1.x, (uint32_t)h1.y, &s_bar[buf], t);
+  };
 
-  // ---- phase 1: geometry records
+  int tile = blockIdx.x;
+  if (tile >= n_tiles) return;
+  int4 h0 = __ldg(tile_hdr + 2 * tile), h1 = __ldg(tile_hdr + 2 * tile + 1);
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    issue(h0, h1, tile, 0);
+  }
+  __syncthreads();
+
+  for (int it = 0; tile < n_tiles; ++it) {
+    const int buf = it & 1;
+    const uint32_t parity = (uint32_t)(it >> 1) & 1u;
+    const int next = tile + (int)gridDim.x;
+    int4 n0 = h0, n1 = h1;
+    if (next < n_tiles) {
+      n0 = __ldg(tile_hdr + 2 * next);
+      n1 = __ldg(tile_hdr + 2 * next + 1);
+      if (threadIdx.x == 0) issue(n0, n1, next, buf ^ 1);  // that stage was last read before the barrier below
+    }
+    const int32_t g0 = h0.x, g1 = h0.y, n_act = h0.w, nd = h1.z;
+    unsigned char* st = stage0 + buf * stage_sz;
+    const uint4* s_meta = reinterpret_cast<const uint4*>(st);
+    unsigned char* s_code = st + TS::meta_bytes(act_max);
+    const int32_t* s_nod = reinterpret_cast<const int32_t*>(s_code + TS::code_bytes(con_max));
+    unsigned char* s_loc = s_code + TS::code_bytes(con_max) + TS::nod_bytes();
+    mbar_wait(&s_bar[buf], parity);  // this tile's plan streams have landed
+
+    // ---- phase 0: coordinates of the tile's distinct nodes, gathered once
+    for (int i = threadIdx.x; i < nd; i += kTileThreads) {
+      const int32_t node = s_nod[i];
+      if constexpr (SD == 2) {
+        reinterpret_cast<double2*>(s_xyz)[i] = __ldg(reinterpret_cast<const double2*>(coords) + node);
+      } else {
+#pragma unroll
+        for (int s = 0; s < SD; ++s) s_xyz[i * SD + s] = __ldg(coords + (int64_t)node * SD + s);
+      }
+    }
+    __syncthreads();
+    const uint32_t* locs = reinterpret_cast<const uint32_t*>(s_loc + s_skew[buf][1]);
+
+  // ---- phase 1: geometry records (corner coordinates come from shared memory)
+  const bool per_elem = cf.d_E != nullptr || cf.d_scale != nullptr;
   for (int32_t base = g0 + threadIdx.x; base < g1; base += kTileThreads * kRecBatch) {
     uint32_t e[kRecBatch];
     bool live[kRecBatch];
+    double X[kRecBatch][RD + 1][SD];
 #pragma unroll
     for (int r = 0; r < kRecBatch; ++r) {
       const int32_t gi = base + r * kTileThreads;
       live[r] = gi < g1;
-      e[r] = live[r] ? (__ldg(ne_code + gi) >> 3) : 0u;
-    }
-    int32_t ids[kRecBatch][RD + 1];
-#pragma unroll
-    for (int r = 0; r < kRecBatch; ++r)
-#pragma unroll
-      for (int n = 0; n <= RD; ++n) ids[r][n] = live[r] ? __ldg(en + (int64_t)e[r] * N + n) : 0;
-    double X[kRecBatch][RD + 1][SD];
-#pragma unroll
-    for (int r = 0; r < kRecBatch; ++r)
+      e[r] = (live[r] && per_elem) ? (__ldg(ne_code + gi) >> 3) : 0u;
+      const uint32_t loc = live[r] ? locs[gi - g0] : 0u;
 #pragma unroll
       for (int n = 0; n <= RD; ++n) {
+        const int li = (loc >> (8 * n)) & 255;
         if constexpr (SD == 2) {
-          const double2 xy = __ldg(reinterpret_cast<const double2*>(coords) + ids[r][n]);
+          const double2 xy = reinterpret_cast<const double2*>(s_xyz)[li];
           X[r][n][0] = xy.x; X[r][n][1] = xy.y;
         } else {
 #pragma unroll
-          for (int s = 0; s < SD; ++s) X[r][n][s] = __ldg(coords + (int64_t)ids[r][n] * SD + s);
+          for (int s = 0; s < SD; ++s) X[r][n][s] = s_xyz[li * SD + s];
         }
       }
+    }
 #pragma unroll
     for (int r = 0; r < kRecBatch; ++r) {
       if (!live[r]) continue;
@@ -243,11 +294,10 @@ k_assemble_tiles(const int32_t* __restrict__ tile_node0, const int32_t* __restri
       }
     }
   }
-  __syncthreads();        // records and s_skew visible
-  mbar_wait(&s_bar, 0);   // staged streams have landed
+  __syncthreads();        // records visible
 
   // ---- phase 2: one thread per active pair
-  const uint16_t* codes = reinterpret_cast<const uint16_t*>(s_code + s_skew);
+  const uint16_t* codes = reinterpret_cast<const uint16_t*>(s_code + s_skew[buf][0]);
   for (int t = threadIdx.x; t < n_act; t += kTileThreads) {
     const uint4 mt = s_meta[t];
     const uint32_t k0 = mt.x & 0xffffu, cnt = (mt.x >> 16) & 0xffu;
@@ -340,6 +390,11 @@ k_assemble_tiles(const int32_t* __restrict__ tile_node0, const int32_t* __restri
       }
     }
   }
+    __syncthreads();  // records, coordinates and this stage are free for reuse
+    tile = next;
+    h0 = n0;
+    h1 = n1;
+  }
 }
 
 // PrecomputedForm: gather caller-supplied (n_el, K, K) matrices, optionally scaled per element
@@ -413,9 +468,19 @@ int run(const Job& j) {
       }
       Coeffs cf = j.cf;
       if (FORM != FES_FORM_MASS && cf.factor < 0.0) { cf.factor = -cf.factor; cf.sign = -1.0; }
-      k_assemble_tiles<ELEM, FORM, C, SD><<<(unsigned)P->n_tiles, kTileThreads, smem, j.stream>>>(
-          P->tile_node0.p, P->ne_ptr.p, P->ne_code.p, P->tile_act0.p, P->tile_con0.p, P->act_meta.p, P->act_codes.p,
-          j.en, j.coords, cf, P->geo_max, P->act_max, j.out);
+      static int per_sm = 0, sms = 0;  // per template instantiation
+      if (per_sm == 0 || smem > configured) {
+        int dev = 0;
+        FES_CUDA(cudaGetDevice(&dev));
+        FES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        FES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_tiles<ELEM, FORM, C, SD>,
+                                                               kTileThreads, smem));
+        if (per_sm < 1) return set_error(FES_ERR_CUDA, "assembly kernel does not fit on an SM (%zu B smem)", smem);
+      }
+      const int64_t grid = std::min<int64_t>(P->n_tiles, (int64_t)sms * per_sm);  // persistent CTAs
+      k_assemble_tiles<ELEM, FORM, C, SD><<<(unsigned)grid, kTileThreads, smem, j.stream>>>(
+          reinterpret_cast<const int4*>(P->tile_hdr.p), (int)P->n_tiles, P->ne_code.p, P->act_meta.p, P->act_codes.p,
+          P->tile_nodes.p, P->rec_local.p, j.coords, cf, P->geo_max, P->act_max, P->con_max, j.out);
     } else {
       k_assemble_pairs<ELEM, FORM, C, SD><<<grid_for(P->n_pairs, kBlock), kBlock, 0, j.stream>>>(
           P->n_pairs, P->pair_start.p, P->pair_row.p, P->node_ptr.p, P->contrib.p, P->indptr.p, j.en, j.coords, j.cf,

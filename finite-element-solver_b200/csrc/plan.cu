@@ -211,6 +211,69 @@ __global__ void k_tile_active(const int32_t* __restrict__ tile_node0, int64_t n_
   }
 }
 
+// One CTA per tile: collect the corner nodes of the tile's records, sort them (bitonic, shared
+// memory), keep the distinct ones, and re-express every record's corners as indices into that list.
+constexpr int kTileIdCap = 1024;  // records per tile (<= 256) x corner nodes (<= 4)
+__global__ void __launch_bounds__(256)
+k_tile_nodes(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__ ne_ptr,
+             const uint32_t* __restrict__ ne_code, const int32_t* __restrict__ en, int N, int n_corner,
+             int32_t* __restrict__ tile_nodes, int32_t* __restrict__ tile_nnod, uint32_t* __restrict__ rec_local,
+             int* __restrict__ bad) {
+  __shared__ uint32_t ids[kTileIdCap];
+  __shared__ uint32_t uniq[kTileIdCap];
+  __shared__ int s_count;
+  const int t = blockIdx.x;
+  const int32_t g0 = ne_ptr[tile_node0[t]], g1 = ne_ptr[tile_node0[t + 1]];
+  const int n_ids = (g1 - g0) * n_corner;
+  for (int i = threadIdx.x; i < kTileIdCap; i += blockDim.x) {
+    uint32_t v = 0xffffffffu;
+    if (i < n_ids) {
+      const int r = i / n_corner, k = i - r * n_corner;
+      v = (uint32_t)en[(int64_t)(ne_code[g0 + r] >> 3) * N + k];
+    }
+    ids[i] = v;
+  }
+  __syncthreads();
+  for (int k = 2; k <= kTileIdCap; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < kTileIdCap; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const uint32_t a = ids[i], b = ids[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { ids[i] = b; ids[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  if (threadIdx.x == 0) {  // <= 1024 entries: a serial compaction is cheap next to the sort
+    int c = 0;
+    for (int i = 0; i < n_ids; ++i)
+      if (i == 0 || ids[i] != ids[i - 1]) uniq[c++] = ids[i];
+    s_count = c;
+    tile_nnod[t] = c;
+    if (c > 255) atomicExch(bad, 1);
+  }
+  __syncthreads();
+  const int nd = s_count;
+  if (nd > 255) return;
+  for (int i = threadIdx.x; i < nd; i += blockDim.x) tile_nodes[(int64_t)t * fes_plan::kTileNodeStride + i] = (int32_t)uniq[i];
+  for (int r = threadIdx.x; r < g1 - g0; r += blockDim.x) {
+    const int64_t e = ne_code[g0 + r] >> 3;
+    uint32_t packed = 0;
+    for (int k = 0; k < n_corner; ++k) {
+      const uint32_t node = (uint32_t)en[e * N + k];
+      int lo = 0, hi = nd;
+      while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        if (uniq[m] < node) lo = m + 1; else hi = m;
+      }
+      packed |= (uint32_t)lo << (8 * k);
+    }
+    rec_local[g0 + r] = packed;
+  }
+}
+
 __global__ void k_widen(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) out[t] = in[t];
@@ -224,7 +287,8 @@ int bits_for(uint64_t max_value) {
 
 // Tile the node range for the fused assembly kernel.  The greedy split runs on the host over the
 // two prefix arrays (O(n_nodes), once per mesh); everything else stays on the device.
-int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream) {
+int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, int gmax, bool* retry) {
+  *retry = false;
   const int64_t nn = P->n_nodes, np_ = P->n_pairs;
   const int N = P->N;
   P->tiled = false;
@@ -248,7 +312,6 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream) {
   P->n_geo = h_ne[nn];
   if (P->n_geo != P->n_el * N) return FES_OK;  // degenerate elements (repeated nodes): keep the untiled kernel
   if (P->n_el >= ((int64_t)1 << 29)) return FES_OK;
-  const int gmax = tile_geo_budget(N);
   P->geo_max = gmax;
   std::vector<int32_t> tiles;
   tiles.push_back(0);
@@ -318,7 +381,36 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream) {
                                                      P->pair_start.p, P->contrib16.p, P->tile_act0.p, P->tile_con0.p,
                                                      P->c, P->act_meta.p, P->act_codes.p);
   FES_LAUNCH_CHECK();
+
+  // distinct nodes per tile + local corner indices per record
+  P->n_corner = (N == 6) ? 3 : N;
+  if (gmax * P->n_corner > kTileIdCap) return FES_OK;
+  FES_CUDA(P->tile_nodes.alloc((size_t)nt * fes_plan::kTileNodeStride + 64));
+  FES_CUDA(P->tile_nnod.alloc(nt + 1));
+  FES_CUDA(P->rec_local.alloc(P->n_geo + 16));
+  FES_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), stream));
+  k_tile_nodes<<<(unsigned)nt, 256, 0, stream>>>(P->tile_node0.p, P->ne_ptr.p, P->ne_code.p, d_elem_nodes, N, P->n_corner,
+                                                 P->tile_nodes.p, P->tile_nnod.p, P->rec_local.p, bad.p);
+  FES_LAUNCH_CHECK();
+  FES_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
   FES_CUDA(cudaStreamSynchronize(stream));
+  if (h_bad) {  // a tile touches > 255 distinct nodes (scattered node numbering): retry with smaller tiles
+    *retry = true;
+    return FES_OK;
+  }
+  // packed tile headers: {g0, g1, a0, n_act}, {c0, n_con, n_distinct_nodes, v0}
+  {
+    std::vector<int32_t> h_nnod(nt);
+    FES_CUDA(cudaMemcpy(h_nnod.data(), P->tile_nnod.p, nt * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> hdr((size_t)nt * 8);
+    for (int64_t t = 0; t < nt; ++t) {
+      int32_t* h = hdr.data() + t * 8;
+      h[0] = h_ne[tiles[t]]; h[1] = h_ne[tiles[t + 1]]; h[2] = h_act[t]; h[3] = h_act[t + 1] - h_act[t];
+      h[4] = h_con[t]; h[5] = h_con[t + 1] - h_con[t]; h[6] = h_nnod[t]; h[7] = tiles[t];
+    }
+    FES_CUDA(P->tile_hdr.alloc(hdr.size() + 16));
+    FES_CUDA(cudaMemcpy(P->tile_hdr.p, hdr.data(), hdr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
   P->tiled = true;
   return FES_OK;
 }
@@ -429,7 +521,19 @@ extern "C" int fes_plan_create(const int32_t* d_elem_nodes, int64_t n_el, int N,
                                                                      n_pairs, n_comp, P->indices.p);
   FES_LAUNCH_CHECK();
   FES_CUDA(cudaStreamSynchronize(stream));
-  FES_TRY(build_tiles(P, d_elem_nodes, stream));
+  {
+    // tiles shrink until every tile references <= 255 distinct nodes; with records*corners <= 255
+    // that always holds, so a mesh with scattered node numbering is still tiled (smaller tiles)
+    int gmax = tile_geo_budget(N);
+    const int n_corner = (N == 6) ? 3 : N;
+    for (;;) {
+      bool retry = false;
+      FES_TRY(build_tiles(P, d_elem_nodes, stream, gmax, &retry));
+      if (!retry) break;
+      if (gmax * n_corner <= 255) break;  // cannot happen: such tiles always fit
+      gmax = std::max(255 / n_corner, gmax / 2);
+    }
+  }
   guard.p = nullptr;
   *out = P;
   return FES_OK;
@@ -447,15 +551,17 @@ extern "C" int64_t fes_plan_bytes(const fes_plan* p) {
   return (int64_t)(p->node_ptr.bytes() + p->node_adj.bytes() + p->pair_row.bytes() + p->pair_start.bytes() +
                    p->contrib.bytes() + p->indptr.bytes() + p->indices.bytes() + p->ne_ptr.bytes() +
                    p->ne_code.bytes() + p->tile_node0.bytes() + p->tile_act0.bytes() + p->tile_con0.bytes() +
-                   p->act_meta.bytes() + p->act_codes.bytes() + p->contrib16.bytes() + p->pair_lrow.bytes());
+                   p->act_meta.bytes() + p->act_codes.bytes() + p->contrib16.bytes() + p->pair_lrow.bytes() +
+                   p->tile_nodes.bytes() + p->tile_nnod.bytes() + p->rec_local.bytes());
 }
 
 // what one fused assembly streams from the plan (overhead on top of the algorithmic bytes)
 extern "C" int64_t fes_plan_read_bytes(const fes_plan* p) {
   if (!p) return 0;
   if (p->tiled)
-    return (int64_t)(p->ne_ptr.bytes() + p->ne_code.bytes() + p->tile_node0.bytes() + p->tile_act0.bytes() +
-                     p->tile_con0.bytes() + p->act_meta.bytes() + p->act_codes.bytes() + p->node_ptr.bytes());
+    return (int64_t)(p->ne_ptr.bytes() + p->tile_node0.bytes() + p->tile_act0.bytes() + p->tile_con0.bytes() +
+                     p->act_meta.bytes() + p->act_codes.bytes() + p->rec_local.bytes() + p->tile_nnod.bytes() +
+                     (int64_t)p->n_tiles * 4 * 128 /* distinct-node lists, ~128 used per tile */);
   return (int64_t)(p->pair_row.bytes() + p->pair_start.bytes() + p->contrib.bytes() + p->node_ptr.bytes() +
                    p->indptr.bytes());
 }

@@ -35,6 +35,14 @@ struct fes_plan {
                                        //   x = off16 | cnt8<<16 | diag<<24, y = q0 own, z = q0 mirror,
                                        //   w = deg own | deg mirror<<16;  row i of a block starts at C*(q0 + i*deg)
   fes::DevBuf<uint16_t> act_codes;     // n_act_contrib : (record index in tile)<<6 | a<<3 | b, ascending element id
+  // distinct nodes referenced by a tile's records (so coordinates are gathered once per tile) and
+  // each record's corner nodes as indices into that list
+  static constexpr int kTileNodeStride = 256;
+  int n_corner = 0;                    // corner nodes stored per record (N, or 3 for the 6-node triangle)
+  fes::DevBuf<int32_t> tile_nodes;     // n_tiles * 256 : sorted distinct node ids (first tile_nnod[t] valid)
+  fes::DevBuf<int32_t> tile_nnod;      // n_tiles
+  fes::DevBuf<int32_t> tile_hdr;       // n_tiles * 8 : {g0, g1, a0, n_act, c0, n_con, n_distinct, v0}
+  fes::DevBuf<uint32_t> rec_local;     // n_geo : corner k's index in the tile list at bits [8k, 8k+8)
   // build-time only (kept for k_assemble_precomputed and the untiled fallback): see above
   fes::DevBuf<uint16_t> contrib16;     // n_contrib : tile-relative codes in pair order
   fes::DevBuf<uint8_t> pair_lrow;      // n_pairs : row node relative to the tile's first node
