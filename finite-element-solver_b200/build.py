@@ -37,7 +37,8 @@ def build(force=False, verbose=False):
         s = os.path.join(CSRC, src)
         o = os.path.join(objdir, src.replace('.cu', '.o'))
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o]
+            cmd = ([nvcc] + NVCC_FLAGS + os.environ.get('FES_NVCC_EXTRA', '').split()  # tuning builds only
+                   + (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o])
             jobs.append(cmd)
 
     def run(cmd):

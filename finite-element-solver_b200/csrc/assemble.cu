@@ -28,7 +28,7 @@ struct Coeffs {
   const double* d_E;
   const double* d_scale;
   double lam_over_mu;  // = 2 nu / (1 - 2 nu)
-  double sign;         // sign of the global factor; the tiled kernel works with |factor|
+  double sign;         // sign of the global factor: the tiled kernel works with |factor|, a negate pass follows
 };
 
 __device__ __forceinline__ void element_coeffs(const Coeffs& c, int64_t e, Material& m, double& w) {
@@ -110,291 +110,462 @@ k_assemble_pairs(int64_t n_pairs, const uint32_t* __restrict__ pair_start, const
 }
 
 
+__global__ void k_negate(double* __restrict__ v, int64_t n) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) v[t] = -v[t];
+}
+
 // ---- fused assembly, tiled (the production kernel) ------------------------------------------
-// One CTA (128 threads) per tile of consecutive nodes.
-//   staging: thread 0 arms an mbarrier and issues two 1-D TMA bulk copies (cp.async.bulk, SASS
-//            UBLKCP) of the tile's contiguous plan streams -- the packed metadata of its active
-//            pairs and their contribution codes -- which land while phase 1 runs.
-//   phase 1: one thread per (node, incident element) record, two records per thread in flight,
-//            evaluates the element's geometry ONCE -- inverse Jacobian (the only fp64 divide) and
-//            every node's physical gradient at every quadrature point, pre-multiplied by
-//            sqrt(w_q mu_e) -- into shared memory, double2-packed and record-minor so both the
-//            writes and the LDS.128 reads of phase 2 are as wide as they can be.
-//   phase 2: one thread per ACTIVE pair (v, w >= v), taken in descending contribution count so a
-//            warp's trip counts agree.  It walks the pair's contributions in ascending element id
-//            (np.bincount's order), accumulates the raw outer products S += g~_a (x) g~_b in
-//            registers, applies K = (lam/mu) S + S^T + tr(S) I once, and writes the block of (v, w)
-//            and -- K being symmetric, bit for bit -- its transpose as the block of (w, v).
-// Every CSR value is written exactly once; no atomics, so results are reproducible.
+// Persistent CTAs; each takes tiles of consecutive nodes (= a contiguous range of CSR values).
+//   staging: one producer lane drives three rings of 1-D TMA bulk copies (cp.async.bulk, SASS
+//            UBLKCP) completing on mbarriers: tile headers (3 tiles ahead), the distinct-node list
+//            (2 ahead) and the per-element corner indices / element ids / work-item metadata /
+//            contribution codes (1 ahead).  Nothing the compute threads touch comes from a dependent
+//            global load except the node coordinates, and those are fetched one tile ahead into
+//            registers so they fly under phase 2.
+//   phase 1: one thread per DISTINCT element of the tile evaluates the geometry once -- cofactors,
+//            one rsqrt (no divide, no sqrt), every node's physical gradient at every quadrature
+//            point pre-multiplied by sqrt(w_q mu_e vol_e) -- into shared-memory planes
+//            (element-minor, swizzled slots; the plane stride is 1 mod 8 so different nodes of one
+//            element sit in different banks).
+//   phase 2: one thread per work item = a stored pair (v, w), or one of the 2^lg adjacent lanes that
+//            share a pair with many contributions.  A lane walks its contributions in ascending
+//            element id, accumulates the raw outer products S += g~_a (x) g~_b in registers; a fixed
+//            xor-shuffle tree adds the lanes of a group; the writer lane applies
+//            K = (lam/mu) S + S^T + tr(S) I once and writes the block into the shared-memory image
+//            of the tile's CSR values.
+//   store:   one TMA bulk store (cp.async.bulk.global.shared::cta) writes the image to HBM in full
+//            lines; it drains while the next tile is evaluated.
+// Every CSR value is written exactly once; no atomics and a fixed summation tree, so results are
+// bit-reproducible, and the blocks of (v, w) and (w, v) are bitwise transposes of each other.
 template <int ELEM, int FORM, int C, int SD>
 struct RecLayout {
   static constexpr int N = ET<ELEM>::N, NQ = ET<ELEM>::NQ;
-  // per (quadrature point, node): SD/2 double2 planes + (SD & 1) double plane; mass: one weight
+  // per (quadrature point, node): one double2 plane (x, y) + a double plane (z) in 3D; mass: one weight
   static constexpr int NV2 = (FORM == FES_FORM_MASS) ? 0 : NQ * N * (SD / 2);
   static constexpr int NV1 = (FORM == FES_FORM_MASS) ? 1 : NQ * N * (SD & 1);
   static constexpr int DOUBLES = 2 * NV2 + NV1;
 };
 
-constexpr int kTileThreads = 128;
+#ifndef FES_TILE_THREADS
+#define FES_TILE_THREADS 256
+#endif
+constexpr int kTileThreads = FES_TILE_THREADS;
 constexpr int kRecBatch = 2;  // records a thread evaluates per pass of phase 1 (memory-level parallelism)
+constexpr int kHdrRing = 4, kNodRing = 3;
+__host__ __device__ constexpr int item_len_of(int N) { return (N == 3) ? 2 : (N == 4) ? 6 : 2; }  // = tile_item_len(N)
+constexpr int kHdrBytes = fes_plan::kHdrInts * 4;
 
-// shared-memory carve-up: geometry records and node coordinates (one copy), then two copies of
-// the TMA-staged plan streams (double buffering across tiles)
+__host__ __device__ constexpr size_t up16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+// shared-memory carve-up: geometry records, node coordinates, the value image (one copy each), two
+// copies of the per-tile streams, the node-list ring and the header ring
 template <int ELEM, int FORM, int C, int SD>
 struct TileSmem {
   using R = RecLayout<ELEM, FORM, C, SD>;
-  __host__ __device__ static size_t rec_bytes(int gmax) { return ((size_t)gmax * R::DOUBLES * 8 + 15) & ~(size_t)15; }
+  __host__ __device__ static size_t rec_bytes(int gs) { return up16((size_t)gs * R::DOUBLES * 8); }
   __host__ __device__ static size_t xyz_bytes() { return (size_t)256 * SD * 8; }   // distinct-node coordinates
-  __host__ __device__ static size_t meta_bytes(int amax) { return (size_t)amax * 16 + 16; }
-  __host__ __device__ static size_t code_bytes(int cmax) { return ((size_t)cmax * 2 + 32 + 15) & ~(size_t)15; }
+  __host__ __device__ static size_t out_bytes(int pmax) { return up16(((size_t)pmax * C * C + 2) * 8); }
+  static constexpr int L = item_len_of(ET<ELEM>::N);
+  __host__ __device__ static size_t meta_bytes(int imax) { return up16((size_t)imax * 4 + 16); }
+  __host__ __device__ static size_t code_bytes(int imax) { return up16((size_t)imax * L * 4 + 32); }
+  __host__ __device__ static size_t loc_bytes(int rmax) { return up16((size_t)rmax * 4 + 32); }
+  __host__ __device__ static size_t stage_bytes(int rmax, int imax, int cmax) {
+    return meta_bytes(imax) + code_bytes(imax) + 2 * loc_bytes(rmax);
+  }
   __host__ __device__ static size_t nod_bytes() { return (size_t)256 * 4; }        // distinct-node ids
-  __host__ __device__ static size_t loc_bytes(int gmax) { return ((size_t)gmax * 4 + 32 + 15) & ~(size_t)15; }
-  __host__ __device__ static size_t stage_bytes(int gmax, int amax, int cmax) {
-    return meta_bytes(amax) + code_bytes(cmax) + nod_bytes() + loc_bytes(gmax);
+  __host__ __device__ static size_t total(int gs, int rmax, int pmax, int imax, int cmax) {
+    return rec_bytes(gs) + xyz_bytes() + out_bytes(pmax) + 2 * stage_bytes(rmax, imax, cmax) + kNodRing * nod_bytes() +
+           kHdrRing * up16(kHdrBytes);
   }
-  __host__ __device__ static size_t total(int gmax, int amax, int cmax) {
-    return rec_bytes(gmax) + xyz_bytes() + 2 * stage_bytes(gmax, amax, cmax);
-  }
+};
+
+struct TileDims {
+  int geo_stride, rec_max, pair_max, item_max, con_max;
 };
 
 template <int ELEM, int FORM, int C, int SD>
 __global__ void __launch_bounds__(kTileThreads)
-k_assemble_tiles(const int4* __restrict__ tile_hdr, int n_tiles, const uint32_t* __restrict__ ne_code,
-                 const uint4* __restrict__ act_meta, const uint16_t* __restrict__ act_codes,
-                 const int32_t* __restrict__ tile_nodes, const uint32_t* __restrict__ rec_local,
-                 const double* __restrict__ coords, Coeffs cf, int geo_stride, int act_max, int con_max,
+k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32_t* __restrict__ tile_elems,
+                 const uint32_t* __restrict__ rec_local, const int32_t* __restrict__ tile_nodes,
+                 const uint32_t* __restrict__ pair_meta, const uint32_t* __restrict__ pair_codes,
+                 const double* __restrict__ coords, Coeffs cf, TileDims dims, int use_tma_store,
                  double* __restrict__ values) {
   using R = RecLayout<ELEM, FORM, C, SD>;
   using TS = TileSmem<ELEM, FORM, C, SD>;
   constexpr int N = ET<ELEM>::N, NQ = ET<ELEM>::NQ, RD = ET<ELEM>::RD;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t s_bar[2];
-  __shared__ uint32_t s_skew[2][2];
-  const int GS = geo_stride;
-  // planes: v2[plane * GS + record] (double2), then v1[plane * GS + record] (double)
+  __shared__ __align__(8) uint64_t bar_h[kHdrRing], bar_n[kNodRing], bar_s[2];
+  __shared__ uint32_t s_skew[2][4];
+  const int GS = dims.geo_stride;
+  [[maybe_unused]] const uint32_t inv_gs = (uint32_t)(((1u << 24) + (uint32_t)GS - 1u) / (uint32_t)GS);  // a = (i * inv_gs) >> 24 for i = a * GS + slot
+  // planes: v2[plane * GS + slot] (double2), then v1[plane * GS + slot] (double)
   double2* v2 = reinterpret_cast<double2*>(smem_raw);
   double* v1 = reinterpret_cast<double*>(smem_raw) + (size_t)2 * R::NV2 * GS;
-  double* s_xyz = reinterpret_cast<double*>(smem_raw + TS::rec_bytes(GS));
-  unsigned char* stage0 = smem_raw + TS::rec_bytes(GS) + TS::xyz_bytes();
-  const size_t stage_sz = TS::stage_bytes(GS, act_max, con_max);
+  unsigned char* sp = smem_raw + TS::rec_bytes(GS);
+  double* s_xyz = reinterpret_cast<double*>(sp);                      sp += TS::xyz_bytes();
+  double* s_out = reinterpret_cast<double*>(sp);                      sp += TS::out_bytes(dims.pair_max);
+  unsigned char* stage0 = sp;
+  const size_t stage_sz = TS::stage_bytes(dims.rec_max, dims.item_max, dims.con_max);
+  sp += 2 * stage_sz;
+  unsigned char* nod0 = sp;                                           sp += kNodRing * TS::nod_bytes();
+  unsigned char* hdr0 = sp;
+  const bool per_elem = cf.d_E != nullptr || cf.d_scale != nullptr;
+  double sq_uniform = 0.0;  // sqrt(w mu ref_measure / NQ) when no per-element coefficient varies it
+  if constexpr (FORM != FES_FORM_MASS) {
+    double c2 = cf.factor * (ref_measure(RD) / (double)NQ);
+    if constexpr (FORM == FES_FORM_ELASTIC) c2 *= cf.E * cf.mu1;
+    sq_uniform = sqrt(c2);
+  }
 
-  // One thread arms the stage's mbarrier and issues four 1-D TMA bulk copies of the tile's
-  // contiguous plan streams; they land while the previous tile is still being computed.
-  auto issue = [&](const int4& h0, const int4& h1, int tile, int buf) {
+  const uint32_t v2_b = smem_u32(v2), v1_b = smem_u32(v1);  // shared addresses of the record planes
+  // slot GS-1 of plane 0 is never a record (slots are < GS-1): the all-zero gradient that pads short items
+  const uint32_t zero_code = ((uint32_t)(GS - 1) << 4) * 0x10001u;
+  for (int pl = threadIdx.x; pl < R::NV2 + R::NV1; pl += kTileThreads) {  // in every plane (all quadrature points)
+    if (pl < R::NV2) v2[(size_t)pl * GS + GS - 1] = make_double2(0.0, 0.0);
+    else v1[(size_t)(pl - R::NV2) * GS + GS - 1] = 0.0;
+  }
+  const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
+  if (n_my <= 0) return;
+  auto tile_of = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
+  auto hdr_of = [&](int k) { return reinterpret_cast<const int4*>(hdr0 + (k & (kHdrRing - 1)) * up16(kHdrBytes)); };
+  auto nod_of = [&](int k) { return reinterpret_cast<const int32_t*>(nod0 + (k % kNodRing) * TS::nod_bytes()); };
+  // the producer is the first lane of the LAST warp: warp 0 gets the longest work items in phase 2
+  const bool producer = threadIdx.x == kTileThreads - 32;
+
+  // ---- producer side: ring fills
+  auto issue_hdr = [&](int k) {
+    uint64_t* bar = &bar_h[k & (kHdrRing - 1)];
+    mbar_arrive_expect_tx(bar, kHdrBytes);
+    bulk_g2s(const_cast<int4*>(hdr_of(k)), tile_hdr + (int64_t)tile_of(k) * fes_plan::kHdrInts, kHdrBytes, bar);
+  };
+  auto issue_nod = [&](int k) {
+    mbar_wait(&bar_h[k & (kHdrRing - 1)], (uint32_t)(k >> 2) & 1u);
+    const uint32_t b_nod = ((uint32_t)hdr_of(k)[1].z * 4u + 15u) & ~15u;
+    uint64_t* bar = &bar_n[k % kNodRing];
+    mbar_arrive_expect_tx(bar, b_nod);
+    if (b_nod) bulk_g2s(const_cast<int32_t*>(nod_of(k)), tile_nodes + (int64_t)tile_of(k) * fes_plan::kTileNodeStride, b_nod, bar);
+  };
+  auto issue_rest = [&](int k) {  // its header landed before issue_nod(k) returned
+    const int buf = k & 1;
+    const int4 h0 = hdr_of(k)[0], h2 = hdr_of(k)[2];
     unsigned char* st = stage0 + buf * stage_sz;
-    unsigned char* s_code = st + TS::meta_bytes(act_max);
-    unsigned char* s_nod = s_code + TS::code_bytes(con_max);
-    unsigned char* s_loc = s_nod + TS::nod_bytes();
-    const uint32_t n_rec = (uint32_t)(h0.y - h0.x);
-    const uint32_t b_meta = (uint32_t)h0.w * 16u;
-    const uint32_t b_code = (uint32_t)(((((uint64_t)h1.x * 2) & 15) + (uint64_t)h1.y * 2 + 15) & ~(uint64_t)15);
-    const uint32_t b_nod = ((uint32_t)h1.z * 4u + 15u) & ~15u;
-    const uint32_t b_loc = (uint32_t)(((((uint64_t)h0.x * 4) & 15) + (uint64_t)n_rec * 4 + 15) & ~(uint64_t)15);
-    mbar_arrive_expect_tx(&s_bar[buf], b_meta + b_code + b_nod + b_loc);
+    unsigned char* s_code = st + TS::meta_bytes(dims.item_max);
+    unsigned char* s_loc = s_code + TS::code_bytes(dims.item_max);
+    unsigned char* s_el = s_loc + TS::loc_bytes(dims.rec_max);
+    const uint32_t g0 = (uint32_t)h0.x, ne = (uint32_t)h0.y;
+    auto win = [](uint32_t i0, uint32_t count, uint32_t es) {
+      return (uint32_t)(((((uint64_t)i0 * es) & 15) + (uint64_t)count * es + 15) & ~(uint64_t)15);
+    };
+    constexpr uint32_t L = (uint32_t)TS::L;
+    const uint32_t i0 = (uint32_t)h2.x, ni = (uint32_t)h2.y;
+    const uint32_t b_meta = win(i0, ni, 4), b_code = win(i0 * L, ni * L, 4);
+    const uint32_t b_loc = win(g0, ne, 4);
+    uint64_t* bar = &bar_s[buf];
+    mbar_arrive_expect_tx(bar, b_meta + b_code + b_loc * (per_elem ? 2u : 1u));
     uint32_t t;
-    if (b_nod) bulk_g2s(s_nod, tile_nodes + (int64_t)tile * fes_plan::kTileNodeStride, b_nod, &s_bar[buf]);
-    s_skew[buf][1] = stage_window<4>(s_loc, rec_local, (uint32_t)h0.x, n_rec, &s_bar[buf], t);
-    if (b_meta) bulk_g2s(st, act_meta + h0.z, b_meta, &s_bar[buf]);
-    s_skew[buf][0] = stage_window<2>(s_code, act_codes, (uint32_t)h1.x, (uint32_t)h1.y, &s_bar[buf], t);
+    s_skew[buf][1] = stage_window<4>(s_loc, rec_local, g0, ne, bar, t);
+    if (per_elem) stage_window<4>(s_el, tile_elems, g0, ne, bar, t);  // same skew as the corner indices
+    s_skew[buf][2] = stage_window<4>(st, pair_meta, i0, ni, bar, t);
+    s_skew[buf][0] = stage_window<4>(s_code, pair_codes, i0 * L, ni * L, bar, t);
   };
 
-  int tile = blockIdx.x;
-  if (tile >= n_tiles) return;
-  int4 h0 = __ldg(tile_hdr + 2 * tile), h1 = __ldg(tile_hdr + 2 * tile + 1);
-  if (threadIdx.x == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
-    issue(h0, h1, tile, 0);
-  }
-  __syncthreads();
-
-  for (int it = 0; tile < n_tiles; ++it) {
-    const int buf = it & 1;
-    const uint32_t parity = (uint32_t)(it >> 1) & 1u;
-    const int next = tile + (int)gridDim.x;
-    int4 n0 = h0, n1 = h1;
-    if (next < n_tiles) {
-      n0 = __ldg(tile_hdr + 2 * next);
-      n1 = __ldg(tile_hdr + 2 * next + 1);
-      if (threadIdx.x == 0) issue(n0, n1, next, buf ^ 1);  // that stage was last read before the barrier below
-    }
-    const int32_t g0 = h0.x, g1 = h0.y, n_act = h0.w, nd = h1.z;
-    unsigned char* st = stage0 + buf * stage_sz;
-    const uint4* s_meta = reinterpret_cast<const uint4*>(st);
-    unsigned char* s_code = st + TS::meta_bytes(act_max);
-    const int32_t* s_nod = reinterpret_cast<const int32_t*>(s_code + TS::code_bytes(con_max));
-    unsigned char* s_loc = s_code + TS::code_bytes(con_max) + TS::nod_bytes();
-    mbar_wait(&s_bar[buf], parity);  // this tile's plan streams have landed
-
-    // ---- phase 0: coordinates of the tile's distinct nodes, gathered once
-    for (int i = threadIdx.x; i < nd; i += kTileThreads) {
-      const int32_t node = s_nod[i];
-      if constexpr (SD == 2) {
-        reinterpret_cast<double2*>(s_xyz)[i] = __ldg(reinterpret_cast<const double2*>(coords) + node);
-      } else {
+  // coordinates of a tile's distinct nodes: global -> registers (<= 255 nodes: a node or two per
+  // thread), stored to shared memory later so the loads fly under phase 2 of the previous tile
+  constexpr int kNPT = (255 + kTileThreads - 1) / kTileThreads;
+  double cx[kNPT][SD];
+  auto load_xyz = [&](const int32_t* s_nod, int nd) {
 #pragma unroll
-        for (int s = 0; s < SD; ++s) s_xyz[i * SD + s] = __ldg(coords + (int64_t)node * SD + s);
-      }
-    }
-    __syncthreads();
-    const uint32_t* locs = reinterpret_cast<const uint32_t*>(s_loc + s_skew[buf][1]);
-
-  // ---- phase 1: geometry records (corner coordinates come from shared memory)
-  const bool per_elem = cf.d_E != nullptr || cf.d_scale != nullptr;
-  for (int32_t base = g0 + threadIdx.x; base < g1; base += kTileThreads * kRecBatch) {
-    uint32_t e[kRecBatch];
-    bool live[kRecBatch];
-    double X[kRecBatch][RD + 1][SD];
-#pragma unroll
-    for (int r = 0; r < kRecBatch; ++r) {
-      const int32_t gi = base + r * kTileThreads;
-      live[r] = gi < g1;
-      e[r] = (live[r] && per_elem) ? (__ldg(ne_code + gi) >> 3) : 0u;
-      const uint32_t loc = live[r] ? locs[gi - g0] : 0u;
-#pragma unroll
-      for (int n = 0; n <= RD; ++n) {
-        const int li = (loc >> (8 * n)) & 255;
+    for (int k = 0; k < kNPT; ++k) {
+      const int i = threadIdx.x + k * kTileThreads;
+      if (i < nd) {
+        const int32_t node = s_nod[i];
         if constexpr (SD == 2) {
-          const double2 xy = reinterpret_cast<const double2*>(s_xyz)[li];
-          X[r][n][0] = xy.x; X[r][n][1] = xy.y;
+          const double2 xy = __ldg(reinterpret_cast<const double2*>(coords) + node);
+          cx[k][0] = xy.x; cx[k][1] = xy.y;
         } else {
 #pragma unroll
-          for (int s = 0; s < SD; ++s) X[r][n][s] = s_xyz[li * SD + s];
+          for (int d = 0; d < SD; ++d) cx[k][d] = __ldg(coords + (int64_t)node * SD + d);
         }
       }
     }
+  };
+  auto store_xyz = [&](int nd) {
 #pragma unroll
-    for (int r = 0; r < kRecBatch; ++r) {
-      if (!live[r]) continue;
-      Geom<RD, SD> g;
-      make_geom<RD, SD>(X[r], g);
-      Material m; double w;
-      element_coeffs(cf, e[r], m, w);
-      const int rec = base + r * kTileThreads - g0;
-      const double vol = g.scale * ref_measure(RD);
-      if constexpr (FORM == FES_FORM_MASS) {
-        v1[rec] = w * vol;
-      } else {
-        // g~ = sqrt(w_q mu_e) g: weight and modulus ride on the gradients (mu1 is divided out by
-        // using lam/mu below), so phase 2 accumulates plain outer products
-        double wq = w * vol / (double)NQ;
-        if constexpr (FORM == FES_FORM_ELASTIC) wq *= m.mu;
-        const double sq = sqrt(wq);
+    for (int k = 0; k < kNPT; ++k) {
+      const int i = threadIdx.x + k * kTileThreads;
+      if (i < nd) {
+        if constexpr (SD == 2) {
+          reinterpret_cast<double2*>(s_xyz)[i] = make_double2(cx[k][0], cx[k][1]);
+        } else {
 #pragma unroll
-        for (int q = 0; q < NQ; ++q)
-#pragma unroll
-          for (int n = 0; n < N; ++n) {
-            double gn[SD];
-            shape_grad<ELEM, SD>(g, q, n, gn);
-#pragma unroll
-            for (int h = 0; h < SD / 2; ++h)
-              v2[((q * N + n) * (SD / 2) + h) * GS + rec] = make_double2(sq * gn[2 * h], sq * gn[2 * h + 1]);
-            if constexpr (SD & 1) v1[(q * N + n) * GS + rec] = sq * gn[SD - 1];
-          }
+          for (int d = 0; d < SD; ++d) s_xyz[i * SD + d] = cx[k][d];
+        }
       }
     }
-  }
-  __syncthreads();        // records visible
+  };
 
-  // ---- phase 2: one thread per active pair
-  const uint16_t* codes = reinterpret_cast<const uint16_t*>(s_code + s_skew[buf][0]);
-  for (int t = threadIdx.x; t < n_act; t += kTileThreads) {
-    const uint4 mt = s_meta[t];
-    const uint32_t k0 = mt.x & 0xffffu, cnt = (mt.x >> 16) & 0xffu;
-    const bool diag = (mt.x >> 24) & 1u;
-    double acc[C][C];
+  if (producer) {
+    for (int i = 0; i < kHdrRing; ++i) mbar_init(&bar_h[i], 1);
+    for (int i = 0; i < kNodRing; ++i) mbar_init(&bar_n[i], 1);
+    mbar_init(&bar_s[0], 1);
+    mbar_init(&bar_s[1], 1);
+    for (int k = 0; k < 3 && k < n_my; ++k) issue_hdr(k);
+    issue_nod(0);
+    if (n_my > 1) issue_nod(1);
+    issue_rest(0);
+  }
+  __syncthreads();
+  mbar_wait(&bar_h[0], 0);
+  mbar_wait(&bar_n[0], 0);
+  load_xyz(nod_of(0), hdr_of(0)[1].z);
+  store_xyz(hdr_of(0)[1].z);
+  __syncthreads();
+
+  // Steady state, tile k:  [header(k), coordinates(k) in shared memory; streams(k) in flight or landed]
+  //   producer: header(k+3), node list(k+2), streams(k+1)  |  phase 1(k)  |  barrier  |
+  //   coordinates(k+1) -> registers  |  phase 2(k)  |  coordinates(k+1) -> shared memory  |  barrier  |  bulk store(k)
+  for (int k = 0; k < n_my; ++k) {
+    const int buf = k & 1;
+    const bool has_next = k + 1 < n_my;
+    if (producer) {
+      if (k + 3 < n_my) issue_hdr(k + 3);
+      if (k + 2 < n_my) issue_nod(k + 2);
+      if (has_next) issue_rest(k + 1);
+    }
+    const int4 h0 = hdr_of(k)[0], h2 = hdr_of(k)[2];
+    const int32_t ne = h0.y, n_pairs = h0.w, n_items = h2.y;
+    const int64_t val0 = (int64_t)C * C * h0.z;          // first CSR value of the tile
+    const int skew_d = (int)(val0 & 1);                   // image slot i <-> values[val0 + i]; equal 16-byte phase
+    unsigned char* st = stage0 + buf * stage_sz;
+    unsigned char* s_code = st + TS::meta_bytes(dims.item_max);
+    unsigned char* s_loc = s_code + TS::code_bytes(dims.item_max);
+    unsigned char* s_el = s_loc + TS::loc_bytes(dims.rec_max);
+    mbar_wait(&bar_s[buf], (uint32_t)(k >> 1) & 1u);  // issued a whole tile ago
+    const uint32_t* locs = reinterpret_cast<const uint32_t*>(s_loc + s_skew[buf][1]);
+    const uint32_t* elems = reinterpret_cast<const uint32_t*>(s_el + s_skew[buf][1]);
+
+    // ---- phase 1: one geometry record per distinct element (corner coordinates from shared memory).
+    // Pass b starts at thread b*T/2, so a short last pass does not land on warp 0 every time.
+    for (int32_t blk = 0; blk * kTileThreads < ne; blk += kRecBatch) {
+      bool live[kRecBatch];
+      int32_t gi[kRecBatch];
+      uint32_t e[kRecBatch];
+      double X[kRecBatch][RD + 1][SD];
 #pragma unroll
-    for (int i = 0; i < C; ++i)
+      for (int r = 0; r < kRecBatch; ++r) {
+        gi[r] = (blk + r) * kTileThreads + (int)((threadIdx.x + (unsigned)(blk + r) * (kTileThreads / 2)) % kTileThreads);
+        live[r] = gi[r] < ne;
+        const uint32_t loc = live[r] ? locs[gi[r]] : 0u;
+        e[r] = (live[r] && per_elem) ? elems[gi[r]] : 0u;
 #pragma unroll
-      for (int j = 0; j < C; ++j) acc[i][j] = 0.0;
-    for (uint32_t k = k0; k < k0 + cnt; ++k) {
-      const uint32_t code = codes[k];
-      const int a = (code >> 3) & 7, b = code & 7;
-      const int rec = code >> 6;
+        for (int n = 0; n <= RD; ++n) {
+          const int li = (loc >> (8 * n)) & 255;
+          if constexpr (SD == 2) {
+            const double2 xy = reinterpret_cast<const double2*>(s_xyz)[li];
+            X[r][n][0] = xy.x; X[r][n][1] = xy.y;
+          } else {
+#pragma unroll
+            for (int s = 0; s < SD; ++s) X[r][n][s] = s_xyz[li * SD + s];
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kRecBatch; ++r) {
+        if (!live[r]) continue;
+        Material m; double w;
+        element_coeffs(cf, e[r], m, w);
+        const int rec = (int)rec_slot((uint32_t)gi[r]);
+        if constexpr (FORM == FES_FORM_MASS) {
+          Geom<RD, SD> g;
+          make_geom<RD, SD>(X[r], g);
+          v1[rec] = w * (g.scale * ref_measure(RD));
+        } else {
+          // g~ = sqrt(w_q mu_e vol) grad(phi) with grad(phi) = cof / det and vol = |det| ref_measure:
+          //    = cof * sign(det) * sqrt(w mu ref_measure / NQ) * rsqrt(|det|)  -- one rsqrt, no divide.
+          // Weight and modulus ride on the gradients (lam/mu is applied in phase 2), so phase 2
+          // accumulates plain outer products.
+          double cof[RD][SD], det;
+          make_cof<RD, SD>(X[r], cof, det);
+          double f = sq_uniform;
+          if (per_elem) {
+            double c2 = w * (ref_measure(RD) / (double)NQ);
+            if constexpr (FORM == FES_FORM_ELASTIC) c2 *= m.mu;
+            f = c2 > 0.0 ? c2 * rsqrt(c2) : 0.0;
+          }
+          f = copysign(f * rsqrt(fabs(det)), det);
+#pragma unroll
+          for (int i = 0; i < RD; ++i)
+#pragma unroll
+            for (int s = 0; s < SD; ++s) cof[i][s] *= f;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+              double gn[SD];
+              shape_grad_rows<ELEM, SD>(cof, q, n, gn);
+#pragma unroll
+              for (int h = 0; h < SD / 2; ++h)
+                v2[((q * N + n) * (SD / 2) + h) * GS + rec] = make_double2(gn[2 * h], gn[2 * h + 1]);
+              if constexpr (SD & 1) v1[(q * N + n) * GS + rec] = gn[SD - 1];
+            }
+        }
+      }
+    }
+    if (producer) bulk_wait_read_all();  // the previous tile's store has finished reading the image
+    __syncthreads();                     // records visible, image free, coordinates consumed
+
+    int nd_next = 0;
+    if (has_next) {  // the next tile's coordinates start flying now and land under phase 2
+      mbar_wait(&bar_h[(k + 1) & (kHdrRing - 1)], (uint32_t)((k + 1) >> 2) & 1u);
+      mbar_wait(&bar_n[(k + 1) % kNodRing], (uint32_t)((k + 1) / kNodRing) & 1u);
+      nd_next = hdr_of(k + 1)[1].z;
+      load_xyz(nod_of(k + 1), nd_next);
+    }
+
+    // ---- phase 2: one thread per work item (explicit shared addresses, bases in registers)
+    const uint32_t code_b = smem_u32(s_code) + s_skew[buf][0];
+    const uint32_t meta_b = smem_u32(st) + s_skew[buf][2];
+    static_assert(TS::L % 2 == 0, "item codes are fetched two at a time");
+    const uint32_t img_b = smem_u32(s_out) + 8u * (uint32_t)skew_d;
+    // A chunk of CH contributions: S += g~_a (x) g~_b each.  A code holds the byte offsets of the two
+    // gradients in the double2 planes (the z plane of a 3D gradient sits at half that offset).  All
+    // loads of a chunk are issued before its FMAs; a lane with fewer contributions reads the
+    // all-zero record instead of branching (fma(0, 0, acc) == acc, bit for bit).
+    constexpr int kItemLen = TS::L;
+    constexpr int CH = (NQ > 1 || FORM == FES_FORM_MASS) ? 1 : (SD == 3 ? 2 : kItemLen);
+    auto gather_chunk = [&](const uint32_t (&code)[CH], double (&acc)[C][C]) {
       if constexpr (FORM == FES_FORM_MASS) {
-        acc[0][0] = fma(v1[rec], mass_ref<ELEM>(a, b), acc[0][0]);
+        const uint32_t ia = (code[0] & 0xffffu) >> 4, ib = code[0] >> 20;
+        const uint32_t a = (uint32_t)(((uint64_t)ia * inv_gs) >> 24), b = (uint32_t)(((uint64_t)ib * inv_gs) >> 24);
+        acc[0][0] = fma(lds_f64(v1_b + 8u * (ia - a * (uint32_t)GS)), mass_ref<ELEM>((int)a, (int)b), acc[0][0]);
       } else {
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-          double A_[SD], B_[SD];
+          double2 ta[CH], tb[CH];
+          [[maybe_unused]] double za[CH], zb[CH];
 #pragma unroll
-          for (int h = 0; h < SD / 2; ++h) {
-            const double2 t2 = v2[((q * N + a) * (SD / 2) + h) * GS + rec];
-            A_[2 * h] = t2.x; A_[2 * h + 1] = t2.y;
-          }
-          if constexpr (SD & 1) A_[SD - 1] = v1[(q * N + a) * GS + rec];
-          if (a == b) {
-#pragma unroll
-            for (int s = 0; s < SD; ++s) B_[s] = A_[s];
-          } else {
-#pragma unroll
-            for (int h = 0; h < SD / 2; ++h) {
-              const double2 t2 = v2[((q * N + b) * (SD / 2) + h) * GS + rec];
-              B_[2 * h] = t2.x; B_[2 * h + 1] = t2.y;
+          for (int x = 0; x < CH; ++x) {
+            const uint32_t oa = code[x] & 0xffffu, ob = code[x] >> 16;
+            ta[x] = lds_f64x2(v2_b + oa + (uint32_t)(q * N * 16) * (uint32_t)GS);
+            tb[x] = lds_f64x2(v2_b + ob + (uint32_t)(q * N * 16) * (uint32_t)GS);  // same address when a == b: a broadcast
+            if constexpr (SD & 1) {
+              za[x] = lds_f64(v1_b + (oa >> 1) + (uint32_t)(q * N * 8) * (uint32_t)GS);
+              zb[x] = lds_f64(v1_b + (ob >> 1) + (uint32_t)(q * N * 8) * (uint32_t)GS);
             }
-            if constexpr (SD & 1) B_[SD - 1] = v1[(q * N + b) * GS + rec];
           }
-          if constexpr (FORM == FES_FORM_LAPLACIAN) {
 #pragma unroll
-            for (int s = 0; s < SD; ++s) acc[0][0] = fma(A_[s], B_[s], acc[0][0]);
-          } else {
+          for (int x = 0; x < CH; ++x) {
+            double A_[SD], B_[SD];
+            A_[0] = ta[x].x; A_[1] = ta[x].y;
+            B_[0] = tb[x].x; B_[1] = tb[x].y;
+            if constexpr (SD & 1) { A_[SD - 1] = za[x]; B_[SD - 1] = zb[x]; }
+            if constexpr (FORM == FES_FORM_LAPLACIAN) {
 #pragma unroll
-            for (int i = 0; i < C; ++i)
+              for (int s = 0; s < SD; ++s) acc[0][0] = fma(A_[s], B_[s], acc[0][0]);
+            } else {
 #pragma unroll
-              for (int j = 0; j < C; ++j) acc[i][j] = fma(A_[i], B_[j], acc[i][j]);  // S += g~_a (x) g~_b
+              for (int i = 0; i < C; ++i)
+#pragma unroll
+                for (int j = 0; j < C; ++j) acc[i][j] = fma(A_[i], B_[j], acc[i][j]);
+            }
           }
         }
       }
-    }
-    double K[C][C];
-    if constexpr (FORM == FES_FORM_ELASTIC) {
-      double tr = 0.0;
+    };
+    for (int t0 = 0; t0 < n_items; t0 += kTileThreads) {  // warp-uniform trip count: the shuffles need every lane
+      const int t = t0 + (int)threadIdx.x;
+      const bool live = t < n_items;
+      const uint32_t mt = live ? lds_u32(meta_b + 4u * (uint32_t)t) : 0u;
+      const uint32_t lg = (mt >> 28) & 7u;
+      uint32_t cd[kItemLen];  // the item's codes: exactly kItemLen, padded with the zero record by the plan
 #pragma unroll
-      for (int i = 0; i < C; ++i) tr += acc[i][i];
+      for (int kk = 0; kk < kItemLen; kk += 2) {
+        const uint2 two = live ? lds_u32x2(code_b + 4u * ((uint32_t)t * kItemLen + kk)) : make_uint2(zero_code, zero_code);
+        cd[kk] = two.x; cd[kk + 1] = two.y;
+      }
+      double acc[C][C];
 #pragma unroll
       for (int i = 0; i < C; ++i)
 #pragma unroll
-        for (int j = 0; j < C; ++j)
-          K[i][j] = cf.sign * (fma(cf.lam_over_mu, acc[i][j], acc[j][i]) + (i == j ? tr : 0.0));
-    } else if constexpr (FORM == FES_FORM_LAPLACIAN) {
-      K[0][0] = cf.sign * acc[0][0];
-    } else {
+        for (int j = 0; j < C; ++j) acc[i][j] = 0.0;
 #pragma unroll
-      for (int i = 0; i < C; ++i)
+      for (int c0_ = 0; c0_ < kItemLen; c0_ += CH) {
+        uint32_t part[CH];
 #pragma unroll
-        for (int j = 0; j < C; ++j) K[i][j] = (i == j) ? acc[0][0] : 0.0;
-    }
-    // row i of a block starts at C * (q0 + i * deg); the block of (w, v) is K^T
-    const int64_t q_own = mt.y, q_mir = mt.z;
-    const int64_t deg_own = mt.w & 0xffffu, deg_mir = mt.w >> 16;
+        for (int x = 0; x < CH; ++x) part[x] = cd[c0_ + x];
+        // later chunks are padding for every lane of most warps (items are sorted by trips)
+        if (c0_ == 0 || __any_sync(0xffffffffu, part[0] != zero_code)) gather_chunk(part, acc);
+      }
+      // lanes that share a pair: fixed xor tree over the 2^lg adjacent lanes (both partners add, so
+      // every lane of the group ends with the same bits)
+      const uint32_t lg_max = __reduce_max_sync(0xffffffffu, lg);
+      for (uint32_t o = 0; o < lg_max; ++o) {
+        constexpr int NACC = (FORM == FES_FORM_ELASTIC) ? C * C : 1;
 #pragma unroll
-    for (int i = 0; i < C; ++i) {
-      double* row = values + (int64_t)C * (q_own + i * deg_own);
-      if constexpr (C == 2) {
-        *reinterpret_cast<double2*>(row) = make_double2(K[i][0], K[i][1]);
+        for (int x = 0; x < NACC; ++x) {
+          double& a_ = acc[x / C][x % C];
+          const double other = __shfl_xor_sync(0xffffffffu, a_, 1 << o);
+          if (o < lg) a_ += other;
+        }
+      }
+      if (!(mt >> 31)) continue;  // not the writer lane of its pair
+      double K[C][C];
+      if constexpr (FORM == FES_FORM_ELASTIC) {
+        double tr = 0.0;
+#pragma unroll
+        for (int i = 0; i < C; ++i) tr += acc[i][i];
+#pragma unroll
+        for (int i = 0; i < C; ++i)
+#pragma unroll
+          for (int j = 0; j < C; ++j) K[i][j] = fma(cf.lam_over_mu, acc[i][j], acc[j][i]) + (i == j ? tr : 0.0);
+      } else if constexpr (FORM == FES_FORM_LAPLACIAN) {
+        K[0][0] = acc[0][0];
       } else {
 #pragma unroll
-        for (int j = 0; j < C; ++j) row[j] = K[i][j];
+        for (int i = 0; i < C; ++i)
+#pragma unroll
+          for (int j = 0; j < C; ++j) K[i][j] = (i == j) ? acc[0][0] : 0.0;
+      }
+      // row i of the block starts at double C * (q + i * deg) of the tile's value image
+      const uint32_t q0 = mt & 0xffffu, deg = (mt >> 16) & 0xfffu;
+      if constexpr (C == 2) {
+        // neighbouring threads hold the same slot of consecutive nodes, 2*deg 16-byte slots apart:
+        // lanes 4..7 of each group of 8 write their rows in the opposite order, which makes the
+        // eight addresses of a quarter-warp hit eight different bank groups when deg is odd
+        const bool swap = (threadIdx.x >> 2) & 1;
+        const uint32_t r0 = img_b + 16u * (q0 + (swap ? deg : 0u)), r1 = img_b + 16u * (q0 + (swap ? 0u : deg));
+        sts_f64x2(r0, swap ? K[1][0] : K[0][0], swap ? K[1][1] : K[0][1]);
+        sts_f64x2(r1, swap ? K[0][0] : K[1][0], swap ? K[0][1] : K[1][1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < C; ++i)
+#pragma unroll
+          for (int j = 0; j < C; ++j) sts_f64(img_b + 8u * (C * (q0 + i * deg) + j), K[i][j]);
       }
     }
-    if (!diag) {
-#pragma unroll
-      for (int i = 0; i < C; ++i) {
-        double* row = values + (int64_t)C * (q_mir + i * deg_mir);
-        if constexpr (C == 2) {
-          *reinterpret_cast<double2*>(row) = make_double2(K[0][i], K[1][i]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < C; ++j) row[j] = K[j][i];
-        }
+    if (has_next) store_xyz(nd_next);  // the coordinate buffer was last read before this tile's first barrier
+
+    // ---- store: the image is the tile's contiguous slice of `values`
+    const int n_out = C * C * n_pairs;
+    double* img = s_out + skew_d;
+    if (use_tma_store) {
+      fence_proxy_async_smem();  // generic-proxy writes to the image -> visible to the async proxy
+      __syncthreads();
+      if (producer) {
+        const int head = skew_d;                           // an odd first slot is 16-byte misaligned on both sides
+        const int body = (n_out - head) & ~1, tail = n_out - head - body;
+        if (body > 0) bulk_s2g(values + val0 + head, img + head, (uint32_t)body * 8u);
+        if (head) values[val0] = img[0];
+        if (tail) values[val0 + n_out - 1] = img[n_out - 1];
       }
+    } else {
+      __syncthreads();
+      for (int i = threadIdx.x; i < n_out; i += kTileThreads) values[val0 + i] = img[i];
+      __syncthreads();
     }
   }
-    __syncthreads();  // records, coordinates and this stage are free for reuse
-    tile = next;
-    h0 = n0;
-    h1 = n1;
-  }
+  if (producer) bulk_wait_read_all();  // shared memory must outlive the last store's reads
 }
 
 // PrecomputedForm: gather caller-supplied (n_el, K, K) matrices, optionally scaled per element
@@ -459,28 +630,38 @@ int run(const Job& j) {
     const fes_plan* P = j.plan;
     if (P->n_pairs == 0) return FES_OK;
     if (P->tiled && !j.untiled) {
-      const size_t smem = TileSmem<ELEM, FORM, C, SD>::total(P->geo_max, P->act_max, P->con_max);
+      const TileDims dims{P->geo_stride, P->rec_max, P->pair_max, P->item_max, P->con_max};
+      const size_t smem = TileSmem<ELEM, FORM, C, SD>::total(dims.geo_stride, dims.rec_max, dims.pair_max, dims.item_max,
+                                                             dims.con_max);
       static size_t configured = 0;  // per template instantiation: largest opt-in so far
-      if (smem + 1024 > 48 * 1024 && smem > configured) {  // static smem counts toward the 48 KB default
-        FES_CUDA(cudaFuncSetAttribute(k_assemble_tiles<ELEM, FORM, C, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-        configured = smem;
-      }
-      Coeffs cf = j.cf;
-      if (FORM != FES_FORM_MASS && cf.factor < 0.0) { cf.factor = -cf.factor; cf.sign = -1.0; }
-      static int per_sm = 0, sms = 0;  // per template instantiation
+      static int per_sm = 0, sms = 0;
       if (per_sm == 0 || smem > configured) {
+        if (smem + 1024 > 48 * 1024)  // static smem counts toward the 48 KB default
+          FES_CUDA(cudaFuncSetAttribute(k_assemble_tiles<ELEM, FORM, C, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+        configured = std::max(configured, smem);
         int dev = 0;
         FES_CUDA(cudaGetDevice(&dev));
         FES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         FES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_tiles<ELEM, FORM, C, SD>,
                                                                kTileThreads, smem));
-        if (per_sm < 1) return set_error(FES_ERR_CUDA, "assembly kernel does not fit on an SM (%zu B smem)", smem);
+        if (per_sm < 1) {
+          per_sm = 0;
+          return set_error(FES_ERR_CUDA, "assembly kernel does not fit on an SM (%zu B smem)", smem);
+        }
       }
+      Coeffs cf = j.cf;
+      if (FORM != FES_FORM_MASS && cf.factor < 0.0) { cf.factor = -cf.factor; cf.sign = -1.0; }
       const int64_t grid = std::min<int64_t>(P->n_tiles, (int64_t)sms * per_sm);  // persistent CTAs
+      static const bool no_tma = getenv("FES_NO_TMA_STORE") != nullptr;  // tuning knob: plain coalesced stores
+      const int use_tma = (!no_tma && (reinterpret_cast<uintptr_t>(j.out) & 15) == 0) ? 1 : 0;
       k_assemble_tiles<ELEM, FORM, C, SD><<<(unsigned)grid, kTileThreads, smem, j.stream>>>(
-          reinterpret_cast<const int4*>(P->tile_hdr.p), (int)P->n_tiles, P->ne_code.p, P->act_meta.p, P->act_codes.p,
-          P->tile_nodes.p, P->rec_local.p, j.coords, cf, P->geo_max, P->act_max, P->con_max, j.out);
+          P->tile_hdr.p, (int)P->n_tiles, P->tile_elems.p, P->rec_local.p, P->tile_nodes.p, P->pair_meta.p,
+          P->pair_codes.p, j.coords, cf, dims, use_tma, j.out);
+      if (cf.sign < 0.0) {  // a negative global factor (ScaledForm): the kernel ran with |factor|
+        FES_LAUNCH_CHECK();
+        k_negate<<<grid_for(P->nnz, 256), 256, 0, j.stream>>>(j.out, P->nnz);
+      }
     } else {
       k_assemble_pairs<ELEM, FORM, C, SD><<<grid_for(P->n_pairs, kBlock), kBlock, 0, j.stream>>>(
           P->n_pairs, P->pair_start.p, P->pair_row.p, P->node_ptr.p, P->contrib.p, P->indptr.p, j.en, j.coords, j.cf,

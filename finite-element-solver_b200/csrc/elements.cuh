@@ -34,11 +34,14 @@ static __constant__ double c_p2tri_dshape[3][6][2] = {
     FES_P2G(1.0 - 1.0 / 6 - 1.0 / 6, 1.0 / 6, 1.0 / 6),
     FES_P2G(1.0 - 2.0 / 3 - 1.0 / 6, 2.0 / 3, 1.0 / 6),
     FES_P2G(1.0 - 1.0 / 6 - 2.0 / 3, 1.0 / 6, 2.0 / 3)};
-// Mass per unit measure: P2 triangle (x180) and P2 line (x30), exact rationals.
-static __constant__ double c_p2tri_mass180[6][6] = {
-    {6, -1, -1, -4, 0, 0}, {-1, 6, -1, 0, -4, 0}, {-1, -1, 6, 0, 0, -4},
-    {-4, 0, 0, 32, 16, 16}, {0, -4, 0, 16, 32, 16}, {0, 0, -4, 16, 16, 32}};
-static __constant__ double c_p2line_mass30[3][3] = {{4, -1, 2}, {-1, 4, 2}, {2, 2, 16}};
+// Mass per unit measure: P2 triangle (k/180) and P2 line (k/30), exact rationals; the
+// divisions are folded at compile time so no kernel divides per contribution.
+#define FES_M180(a, b, c, d, e, f) {(a) / 180.0, (b) / 180.0, (c) / 180.0, (d) / 180.0, (e) / 180.0, (f) / 180.0}
+static __constant__ double c_p2tri_mass[6][6] = {
+    FES_M180(6, -1, -1, -4, 0, 0), FES_M180(-1, 6, -1, 0, -4, 0), FES_M180(-1, -1, 6, 0, 0, -4),
+    FES_M180(-4, 0, 0, 32, 16, 16), FES_M180(0, -4, 0, 16, 32, 16), FES_M180(0, 0, -4, 16, 16, 32)};
+static __constant__ double c_p2line_mass[3][3] = {
+    {4 / 30.0, -1 / 30.0, 2 / 30.0}, {-1 / 30.0, 4 / 30.0, 2 / 30.0}, {2 / 30.0, 2 / 30.0, 16 / 30.0}};
 
 // Inverse Jacobian rows (d xi_r / d x_s) and the measure scale |det J| (or sqrt det J^T J for
 // an embedded facet, where only the scale is defined here: boundary integrals are mass-type).
@@ -98,6 +101,39 @@ __device__ __forceinline__ void make_geom(const double (&X)[RD + 1][SD], Geom<RD
   }
 }
 
+// Cofactor form of the same geometry for volume elements (RD == SD): cof = det * Jinv, no
+// division.  The tiled assembly kernel scales it by one rsqrt instead of a divide and a sqrt.
+template <int RD, int SD>
+__device__ __forceinline__ void make_cof(const double (&X)[RD + 1][SD], double (&cof)[RD][SD], double& det) {
+  static_assert(RD == SD, "cofactor geometry is for volume elements");
+  if constexpr (RD == 1) {
+    det = X[1][0] - X[0][0];
+    cof[0][0] = 1.0;
+  } else if constexpr (RD == 2) {
+    const double a = X[1][0] - X[0][0], b = X[2][0] - X[0][0];
+    const double c = X[1][1] - X[0][1], d = X[2][1] - X[0][1];
+    det = a * d - b * c;
+    cof[0][0] = d;  cof[0][1] = -b;
+    cof[1][0] = -c; cof[1][1] = a;
+  } else {
+    double J[3][3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) J[s][r] = X[r + 1][s] - X[0][s];
+    cof[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    cof[1][0] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+    cof[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    det = J[0][0] * cof[0][0] + J[0][1] * cof[1][0] + J[0][2] * cof[2][0];
+    cof[0][1] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+    cof[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+    cof[2][1] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+    cof[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+    cof[1][2] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+    cof[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+  }
+}
+
 template <int ELEM, int SD>
 __device__ __forceinline__ void load_geom(const int32_t* __restrict__ en, const double* __restrict__ coords,
                                           Geom<ET<ELEM>::RD, SD>& g) {
@@ -114,9 +150,10 @@ __device__ __forceinline__ void load_geom(const int32_t* __restrict__ en, const 
 
 __device__ __forceinline__ double ref_measure(int rd) { return rd == 1 ? 1.0 : (rd == 2 ? 0.5 : 1.0 / 6.0); }
 
-// physical gradient of shape function `a` at quadrature point q
+// physical gradient of shape function `a` at quadrature point q, from the rows of the inverse
+// Jacobian (or of any multiple of it: the map is linear)
 template <int ELEM, int SD>
-__device__ __forceinline__ void shape_grad(const Geom<ET<ELEM>::RD, SD>& g, int q, int a, double (&out)[SD]) {
+__device__ __forceinline__ void shape_grad_rows(const double (&Jinv)[ET<ELEM>::RD][SD], int q, int a, double (&out)[SD]) {
   constexpr int RD = ET<ELEM>::RD;
   if constexpr (!ET<ELEM>::P2) {
 #pragma unroll
@@ -124,8 +161,8 @@ __device__ __forceinline__ void shape_grad(const Geom<ET<ELEM>::RD, SD>& g, int 
       double first = 0.0, pick = 0.0;
 #pragma unroll
       for (int r = 0; r < RD; ++r) {
-        first -= g.Jinv[r][s];
-        pick = (a == r + 1) ? g.Jinv[r][s] : pick;
+        first -= Jinv[r][s];
+        pick = (a == r + 1) ? Jinv[r][s] : pick;
       }
       out[s] = (a == 0) ? first : pick;
     }
@@ -133,16 +170,21 @@ __device__ __forceinline__ void shape_grad(const Geom<ET<ELEM>::RD, SD>& g, int 
     static_assert(ELEM == FES_P2_TRI, "gradient forms on P2 are implemented for the triangle only");
 #pragma unroll
     for (int s = 0; s < SD; ++s)
-      out[s] = c_p2tri_dshape[q][a][0] * g.Jinv[0][s] + c_p2tri_dshape[q][a][1] * g.Jinv[1][s];
+      out[s] = c_p2tri_dshape[q][a][0] * Jinv[0][s] + c_p2tri_dshape[q][a][1] * Jinv[1][s];
   }
+}
+
+template <int ELEM, int SD>
+__device__ __forceinline__ void shape_grad(const Geom<ET<ELEM>::RD, SD>& g, int q, int a, double (&out)[SD]) {
+  shape_grad_rows<ELEM, SD>(g.Jinv, q, a, out);
 }
 
 template <int ELEM>
 __device__ __forceinline__ double mass_ref(int a, int b) {
   constexpr int N = ET<ELEM>::N;
-  if constexpr (!ET<ELEM>::P2) return ((a == b) ? 2.0 : 1.0) / (double)(N * (N + 1));
-  else if constexpr (ELEM == FES_P2_TRI) return c_p2tri_mass180[a][b] / 180.0;
-  else return c_p2line_mass30[a][b] / 30.0;
+  if constexpr (!ET<ELEM>::P2) return (a == b) ? 2.0 / (double)(N * (N + 1)) : 1.0 / (double)(N * (N + 1));
+  else if constexpr (ELEM == FES_P2_TRI) return c_p2tri_mass[a][b];
+  else return c_p2line_mass[a][b];
 }
 
 struct Material {

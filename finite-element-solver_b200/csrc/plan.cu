@@ -111,132 +111,20 @@ __global__ void k_fill_ne(const int32_t* __restrict__ pair_row, const int32_t* _
   }
 }
 
-// per pair: tile-relative row and contribution offset; per contribution: the tile-local record
-// index of (row node, element) packed with the local node indices
-__global__ void k_tile_codes(const int32_t* __restrict__ pair_row, const uint32_t* __restrict__ pair_start,
-                             const uint32_t* __restrict__ contrib, int64_t n_pairs, int N,
-                             const int32_t* __restrict__ ne_ptr, const uint32_t* __restrict__ ne_code,
-                             const int32_t* __restrict__ tile_node0, int64_t n_tiles,
-                             uint16_t* __restrict__ contrib16, uint8_t* __restrict__ pair_lrow) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pairs) return;
-  const int32_t v = pair_row[p];
-  int64_t lo = 0, hi = n_tiles;  // last tile with tile_node0[t] <= v
-  while (hi - lo > 1) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (tile_node0[mid] <= v) lo = mid; else hi = mid;
-  }
-  const int32_t v0 = tile_node0[lo];
-  const int32_t g0 = ne_ptr[v0], gv0 = ne_ptr[v], gv1 = ne_ptr[v + 1];
-  const int N2 = N * N;
-  pair_lrow[p] = (uint8_t)(v - v0);
-  const uint32_t k0 = pair_start[p], k1 = pair_start[p + 1];
-  for (uint32_t k = k0; k < k1; ++k) {
-    const uint32_t code = contrib[k], e = code / N2, ab = code - e * N2, a = ab / N, b = ab - a * N;
-    int32_t l = gv0, h = gv1;  // lower_bound of e in v's ascending incident list
-    while (l < h) {
-      const int32_t m = (l + h) >> 1;
-      if ((ne_code[m] >> 3) < e) l = m + 1; else h = m;
-    }
-    contrib16[k] = (uint16_t)(((uint32_t)(l - g0) << 6) | (a << 3) | b);
-  }
-}
+// ---- per-tile build ---------------------------------------------------------------------------
+constexpr int kTileIdCap = 2048;   // ids sorted per tile: records, then distinct elements x corner nodes
+constexpr int kTileRecCap = 1024;  // distinct elements per tile (10-bit record index in a code)
 
-// Active pairs of a tile (w >= v): count them and their contributions; flag anything the packed
-// metadata cannot hold.
-__global__ void k_tile_count(const int32_t* __restrict__ tile_node0, int64_t n_tiles,
-                             const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ node_adj,
-                             const int32_t* __restrict__ pair_row, const uint32_t* __restrict__ pair_start,
-                             int32_t* __restrict__ act_cnt, int32_t* __restrict__ con_cnt, int* __restrict__ bad) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_tiles) return;
-  const int32_t p0 = node_ptr[tile_node0[t]], p1 = node_ptr[tile_node0[t + 1]];
-  int32_t na = 0, nc = 0;
-  for (int32_t p = p0; p < p1; ++p) {
-    if (node_adj[p] < pair_row[p]) continue;
-    const uint32_t c = pair_start[p + 1] - pair_start[p];
-    if (c > 255u) atomicExch(bad, 1);
-    ++na;
-    nc += (int32_t)c;
-  }
-  if (nc > 65535) atomicExch(bad, 1);
-  act_cnt[t] = na;
-  con_cnt[t] = nc;
-}
-
-// Emit a tile's active pairs in descending contribution count (stable), so the 32 pairs a warp
-// gathers have equal trip counts, with their packed metadata and their contribution codes.
-__global__ void k_tile_active(const int32_t* __restrict__ tile_node0, int64_t n_tiles,
-                              const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ node_adj,
-                              const int32_t* __restrict__ pair_row, const uint32_t* __restrict__ pair_start,
-                              const uint16_t* __restrict__ contrib16, const int32_t* __restrict__ tile_act0,
-                              const int32_t* __restrict__ tile_con0, int c, uint4* __restrict__ meta,
-                              uint16_t* __restrict__ codes) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_tiles) return;
-  const int32_t p0 = node_ptr[tile_node0[t]], p1 = node_ptr[tile_node0[t + 1]];
-  uint32_t hi = 0;
-  for (int32_t p = p0; p < p1; ++p)
-    if (node_adj[p] >= pair_row[p]) hi = max(hi, pair_start[p + 1] - pair_start[p]);
-  int32_t wa = tile_act0[t];
-  const int32_t con_base = tile_con0[t];
-  uint32_t off = 0;
-  while (hi > 0) {
-    uint32_t next = 0;
-    for (int32_t p = p0; p < p1; ++p) {
-      const int32_t v = pair_row[p], w = node_adj[p];
-      if (w < v) continue;
-      const uint32_t k0 = pair_start[p], cnt = pair_start[p + 1] - k0;
-      if (cnt == hi) {
-        const int32_t npv = node_ptr[v], degv = node_ptr[v + 1] - npv;
-        const int32_t npw = node_ptr[w], degw = node_ptr[w + 1] - npw;
-        int32_t lo_ = npw, hi_ = npw + degw;  // slot of v in row w (the pattern is symmetric)
-        while (lo_ < hi_) {
-          const int32_t m = (lo_ + hi_) >> 1;
-          if (node_adj[m] < v) lo_ = m + 1; else hi_ = m;
-        }
-        uint4 mt;
-        mt.x = off | (cnt << 16) | ((w == v ? 1u : 0u) << 24);
-        mt.y = (uint32_t)c * (uint32_t)npv + (uint32_t)(p - npv);
-        mt.z = (uint32_t)c * (uint32_t)npw + (uint32_t)(lo_ - npw);
-        mt.w = (uint32_t)degv | ((uint32_t)degw << 16);
-        meta[wa++] = mt;
-        for (uint32_t k = 0; k < cnt; ++k) codes[con_base + off + k] = contrib16[k0 + k];
-        off += cnt;
-      } else if (cnt < hi) {
-        next = max(next, cnt);
-      }
-    }
-    hi = next;
-  }
-}
-
-// One CTA per tile: collect the corner nodes of the tile's records, sort them (bitonic, shared
-// memory), keep the distinct ones, and re-express every record's corners as indices into that list.
-constexpr int kTileIdCap = 1024;  // records per tile (<= 256) x corner nodes (<= 4)
-__global__ void __launch_bounds__(256)
-k_tile_nodes(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__ ne_ptr,
-             const uint32_t* __restrict__ ne_code, const int32_t* __restrict__ en, int N, int n_corner,
-             int32_t* __restrict__ tile_nodes, int32_t* __restrict__ tile_nnod, uint32_t* __restrict__ rec_local,
-             int* __restrict__ bad) {
-  __shared__ uint32_t ids[kTileIdCap];
-  __shared__ uint32_t uniq[kTileIdCap];
-  __shared__ int s_count;
-  const int t = blockIdx.x;
-  const int32_t g0 = ne_ptr[tile_node0[t]], g1 = ne_ptr[tile_node0[t + 1]];
-  const int n_ids = (g1 - g0) * n_corner;
-  for (int i = threadIdx.x; i < kTileIdCap; i += blockDim.x) {
-    uint32_t v = 0xffffffffu;
-    if (i < n_ids) {
-      const int r = i / n_corner, k = i - r * n_corner;
-      v = (uint32_t)en[(int64_t)(ne_code[g0 + r] >> 3) * N + k];
-    }
-    ids[i] = v;
-  }
+// Block-wide (256 threads): sort ids[0..n) ascending (bitonic over the enclosing power of two) and
+// write the distinct values to out[]; returns their count.  s_cnt holds 257 ints.
+__device__ int sort_unique(uint32_t* ids, uint32_t* out, int n, int* s_cnt) {
+  int cap = 2;
+  while (cap < n) cap <<= 1;
+  for (int i = n + threadIdx.x; i < cap; i += blockDim.x) ids[i] = 0xffffffffu;
   __syncthreads();
-  for (int k = 2; k <= kTileIdCap; k <<= 1)
+  for (int k = 2; k <= cap; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < kTileIdCap; i += blockDim.x) {
+      for (int i = threadIdx.x; i < cap; i += blockDim.x) {
         const int l = i ^ j;
         if (l > i) {
           const uint32_t a = ids[i], b = ids[l];
@@ -246,20 +134,68 @@ k_tile_nodes(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__
       }
       __syncthreads();
     }
-  if (threadIdx.x == 0) {  // <= 1024 entries: a serial compaction is cheap next to the sort
-    int c = 0;
-    for (int i = 0; i < n_ids; ++i)
-      if (i == 0 || ids[i] != ids[i - 1]) uniq[c++] = ids[i];
-    s_count = c;
-    tile_nnod[t] = c;
-    if (c > 255) atomicExch(bad, 1);
+  const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+  int c = 0;
+  for (int i = lo; i < hi; ++i) c += (i == 0 || ids[i] != ids[i - 1]);
+  s_cnt[threadIdx.x] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < (int)blockDim.x; ++i) { const int t = s_cnt[i]; s_cnt[i] = run; run += t; }
+    s_cnt[blockDim.x] = run;
   }
   __syncthreads();
-  const int nd = s_count;
+  int w = s_cnt[threadIdx.x];
+  for (int i = lo; i < hi; ++i)
+    if (i == 0 || ids[i] != ids[i - 1]) out[w++] = ids[i];
+  __syncthreads();
+  return s_cnt[blockDim.x];
+}
+
+// One CTA per tile: the distinct elements touching the tile's nodes (ascending id), the distinct
+// corner nodes of those elements (ascending), and every element's corners as indices into that list.
+__global__ void __launch_bounds__(256)
+k_tile_build(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__ ne_ptr,
+             const uint32_t* __restrict__ ne_code, const int32_t* __restrict__ en, int N, int n_corner,
+             uint32_t* __restrict__ tile_elems, uint32_t* __restrict__ rec_local, int32_t* __restrict__ tile_nodes,
+             int32_t* __restrict__ tile_cnt, int* __restrict__ bad) {
+  __shared__ uint32_t ids[kTileIdCap];
+  __shared__ uint32_t uniq[kTileIdCap];
+  __shared__ uint32_t s_el[kTileRecCap];
+  __shared__ int s_cnt[257];
+  const int t = blockIdx.x;
+  const int32_t g0 = ne_ptr[tile_node0[t]], g1 = ne_ptr[tile_node0[t + 1]];
+  const int n_rec = g1 - g0;  // <= inc_max <= kTileRecCap
+  for (int i = threadIdx.x; i < n_rec; i += blockDim.x) ids[i] = ne_code[g0 + i] >> 3;
+  __syncthreads();
+  const int ne = sort_unique(ids, uniq, n_rec, s_cnt);
+  for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+    s_el[i] = uniq[i];
+    tile_elems[g0 + i] = uniq[i];
+  }
+  __syncthreads();
+  const int n_ids = ne * n_corner;
+  if (n_ids > kTileIdCap) {  // uniform across the CTA
+    if (threadIdx.x == 0) { atomicExch(bad, 1); tile_cnt[2 * t] = ne; tile_cnt[2 * t + 1] = 0; }
+    return;
+  }
+  for (int i = threadIdx.x; i < n_ids; i += blockDim.x) {
+    const int r = i / n_corner, k = i - r * n_corner;
+    ids[i] = (uint32_t)en[(int64_t)s_el[r] * N + k];
+  }
+  __syncthreads();
+  const int nd = sort_unique(ids, uniq, n_ids, s_cnt);
+  if (threadIdx.x == 0) {
+    tile_cnt[2 * t] = ne;
+    tile_cnt[2 * t + 1] = nd;
+    if (nd > 255) atomicExch(bad, 1);
+  }
   if (nd > 255) return;
-  for (int i = threadIdx.x; i < nd; i += blockDim.x) tile_nodes[(int64_t)t * fes_plan::kTileNodeStride + i] = (int32_t)uniq[i];
-  for (int r = threadIdx.x; r < g1 - g0; r += blockDim.x) {
-    const int64_t e = ne_code[g0 + r] >> 3;
+  for (int i = threadIdx.x; i < nd; i += blockDim.x)
+    tile_nodes[(int64_t)t * fes_plan::kTileNodeStride + i] = (int32_t)uniq[i];
+  for (int r = threadIdx.x; r < ne; r += blockDim.x) {
+    const int64_t e = s_el[r];
     uint32_t packed = 0;
     for (int k = 0; k < n_corner; ++k) {
       const uint32_t node = (uint32_t)en[e * N + k];
@@ -271,6 +207,111 @@ k_tile_nodes(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__
       packed |= (uint32_t)lo << (8 * k);
     }
     rec_local[g0 + r] = packed;
+  }
+}
+
+// Work items of a pair with `cnt` contributions when an item takes at most L of them: a power-of-two
+// group of lanes (so a fixed xor-shuffle tree sums the partial blocks) with m contributions each.
+__device__ __forceinline__ void item_split(uint32_t cnt, uint32_t L, uint32_t& lg, uint32_t& m) {
+  const uint32_t need = (cnt + L - 1) / L;
+  lg = 0;
+  while ((1u << lg) < need && lg < 5) ++lg;
+  m = (cnt + (1u << lg) - 1) >> lg;
+}
+
+// packed tile headers (12 ints): {g0, ne, p0, n_pairs}, {c0, n_con, n_distinct_nodes, v0},
+// {i0 (filled in by the host scan), n_items, 0, 0}
+__global__ void k_tile_hdr(const int32_t* __restrict__ tile_node0, int64_t n_tiles, const int32_t* __restrict__ ne_ptr,
+                           const int32_t* __restrict__ node_ptr, const uint32_t* __restrict__ pair_start,
+                           const int32_t* __restrict__ tile_cnt, uint32_t L, int32_t* __restrict__ hdr,
+                           int* __restrict__ bad) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const int32_t v0 = tile_node0[t], v1 = tile_node0[t + 1];
+  const int32_t p0 = node_ptr[v0], p1 = node_ptr[v1];
+  const uint32_t c0 = pair_start[p0], c1 = pair_start[p1];
+  int32_t items = 0;
+  for (int32_t p = p0; p < p1; ++p) {
+    const uint32_t cnt = pair_start[p + 1] - pair_start[p];
+    uint32_t lg, m;
+    item_split(cnt, L, lg, m);
+    if (m > L) atomicExch(bad, 1);  // a pair shared by > 32 L elements: keep the untiled kernel
+    items += 1 << lg;
+  }
+  int32_t* h = hdr + t * fes_plan::kHdrInts;
+  h[0] = ne_ptr[v0]; h[1] = tile_cnt[2 * t]; h[2] = p0; h[3] = p1 - p0;
+  h[4] = (int32_t)c0; h[5] = (int32_t)(c1 - c0); h[6] = tile_cnt[2 * t + 1]; h[7] = v0;
+  h[8] = 0; h[9] = items; h[10] = 0; h[11] = 0;
+}
+
+// Emit a tile's work items: 4 bytes of metadata and exactly L contribution codes each (short items
+// are padded with the all-zero record, so the kernel's gather loop has no trip count at all).
+// A pair with more than L contributions is split over a power-of-two group of adjacent lanes (a
+// diagonal pair of a triangle mesh: 6-8 contributions over 4 lanes).  Order: descending group size
+// (keeps groups aligned), descending trips, then slot-in-row, then node -- so neighbouring threads
+// handle the SAME relative neighbour of consecutive nodes.  On a regularly numbered mesh their
+// record indices then form a constant-stride sequence, which the rec_slot swizzle spreads over all
+// banks (conflict-free gathers); on an irregular mesh any order is equally random.
+//   meta = q (16) | deg (12) | lg (3) | writer (1);  code = byte offset of g~_a | byte offset of g~_b << 16
+__global__ void k_tile_emit(const int32_t* __restrict__ hdr, int64_t n_tiles, const int32_t* __restrict__ node_ptr,
+                            const int32_t* __restrict__ pair_row, const int32_t* __restrict__ node_adj,
+                            const uint32_t* __restrict__ pair_start, const uint32_t* __restrict__ contrib,
+                            const uint32_t* __restrict__ tile_elems, int N, int c, int gs, uint32_t L,
+                            uint32_t* __restrict__ meta, uint32_t* __restrict__ codes, int* __restrict__ bad) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const int32_t* h = hdr + t * fes_plan::kHdrInts;
+  const int32_t g0 = h[0], ne = h[1], p0 = h[2], p1 = h[2] + h[3], v0 = h[7];
+  const int N2 = N * N;
+  const uint32_t zero_code = ((uint32_t)(gs - 1) << 4) * 0x10001u;
+  uint32_t hi = 0;  // class key: lg << 8 | m
+  int32_t max_deg = 0, v1 = v0;
+  for (int32_t p = p0; p < p1; ++p) {
+    uint32_t lg, m;
+    item_split(pair_start[p + 1] - pair_start[p], L, lg, m);
+    hi = max(hi, (lg << 8) | m);
+  }
+  if (p1 > p0) v1 = pair_row[p1 - 1] + 1;
+  for (int32_t v = v0; v < v1; ++v) max_deg = max(max_deg, node_ptr[v + 1] - node_ptr[v]);
+  if (max_deg > 4095 || h[9] > 65535) { atomicExch(bad, 1); return; }
+  int64_t wa = h[8];
+  while (hi > 0) {
+    uint32_t next = 0;
+    for (int32_t sl = 0; sl < max_deg; ++sl)
+      for (int32_t v = v0; v < v1; ++v) {
+        const int32_t npv = node_ptr[v], degv = node_ptr[v + 1] - npv;
+        if (sl >= degv) continue;
+        const int32_t p = npv + sl;
+        const uint32_t k0 = pair_start[p], cnt = pair_start[p + 1] - k0;
+        uint32_t lg, m;
+        item_split(cnt, L, lg, m);
+        const uint32_t key = (lg << 8) | m;
+        if (key == hi) {
+          const uint32_t q = (uint32_t)c * (uint32_t)(npv - p0) + (uint32_t)sl;
+          if (q > 65535u) atomicExch(bad, 1);
+          for (uint32_t j = 0; j < (1u << lg); ++j, ++wa) {
+            meta[wa] = (q & 0xffffu) | ((uint32_t)degv << 16) | (lg << 28) | ((j == 0 ? 1u : 0u) << 31);
+            for (uint32_t x = 0; x < L; ++x) {
+              const uint32_t k = j * m + x;
+              uint32_t out = zero_code;
+              if (x < m && k < cnt) {
+                const uint32_t code = contrib[k0 + k], e = code / N2, ab = code - e * N2, a = ab / N, b = ab - a * N;
+                int lo = 0, hi_ = ne;  // record of element e: its rank among the tile's distinct elements
+                while (lo < hi_) {
+                  const int mid = (lo + hi_) >> 1;
+                  if (tile_elems[g0 + mid] < e) lo = mid + 1; else hi_ = mid;
+                }
+                const uint32_t slot = rec_slot((uint32_t)lo);
+                out = ((a * (uint32_t)gs + slot) << 4) | ((b * (uint32_t)gs + slot) << 20);
+              }
+              codes[wa * L + x] = out;
+            }
+          }
+        } else if (key < hi) {
+          next = max(next, key);
+        }
+      }
+    hi = next;
   }
 }
 
@@ -287,10 +328,10 @@ int bits_for(uint64_t max_value) {
 
 // Tile the node range for the fused assembly kernel.  The greedy split runs on the host over the
 // two prefix arrays (O(n_nodes), once per mesh); everything else stays on the device.
-int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, int gmax, bool* retry) {
+int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, int inc_max, bool* retry) {
   *retry = false;
   const int64_t nn = P->n_nodes, np_ = P->n_pairs;
-  const int N = P->N;
+  const int N = P->N, c = P->c;
   P->tiled = false;
   if (np_ == 0) return FES_OK;
   DevBuf<int32_t> ne_cnt;
@@ -312,105 +353,101 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
   P->n_geo = h_ne[nn];
   if (P->n_geo != P->n_el * N) return FES_OK;  // degenerate elements (repeated nodes): keep the untiled kernel
   if (P->n_el >= ((int64_t)1 << 29)) return FES_OK;
-  P->geo_max = gmax;
+  P->inc_max = inc_max;
+  // a tile's value image stays under 32 KB of shared memory, its packed offsets under 16 bits
+  const int pair_cap = std::min(32768 / (8 * c * c), 65535 / c);
   std::vector<int32_t> tiles;
   tiles.push_back(0);
   int64_t v0 = 0;
   for (int64_t v = 0; v < nn; ++v) {
-    const int64_t geo = h_ne[v + 1] - h_ne[v0];
-    if (h_ne[v + 1] - h_ne[v] > gmax) return FES_OK;  // one node alone overflows a tile: untiled kernel
-    if (geo > gmax || v - v0 >= 255) {
+    if (h_ne[v + 1] - h_ne[v] > inc_max || h_np[v + 1] - h_np[v] > pair_cap) return FES_OK;  // one node overflows a tile
+    if (h_ne[v + 1] - h_ne[v0] > inc_max || h_np[v + 1] - h_np[v0] > pair_cap || v - v0 >= 255) {
       tiles.push_back((int32_t)v);
       v0 = v;
     }
   }
   tiles.push_back((int32_t)nn);
   P->n_tiles = (int64_t)tiles.size() - 1;
+  const int64_t nt = P->n_tiles;
   FES_CUDA(P->tile_node0.alloc(tiles.size()));
   FES_CUDA(cudaMemcpyAsync(P->tile_node0.p, tiles.data(), tiles.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
   FES_CUDA(P->ne_code.alloc(P->n_geo));
   k_fill_ne<<<grid_for(np_, kBlock), kBlock, 0, stream>>>(P->pair_row.p, P->node_adj.p, P->pair_start.p, P->contrib.p, np_,
                                                           N, P->ne_ptr.p, P->ne_code.p);
   FES_LAUNCH_CHECK();
-  FES_CUDA(P->contrib16.alloc(P->n_contrib + 16));
-  FES_CUDA(P->pair_lrow.alloc(np_ + 32));
-  k_tile_codes<<<grid_for(np_, kBlock), kBlock, 0, stream>>>(P->pair_row.p, P->pair_start.p, P->contrib.p, np_, N,
-                                                             P->ne_ptr.p, P->ne_code.p, P->tile_node0.p, P->n_tiles,
-                                                             P->contrib16.p, P->pair_lrow.p);
-  FES_LAUNCH_CHECK();
 
-  // active pairs (w >= v) per tile: counts -> offsets -> sorted emission with packed metadata
-  const int64_t nt = P->n_tiles;
-  DevBuf<int32_t> act_cnt, con_cnt;
-  DevBuf<int> bad;
-  FES_CUDA(act_cnt.alloc(nt + 1)); FES_CUDA(con_cnt.alloc(nt + 1)); FES_CUDA(bad.alloc(1));
-  FES_CUDA(cudaMemsetAsync(act_cnt.p, 0, act_cnt.bytes(), stream));
-  FES_CUDA(cudaMemsetAsync(con_cnt.p, 0, con_cnt.bytes(), stream));
-  FES_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), stream));
-  k_tile_count<<<grid_for(nt, 64), 64, 0, stream>>>(P->tile_node0.p, nt, P->node_ptr.p, P->node_adj.p, P->pair_row.p,
-                                                    P->pair_start.p, act_cnt.p, con_cnt.p, bad.p);
-  FES_LAUNCH_CHECK();
-  FES_CUDA(P->tile_act0.alloc(nt + 1));
-  FES_CUDA(P->tile_con0.alloc(nt + 1));
-  size_t sb = 0;
-  FES_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, sb, act_cnt.p, P->tile_act0.p, nt + 1, stream));
-  if (sb > tmp.bytes()) FES_CUDA(tmp.alloc(sb));
-  FES_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, sb, act_cnt.p, P->tile_act0.p, nt + 1, stream));
-  FES_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, sb, con_cnt.p, P->tile_con0.p, nt + 1, stream));
-  count_launch(4);
-  std::vector<int32_t> h_act(nt + 1), h_con(nt + 1);
-  int h_bad = 0;
-  FES_CUDA(cudaMemcpyAsync(h_act.data(), P->tile_act0.p, (nt + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-  FES_CUDA(cudaMemcpyAsync(h_con.data(), P->tile_con0.p, (nt + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-  FES_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  FES_CUDA(cudaStreamSynchronize(stream));
-  if (h_bad) return FES_OK;  // a pair shared by > 255 elements: keep the untiled kernel
-  P->n_active = h_act[nt];
-  P->n_act_contrib = h_con[nt];
-  int amax = 0, cmax = 0, dmax = 0;
-  for (int64_t t = 0; t < nt; ++t) {
-    amax = std::max(amax, h_act[t + 1] - h_act[t]);
-    cmax = std::max(cmax, h_con[t + 1] - h_con[t]);
-  }
-  for (int64_t v = 0; v < nn; ++v) dmax = std::max(dmax, h_np[v + 1] - h_np[v]);
-  if (dmax > 65535) return FES_OK;
-  P->act_max = amax; P->con_max = cmax;
-  FES_CUDA(P->act_meta.alloc(P->n_active + 4));
-  FES_CUDA(P->act_codes.alloc(P->n_act_contrib + 16));
-  k_tile_active<<<grid_for(nt, 64), 64, 0, stream>>>(P->tile_node0.p, nt, P->node_ptr.p, P->node_adj.p, P->pair_row.p,
-                                                     P->pair_start.p, P->contrib16.p, P->tile_act0.p, P->tile_con0.p,
-                                                     P->c, P->act_meta.p, P->act_codes.p);
-  FES_LAUNCH_CHECK();
-
-  // distinct nodes per tile + local corner indices per record
+  // distinct elements and distinct corner nodes per tile
   P->n_corner = (N == 6) ? 3 : N;
-  if (gmax * P->n_corner > kTileIdCap) return FES_OK;
-  FES_CUDA(P->tile_nodes.alloc((size_t)nt * fes_plan::kTileNodeStride + 64));
-  FES_CUDA(P->tile_nnod.alloc(nt + 1));
-  FES_CUDA(P->rec_local.alloc(P->n_geo + 16));
+  DevBuf<int> bad;
+  FES_CUDA(bad.alloc(1));
   FES_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), stream));
-  k_tile_nodes<<<(unsigned)nt, 256, 0, stream>>>(P->tile_node0.p, P->ne_ptr.p, P->ne_code.p, d_elem_nodes, N, P->n_corner,
-                                                 P->tile_nodes.p, P->tile_nnod.p, P->rec_local.p, bad.p);
+  FES_CUDA(P->tile_elems.alloc(P->n_geo + 16));
+  FES_CUDA(P->rec_local.alloc(P->n_geo + 16));
+  FES_CUDA(P->tile_nodes.alloc((size_t)nt * fes_plan::kTileNodeStride + 64));
+  FES_CUDA(P->tile_cnt.alloc(2 * nt));
+  k_tile_build<<<(unsigned)nt, 256, 0, stream>>>(P->tile_node0.p, P->ne_ptr.p, P->ne_code.p, d_elem_nodes, N, P->n_corner,
+                                                 P->tile_elems.p, P->rec_local.p, P->tile_nodes.p, P->tile_cnt.p, bad.p);
   FES_LAUNCH_CHECK();
+  int h_bad = 0;
   FES_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
   FES_CUDA(cudaStreamSynchronize(stream));
   if (h_bad) {  // a tile touches > 255 distinct nodes (scattered node numbering): retry with smaller tiles
+    if (getenv("FES_PLAN_DEBUG")) {
+      std::vector<int32_t> cnts(2 * nt);
+      cudaMemcpy(cnts.data(), P->tile_cnt.p, cnts.size() * sizeof(int32_t), cudaMemcpyDeviceToHost);
+      int mr = 0, mn = 0;
+      for (int64_t t = 0; t < nt; ++t) { mr = std::max(mr, cnts[2 * t]); mn = std::max(mn, cnts[2 * t + 1]); }
+      fprintf(stderr, "[fes plan] retry: inc_max=%d tiles=%lld max distinct elements=%d max distinct nodes=%d\n", inc_max,
+              (long long)nt, mr, mn);
+    }
     *retry = true;
     return FES_OK;
   }
-  // packed tile headers: {g0, g1, a0, n_act}, {c0, n_con, n_distinct_nodes, v0}
-  {
-    std::vector<int32_t> h_nnod(nt);
-    FES_CUDA(cudaMemcpy(h_nnod.data(), P->tile_nnod.p, nt * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    std::vector<int32_t> hdr((size_t)nt * 8);
-    for (int64_t t = 0; t < nt; ++t) {
-      int32_t* h = hdr.data() + t * 8;
-      h[0] = h_ne[tiles[t]]; h[1] = h_ne[tiles[t + 1]]; h[2] = h_act[t]; h[3] = h_act[t + 1] - h_act[t];
-      h[4] = h_con[t]; h[5] = h_con[t + 1] - h_con[t]; h[6] = h_nnod[t]; h[7] = tiles[t];
-    }
-    FES_CUDA(P->tile_hdr.alloc(hdr.size() + 16));
-    FES_CUDA(cudaMemcpy(P->tile_hdr.p, hdr.data(), hdr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  // an item gathers at most L contributions.  L depends on the element type only, never on the mesh,
+  // so the summation tree of a pair is a function of its contribution count alone: a rank that
+  // assembles a slab with ghost elements produces the same bits as the single-GPU assembly.
+  const uint32_t L = (uint32_t)tile_item_len(N);
+  constexpr int HI = fes_plan::kHdrInts;
+  FES_CUDA(P->tile_hdr.alloc((size_t)nt * HI + 16));
+  FES_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), stream));
+  k_tile_hdr<<<grid_for(nt, kBlock), kBlock, 0, stream>>>(P->tile_node0.p, nt, P->ne_ptr.p, P->node_ptr.p, P->pair_start.p,
+                                                          P->tile_cnt.p, L, P->tile_hdr.p, bad.p);
+  FES_LAUNCH_CHECK();
+  std::vector<int32_t> hdr((size_t)nt * HI);
+  FES_CUDA(cudaMemcpyAsync(hdr.data(), P->tile_hdr.p, hdr.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  FES_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  FES_CUDA(cudaStreamSynchronize(stream));
+  if (h_bad) return FES_OK;
+  int rmax = 0, pmax = 0, cmax = 0, imax = 0;
+  int64_t rd = 0, items = 0;
+  for (int64_t t = 0; t < nt; ++t) {
+    int32_t* h = hdr.data() + t * HI;
+    rmax = std::max(rmax, h[1]); pmax = std::max(pmax, h[3]); cmax = std::max(cmax, h[5]); imax = std::max(imax, h[9]);
+    h[8] = (int32_t)items;
+    items += h[9];
+    rd += 4 * HI + (int64_t)h[9] * 4 * (1 + L) + (int64_t)h[1] * 4 + (int64_t)h[6] * 4;
   }
+  if (imax > 65535 || rmax > kTileRecCap || items * L >= ((int64_t)1 << 32)) return FES_OK;
+  P->rec_max = rmax; P->pair_max = pmax; P->con_max = cmax; P->item_max = imax; P->n_items = items;
+  // plane stride 1 (mod 8): plane n sits n x 16 B further in bank space, so pairs that read different
+  // nodes of the SAME record do not collide; slots are swizzled inside aligned groups of 8
+  P->geo_stride = ((rmax + 7) & ~7) + 1;
+  if ((int64_t)N * P->geo_stride * 16 > 65535) return FES_OK;  // 16-bit byte offsets in the codes
+  P->tile_read_bytes = rd;
+  if (getenv("FES_PLAN_DEBUG"))
+    fprintf(stderr, "[fes plan] N=%d c=%d nodes=%lld pairs=%lld tiles=%lld inc_max=%d rec_max=%d pair_max=%d item_max=%d con_max=%d items=%lld gs=%d\n",
+            N, c, (long long)nn, (long long)np_, (long long)nt, inc_max, rmax, pmax, imax, cmax, (long long)items, P->geo_stride);
+  FES_CUDA(cudaMemcpyAsync(P->tile_hdr.p, hdr.data(), hdr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  P->item_len = (int)L;
+  FES_CUDA(P->pair_meta.alloc(items + 16));
+  FES_CUDA(P->pair_codes.alloc(items * L + 32));
+  k_tile_emit<<<grid_for(nt, 64), 64, 0, stream>>>(P->tile_hdr.p, nt, P->node_ptr.p, P->pair_row.p, P->node_adj.p,
+                                                   P->pair_start.p, P->contrib.p, P->tile_elems.p, N, c, P->geo_stride, L,
+                                                   P->pair_meta.p, P->pair_codes.p, bad.p);
+  FES_LAUNCH_CHECK();
+  FES_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  FES_CUDA(cudaStreamSynchronize(stream));  // also keeps `hdr` alive until the upload is done
+  if (h_bad) return FES_OK;  // offsets beyond 16 bits: keep the untiled kernel
   P->tiled = true;
   return FES_OK;
 }
@@ -522,16 +559,17 @@ extern "C" int fes_plan_create(const int32_t* d_elem_nodes, int64_t n_el, int N,
   FES_LAUNCH_CHECK();
   FES_CUDA(cudaStreamSynchronize(stream));
   {
-    // tiles shrink until every tile references <= 255 distinct nodes; with records*corners <= 255
+    // tiles shrink until every tile references <= 255 distinct nodes; with elements*corners <= 255
     // that always holds, so a mesh with scattered node numbering is still tiled (smaller tiles)
-    int gmax = tile_geo_budget(N);
+    int inc = tile_inc_budget(N);
+    if (const char* env = getenv("FES_TILE_INC")) inc = std::max(16, std::min(kTileRecCap, atoi(env)));  // tuning knob
     const int n_corner = (N == 6) ? 3 : N;
     for (;;) {
       bool retry = false;
-      FES_TRY(build_tiles(P, d_elem_nodes, stream, gmax, &retry));
+      FES_TRY(build_tiles(P, d_elem_nodes, stream, inc, &retry));
       if (!retry) break;
-      if (gmax * n_corner <= 255) break;  // cannot happen: such tiles always fit
-      gmax = std::max(255 / n_corner, gmax / 2);
+      if (inc * n_corner <= 255) break;  // cannot happen: such tiles always fit
+      inc = std::max(255 / n_corner, inc - std::max(1, inc / 8));  // shrink gently: usually a few tiles overflow
     }
   }
   guard.p = nullptr;
@@ -550,18 +588,15 @@ extern "C" int64_t fes_plan_bytes(const fes_plan* p) {
   if (!p) return 0;
   return (int64_t)(p->node_ptr.bytes() + p->node_adj.bytes() + p->pair_row.bytes() + p->pair_start.bytes() +
                    p->contrib.bytes() + p->indptr.bytes() + p->indices.bytes() + p->ne_ptr.bytes() +
-                   p->ne_code.bytes() + p->tile_node0.bytes() + p->tile_act0.bytes() + p->tile_con0.bytes() +
-                   p->act_meta.bytes() + p->act_codes.bytes() + p->contrib16.bytes() + p->pair_lrow.bytes() +
-                   p->tile_nodes.bytes() + p->tile_nnod.bytes() + p->rec_local.bytes());
+                   p->ne_code.bytes() + p->tile_node0.bytes() + p->tile_elems.bytes() + p->rec_local.bytes() +
+                   p->tile_nodes.bytes() + p->tile_cnt.bytes() + p->tile_hdr.bytes() + p->pair_meta.bytes() +
+                   p->pair_codes.bytes());
 }
 
 // what one fused assembly streams from the plan (overhead on top of the algorithmic bytes)
 extern "C" int64_t fes_plan_read_bytes(const fes_plan* p) {
   if (!p) return 0;
-  if (p->tiled)
-    return (int64_t)(p->ne_ptr.bytes() + p->tile_node0.bytes() + p->tile_act0.bytes() + p->tile_con0.bytes() +
-                     p->act_meta.bytes() + p->act_codes.bytes() + p->rec_local.bytes() + p->tile_nnod.bytes() +
-                     (int64_t)p->n_tiles * 4 * 128 /* distinct-node lists, ~128 used per tile */);
+  if (p->tiled) return p->tile_read_bytes;
   return (int64_t)(p->pair_row.bytes() + p->pair_start.bytes() + p->contrib.bytes() + p->node_ptr.bytes() +
                    p->indptr.bytes());
 }

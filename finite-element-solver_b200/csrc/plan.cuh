@@ -18,47 +18,67 @@ struct fes_plan {
   fes::DevBuf<int32_t> indices;  // nnz
 
   // ---- tiled layout for the fused assembly kernel ------------------------------------------
-  // A tile is a run of consecutive nodes whose (node, incident element) records fit in shared
-  // memory.  Phase 1 of the kernel evaluates one geometry record per (node, element); phase 2
-  // gathers the contributions of the tile's ACTIVE pairs -- pairs (v, w) with w >= v; the block of
-  // (w, v) is the transpose and is written by the same thread.
+  // A tile is a run of consecutive nodes = a contiguous range of stored pairs = a contiguous range
+  // of CSR values.  Phase 1 of the kernel evaluates one geometry record per DISTINCT element
+  // touching the tile; phase 2 gathers the contributions of every pair of the tile into a
+  // shared-memory image of the tile's values, which one TMA bulk store writes out.
   bool tiled = false;
-  int64_t n_tiles = 0, n_geo = 0, n_active = 0, n_act_contrib = 0;
-  int geo_max = 0;                     // records per tile upper bound
-  int act_max = 0, con_max = 0;        // active pairs / their contributions per tile, upper bounds
+  int64_t n_tiles = 0, n_geo = 0, tile_read_bytes = 0;
+  int inc_max = 0;                     // (node, incident element) records per tile: the tiling budget
+  int geo_stride = 0;                  // shared-memory plane stride of the records: 1 (mod 8), > rec_max
+  int rec_max = 0, pair_max = 0, con_max = 0, item_max = 0;  // distinct elements / pairs / contributions / work items per tile, upper bounds
+  int64_t n_items = 0;
+  int item_len = 0;                    // contribution codes per work item (= tile_item_len(N))
   fes::DevBuf<int32_t> ne_ptr;         // n_nodes + 1 : incident-element ranges per node
   fes::DevBuf<uint32_t> ne_code;       // n_geo : e*8 + a, ascending e per node
   fes::DevBuf<int32_t> tile_node0;     // n_tiles + 1
-  fes::DevBuf<int32_t> tile_act0;      // n_tiles + 1 : active-pair ranges
-  fes::DevBuf<int32_t> tile_con0;      // n_tiles + 1 : ranges in act_codes
-  fes::DevBuf<uint4> act_meta;         // n_active : per active pair, in descending contribution count per tile:
-                                       //   x = off16 | cnt8<<16 | diag<<24, y = q0 own, z = q0 mirror,
-                                       //   w = deg own | deg mirror<<16;  row i of a block starts at C*(q0 + i*deg)
-  fes::DevBuf<uint16_t> act_codes;     // n_act_contrib : (record index in tile)<<6 | a<<3 | b, ascending element id
-  // distinct nodes referenced by a tile's records (so coordinates are gathered once per tile) and
-  // each record's corner nodes as indices into that list
+  // distinct elements of a tile (ascending id) at [g0, g0 + ne), g0 = ne_ptr[first node]; each
+  // element's corner nodes as indices into the tile's sorted distinct-node list
   static constexpr int kTileNodeStride = 256;
   int n_corner = 0;                    // corner nodes stored per record (N, or 3 for the 6-node triangle)
-  fes::DevBuf<int32_t> tile_nodes;     // n_tiles * 256 : sorted distinct node ids (first tile_nnod[t] valid)
-  fes::DevBuf<int32_t> tile_nnod;      // n_tiles
-  fes::DevBuf<int32_t> tile_hdr;       // n_tiles * 8 : {g0, g1, a0, n_act, c0, n_con, n_distinct, v0}
-  fes::DevBuf<uint32_t> rec_local;     // n_geo : corner k's index in the tile list at bits [8k, 8k+8)
-  // build-time only (kept for k_assemble_precomputed and the untiled fallback): see above
-  fes::DevBuf<uint16_t> contrib16;     // n_contrib : tile-relative codes in pair order
-  fes::DevBuf<uint8_t> pair_lrow;      // n_pairs : row node relative to the tile's first node
+  fes::DevBuf<uint32_t> tile_elems;    // n_geo (+pad)
+  fes::DevBuf<uint32_t> rec_local;     // n_geo (+pad) : corner k's index in the tile list at bits [8k, 8k+8)
+  fes::DevBuf<int32_t> tile_nodes;     // n_tiles * 256 : sorted distinct node ids (first nd valid)
+  fes::DevBuf<int32_t> tile_cnt;       // n_tiles * 2 : {distinct elements, distinct nodes}
+  static constexpr int kHdrInts = 12;
+  fes::DevBuf<int32_t> tile_hdr;       // n_tiles * 12 : {g0, ne, p0, n_pairs}, {c0, n_con, n_distinct_nodes, v0}, {i0, n_items, 0, 0}
+  // work items of a tile (a pair, or one of the 2^lg lanes that share a long pair), ordered by
+  // descending group size, descending trips, slot-in-row, node:
+  //   meta = q (16) | deg (12) | lg (3) | writer (1);  row i of the pair's C x C block starts at double
+  //   C*(q + i*deg) of the tile's value image.  Item t owns codes [t*item_len, (t+1)*item_len).
+  fes::DevBuf<uint32_t> pair_meta;     // n_items (+pad)
+  fes::DevBuf<uint32_t> pair_codes;    // n_items * item_len (+pad) : 16*(a*geo_stride + slot) | 16*(b*geo_stride + slot) << 16
+                                       //   (byte offsets), slot = rec_slot(record index in tile); short items padded with
+                                       //   the zero record (slot geo_stride-1); ascending element id within an item
 
   // staging for the host-buffer entry point (fes_assemble_host), allocated on first use
   mutable fes::DevBuf<double> stage_coords, stage_values, stage_E, stage_scale;
 };
 
 namespace fes {
-// records per tile for an element with N nodes (sized for the largest record, elasticity)
-inline int tile_geo_budget(int N) {
+// Shared-memory slot of a tile's r-th distinct element: an XOR swizzle of the low three bits, so
+// strided record sequences (the k-th element of consecutive nodes) spread over the banks.  Baked
+// into the contribution codes at plan time; phase 1 of the kernel applies it when it writes.
+__host__ __device__ inline uint32_t rec_slot(uint32_t r) { return r ^ ((r >> 3) & 7u); }
+
+// contributions one lane gathers at most (longer pairs are split over 2^lg lanes): about the count of
+// an interior off-diagonal pair of that element type
+inline int tile_item_len(int N) {
+  switch (N) {
+    case 3: return 2;   // triangle edge: 2 elements (P2 line: 1-2)
+    case 4: return 6;   // tet edge: 4-6 elements
+    default: return 2;  // lines, P2 triangle (most pairs: 1-2)
+  }
+}
+
+// (node, incident element) records per tile for an element with N nodes: bounds the distinct
+// elements a tile can reference (sized for the largest record, elasticity)
+inline int tile_inc_budget(int N) {
   switch (N) {
     case 2: return 256;
-    case 3: return 256;    // 3-node: P1 triangle (6 doubles -> 12 KB) or P2 line
-    case 4: return 256;    // P1 tet (12 doubles -> 24 KB)
-    default: return 128;   // P2 triangle (36 doubles -> 36 KB)
+    case 3: return 384;    // P1 triangle (6 doubles per element record) or P2 line
+    case 4: return 384;    // P1 tet (12 doubles)
+    default: return 256;   // P2 triangle (36 doubles)
   }
 }
 }  // namespace fes

@@ -49,6 +49,36 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// Explicit shared-memory accesses by 32-bit shared address: the hot loops of the assembly kernel
+// keep their base addresses in registers instead of re-deriving the shared window from a generic
+// pointer at every access.
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds_u32x2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f64x2(uint32_t addr, double a, double b) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double a) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(a) : "memory");
+}
+
 // A stream of `count` elements of size ES starting at element i0 of `base`, staged with one bulk
 // copy from the enclosing 16-byte aligned window.  Returns the byte skew of element i0 inside
 // the window; the caller reads dst + skew.  Arrays are allocated with 32 bytes of tail padding.

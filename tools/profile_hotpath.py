@@ -27,6 +27,12 @@ if what in ('all', 'tri'):
             system.solve(prob.load_d)
         except RuntimeError as e:
             print('expected:', str(e)[:60])
+if what == 'trimass':
+    mesh = F.create_rect_mesh([[0, 0], [4, 1]], (2829, 708))
+    V = F.FunctionSpace(mesh, n_components=2)
+    for _ in range(4):
+        A = V.assemble_device(F.MassForm(2))
+    torch.cuda.synchronize()
 if what in ('all', 'tet'):
     mesh = F.create_box_mesh([[0, 0, 0], [1, 1, 1]], (61, 61, 61))
     V = F.FunctionSpace(mesh, n_components=3)
