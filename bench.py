@@ -202,7 +202,7 @@ def run_gpu(args):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get('k_assemble_tiles_c2_bytes_per_launch')
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': traffic, 'kernel': 'k_assemble_tiles<P1_TRI,ELASTIC,2,2>', 'peak_source': peak_src,
+                'traffic': traffic, 'kernel': 'k_assemble_tiles<P1_TRI,ELASTIC,2,2,128>', 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg_bytes, 'bytes_per_element': alg_bytes / n_el,
                 'plan_bytes_read_per_launch': plan.read_bytes}
 
@@ -352,12 +352,42 @@ def config5_metrics(F, world, rank, dev, n=151, pcg_iters=300):
             'pcg_iterations_timed': pcg_iters, 'scaling': 'strong'}
 
 
+def assembly_case(F, V, form, reps=20):
+    """Warm fused assembly of `form` on space V: ms per assembly (CUDA events), elements/s and the
+    algorithmic-byte fraction of the measured HBM peak (SURVEY 8d byte formula)."""
+    import torch
+    plan = V.plan()
+    A = V.assemble_device(form)
+    for _ in range(3):
+        V.assemble_device(form, out=A.data_d)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(reps):
+        V.assemble_device(form, out=A.data_d)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / reps
+    n_el, N = len(V.element_nodes), V.element_nodes.shape[1]
+    alg = 4 * N * n_el + 8 * V.spatial_dim * V.n_nodes + 8 * plan.nnz
+    return {'ms': ms, 'elements': n_el, 'nnz': plan.nnz, 'elements_per_s': n_el / (ms * 1e-3),
+            'algorithmic_bytes': alg, 'hbm_frac_of_measured': alg / (ms * 1e-3) / 1e9 / measured_peak()[0]}
+
+
 def extra_metrics(F, V, mesh, dev):
-    """Secondary numbers of BASELINE.json: the PCG solve of config 2 and SIMP iterations/sec on
-    config 4 (1201x401 nodes, 960 000 triangles, MBB beam)."""
+    """Secondary numbers of BASELINE.json: configs 1 and 3 (assembly only), the PCG solve of
+    config 2 and SIMP iterations/sec on config 4 (1201x401 nodes, 960 000 triangles, MBB beam)."""
     import torch
     from fes_b200.regions import in_box, intersect, on_plane
     out = {}
+    V1 = F.FunctionSpace(F.create_rect_mesh([[0, 0], [1, 1]], (225, 225)))
+    out['config1_p1_laplacian_225x225'] = assembly_case(F, V1, F.LaplacianForm())
+    del V1
+    V3 = F.FunctionSpace(F.create_rect_mesh([[0, 0], [1, 1]], (708, 708)), F.QuadraticTriangleElement, n_components=2)
+    out['config3_p2_elastic_708x708'] = assembly_case(F, V3, F.LinearElasticForm(F.LinearElasticMaterial(E, NU)))
+    out['config3_p2_mass_708x708'] = assembly_case(F, V3, F.MassForm(2))
+    del V3
+    torch.cuda.empty_cache()
     bc = F.BoundaryConditions()
     bc.add(F.BCType.DIRICHLET, on_plane(0, 0.0), [0, 0])
     bc.add(F.BCType.NEUMANN, on_plane(0, 4.0), [0, -1])

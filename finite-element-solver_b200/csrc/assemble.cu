@@ -147,10 +147,16 @@ struct RecLayout {
   static constexpr int DOUBLES = 2 * NV2 + NV1;
 };
 
-#ifndef FES_TILE_THREADS
-#define FES_TILE_THREADS 256
+// CTA size, measured (tools/tune_tiles.sh): 4 warps per CTA and more CTAs per SM win for the gradient
+// forms; the mass form (hardly any arithmetic) prefers 8 warps.  FES_TILE_THREADS overrides both.
+template <int FORM>
+constexpr int tile_threads() {
+#ifdef FES_TILE_THREADS
+  return FES_TILE_THREADS;
+#else
+  return FORM == FES_FORM_MASS ? 256 : 128;
 #endif
-constexpr int kTileThreads = FES_TILE_THREADS;
+}
 constexpr int kRecBatch = 2;  // records a thread evaluates per pass of phase 1 (memory-level parallelism)
 constexpr int kHdrRing = 4, kNodRing = 3;
 __host__ __device__ constexpr int item_len_of(int N) { return (N == 3) ? 2 : (N == 4) ? 6 : 2; }  // = tile_item_len(N)
@@ -184,7 +190,7 @@ struct TileDims {
   int geo_stride, rec_max, pair_max, item_max, con_max;
 };
 
-template <int ELEM, int FORM, int C, int SD>
+template <int ELEM, int FORM, int C, int SD, int kTileThreads>
 __global__ void __launch_bounds__(kTileThreads)
 k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32_t* __restrict__ tile_elems,
                  const uint32_t* __restrict__ rec_local, const int32_t* __restrict__ tile_nodes,
@@ -633,17 +639,18 @@ int run(const Job& j) {
       const TileDims dims{P->geo_stride, P->rec_max, P->pair_max, P->item_max, P->con_max};
       const size_t smem = TileSmem<ELEM, FORM, C, SD>::total(dims.geo_stride, dims.rec_max, dims.pair_max, dims.item_max,
                                                              dims.con_max);
+      constexpr int kTileThreads = tile_threads<FORM>();
       static size_t configured = 0;  // per template instantiation: largest opt-in so far
       static int per_sm = 0, sms = 0;
       if (per_sm == 0 || smem > configured) {
         if (smem + 1024 > 48 * 1024)  // static smem counts toward the 48 KB default
-          FES_CUDA(cudaFuncSetAttribute(k_assemble_tiles<ELEM, FORM, C, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          FES_CUDA(cudaFuncSetAttribute(k_assemble_tiles<ELEM, FORM, C, SD, kTileThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
         configured = std::max(configured, smem);
         int dev = 0;
         FES_CUDA(cudaGetDevice(&dev));
         FES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        FES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_tiles<ELEM, FORM, C, SD>,
+        FES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_tiles<ELEM, FORM, C, SD, kTileThreads>,
                                                                kTileThreads, smem));
         if (per_sm < 1) {
           per_sm = 0;
@@ -655,7 +662,7 @@ int run(const Job& j) {
       const int64_t grid = std::min<int64_t>(P->n_tiles, (int64_t)sms * per_sm);  // persistent CTAs
       static const bool no_tma = getenv("FES_NO_TMA_STORE") != nullptr;  // tuning knob: plain coalesced stores
       const int use_tma = (!no_tma && (reinterpret_cast<uintptr_t>(j.out) & 15) == 0) ? 1 : 0;
-      k_assemble_tiles<ELEM, FORM, C, SD><<<(unsigned)grid, kTileThreads, smem, j.stream>>>(
+      k_assemble_tiles<ELEM, FORM, C, SD, kTileThreads><<<(unsigned)grid, kTileThreads, smem, j.stream>>>(
           P->tile_hdr.p, (int)P->n_tiles, P->tile_elems.p, P->rec_local.p, P->tile_nodes.p, P->pair_meta.p,
           P->pair_codes.p, j.coords, cf, dims, use_tma, j.out);
       if (cf.sign < 0.0) {  // a negative global factor (ScaledForm): the kernel ran with |factor|
