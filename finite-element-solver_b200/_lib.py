@@ -35,6 +35,7 @@ SIGNATURES = {
     'fes_plan_n_dofs': (_i64, [_p]),
     'fes_plan_nnz': (_i64, [_p]),
     'fes_plan_n_pairs': (_i64, [_p]),
+    'fes_plan_n_tiles': (_i64, [_p]),
     'fes_plan_bytes': (_i64, [_p]),
     'fes_plan_read_bytes': (_i64, [_p]),
     'fes_plan_indptr': (_p, [_p]),

@@ -581,6 +581,7 @@ extern "C" void fes_plan_destroy(fes_plan* plan) { delete plan; }
 extern "C" int64_t fes_plan_n_dofs(const fes_plan* p) { return p ? p->n_dofs : 0; }
 extern "C" int64_t fes_plan_nnz(const fes_plan* p) { return p ? p->nnz : 0; }
 extern "C" int64_t fes_plan_n_pairs(const fes_plan* p) { return p ? p->n_pairs : 0; }
+extern "C" int64_t fes_plan_n_tiles(const fes_plan* p) { return (p && p->tiled) ? p->n_tiles : 0; }
 extern "C" const int32_t* fes_plan_indptr(const fes_plan* p) { return p ? p->indptr.p : nullptr; }
 extern "C" const int32_t* fes_plan_indices(const fes_plan* p) { return p ? p->indices.p : nullptr; }
 

@@ -92,6 +92,11 @@ class ScatterPlan:
         return self._host
 
     @property
+    def n_tiles(self):
+        """Tiles of the fused kernel; 0 when the mesh needs the untiled fallback kernel."""
+        return int(_lib.lib().fes_plan_n_tiles(self._h))
+
+    @property
     def bytes(self):
         return int(_lib.lib().fes_plan_bytes(self._h))
 
