@@ -40,22 +40,47 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (the timed
+    region is milliseconds long, too short for `nvidia-smi -lms`); nvidia-smi is the fallback."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
+        self.stop, self.thread, self.proc, self.rows = threading.Event(), None, None, []
+
+    def _poll(self):
+        import pynvml as nv
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        names = {getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8): 'hw_slowdown',
+                 getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+                 getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+                 getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4): 'sw_power_cap'}
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop.is_set():
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            mask = int(get_reasons(h))
+            self.reasons.update(n for bit, n in names.items() if mask & bit)
+            time.sleep(0.0005)
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
+            try:
+                self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                              '--format=csv,noheader,nounits', '-lms', '100'],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.reader = threading.Thread(target=self._read, daemon=True)
+                self.reader.start()
+            except Exception:
+                self.proc = None
         return self
 
     def _read(self):
@@ -63,18 +88,41 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(',')])
 
     def __exit__(self, *a):
+        self.stop.set()
+        if self.thread:
+            self.thread.join(timeout=2)
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
-            self.thread.join(timeout=2)
+            self.reader.join(timeout=2)
 
     def summary(self):
+        if self.thread:
+            return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.max_mhz,
+                    'reasons': sorted(self.reasons), 'samples': len(self.sm), 'source': 'nvml polling thread'}
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         reasons = sorted({n for r in self.rows if len(r) >= 6 for n, f in zip(names, r[2:6]) if f == 'Active'})
         mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(sm)}
+                'reasons': reasons, 'samples': len(sm), 'source': 'nvidia-smi -lms 100'}
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index`, so the pinned host buffers of
+    the end-to-end leg are first-touched on that GPU's NUMA node (matters when 8 ranks share the host)."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        words = nv.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
 
 
 # ---------------------------------------------------------------------------------------------
@@ -146,6 +194,7 @@ def run_gpu(args):
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
+    local_cpus = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
@@ -229,7 +278,8 @@ def run_gpu(args):
         e2e_s = float(t.item())
     e2e = {'value': total_el / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(h_coords.numel() * 8),
            'd2h_bytes_per_step': int(plan.nnz * 8), 'ms_per_step': e2e_s * 1e3,
-           'api': 'fes_assemble_host (pinned host coordinates in, pinned host CSR values out)'}
+           'api': 'fes_assemble_host (pinned host coordinates in, pinned host CSR values out)',
+           'host_cpus_bound_to_gpu_numa_node': local_cpus}
 
     out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
            'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
@@ -430,7 +480,7 @@ def extra_metrics(F, V, mesh, dev):
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-extra', action='store_true')
