@@ -76,9 +76,9 @@ inline int tile_item_len(int N) {
 inline int tile_inc_budget(int N) {
   switch (N) {
     case 2: return 256;
-    case 3: return 384;    // P1 triangle (6 doubles per element record) or P2 line
+    case 3: return 384;    // P1 triangle (6 doubles per element record) or P2 line; settles at 336 on row-numbered meshes
     case 4: return 512;    // P1 tet (12 doubles)
-    default: return 256;   // P2 triangle (36 doubles)
+    default: return 96;    // P2 triangle (36 doubles per element record): small tiles keep 5+ CTAs per SM
   }
 }
 }  // namespace fes
