@@ -198,7 +198,7 @@ __device__ __forceinline__ double sparse_product(const PcgArgs& A, int64_t tid, 
   for (int64_t slot = tid; slot < A.n_slots; slot += nth) {
     const int lane = (int)(slot & 31);
     const int64_t slice = slot >> 5;
-    const int32_t brow = __ldg(A.sell_row + slot);
+    const int32_t brow = __ldcs(A.sell_row + slot);
     const int32_t base = __ldg(A.sell_slice_ptr + slice);
     const int32_t width = (__ldg(A.sell_slice_ptr + slice + 1) - base) >> 5;
     uint8_t fr[C];
@@ -211,7 +211,7 @@ __device__ __forceinline__ double sparse_product(const PcgArgs& A, int64_t tid, 
     for (int i = 0; i < C; ++i) acc[i] = 0.0;
 #pragma unroll 4
     for (int32_t s = 0; s < width; ++s) {
-      const int32_t col = __ldg(cp + s * 32);
+      const int32_t col = __ldcs(cp + s * 32);  // the operator streams through L2 (evict-first): the vectors stay resident
       double pw[C];
       if constexpr (C == 2) {
         const double2 t = *reinterpret_cast<const double2*>(vec + 2 * (int64_t)col);
@@ -228,7 +228,7 @@ __device__ __forceinline__ double sparse_product(const PcgArgs& A, int64_t tid, 
 #pragma unroll
       for (int i = 0; i < C; ++i)
 #pragma unroll
-        for (int j = 0; j < C; ++j) acc[i] = fma(__ldg(a + (i * C + j) * 32), pw[j], acc[i]);
+        for (int j = 0; j < C; ++j) acc[i] = fma(__ldcs(a + (i * C + j) * 32), pw[j], acc[i]);
     }
     if (brow >= 0) {
 #pragma unroll
