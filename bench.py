@@ -87,6 +87,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(',')])
 
+    def sample_now(self):
+        """One sample from the calling thread (the poller can be starved while Python enqueues launches)."""
+        if self.thread:
+            try:
+                import pynvml as nv
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(nv.nvmlDeviceGetHandleByIndex(self.index), nv.NVML_CLOCK_SM)))
+            except Exception:
+                pass
+
     def __exit__(self, *a):
         self.stop.set()
         if self.thread:
@@ -196,6 +205,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     local_cpus = bind_to_gpu_numa_node(local)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')  # stdout carries the one JSON line only
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
     L = _lib.lib()
@@ -231,6 +241,7 @@ def run_gpu(args):
         for _ in range(args.steps):
             step()
         ev1.record()
+        clocks.sample_now()      # the queue is still draining: a sample under load even for a short region
         barrier()
     ms = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - launches0
