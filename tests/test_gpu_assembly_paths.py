@@ -159,3 +159,27 @@ def test_negative_and_zero_factors():
     close(B, fo.assemble(mesh.elements, 2, len(mesh.vertices), fo.ke_elastic(geo, Ez, 0.25)).data)
     K0 = form.element_matrices(V)
     close(V.assemble(F.PrecomputedForm(K0, scale=Ez / 50.0)).data, B)
+
+
+@pytest.mark.parametrize('kind', ['tri', 'tet', 'p2tri'])
+def test_two_hundred_reassemblies_are_bit_identical(kind):
+    """Race hunting without a sanitizer: the persistent kernel recycles its shared-memory rings, the
+    value image and the coordinate buffer across tiles; any missing barrier or early TMA reuse shows up
+    as run-to-run differences.  Mid-size meshes so every CTA walks many tiles."""
+    F = fes()
+    if kind == 'tri':
+        V = F.FunctionSpace(F.create_rect_mesh([[0, 0], [3, 1]], (901, 301)), n_components=2)
+    elif kind == 'tet':
+        V = F.FunctionSpace(F.create_box_mesh([[0, 0, 0], [1, 1, 1]], (41, 41, 41)), n_components=3)
+    else:
+        V = F.FunctionSpace(F.create_rect_mesh([[0, 0], [1, 1]], (301, 301)), F.QuadraticTriangleElement, n_components=2)
+    n_el = V._n_elements()
+    E = torch.as_tensor(np.random.default_rng(0).uniform(1.0, 9.0, n_el), device=V.device)
+    form = F.LinearElasticForm(F.LinearElasticMaterial(E, 0.3))
+    ref = V.assemble_device(form).data_d.clone()
+    out = torch.empty_like(ref)
+    for rep in range(200):
+        out.fill_(float('nan'))
+        V.assemble_device(form, out=out)
+        assert torch.equal(out, ref), f'reassembly {rep} differs'
+    assert bool(torch.isfinite(ref).all())
