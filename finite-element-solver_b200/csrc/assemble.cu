@@ -450,14 +450,23 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
         for (int q = 0; q < NQ; ++q) {
           double2 ta[CH], tb[CH];
           [[maybe_unused]] double za[CH], zb[CH];
+          // a warp of diagonal pairs (a == b in every lane; items are sorted, so such warps are whole):
+          // one gradient per contribution instead of two
+          bool same = true;
+#pragma unroll
+          for (int x = 0; x < CH; ++x) same = same && ((code[x] ^ (code[x] >> 16)) & 0xffffu) == 0u;
+          same = __all_sync(0xffffffffu, same);
 #pragma unroll
           for (int x = 0; x < CH; ++x) {
             const uint32_t oa = code[x] & 0xffffu, ob = code[x] >> 16;
             ta[x] = lds_f64x2(v2_b + oa + (uint32_t)(q * N * 16) * (uint32_t)GS);
-            tb[x] = lds_f64x2(v2_b + ob + (uint32_t)(q * N * 16) * (uint32_t)GS);  // same address when a == b: a broadcast
-            if constexpr (SD & 1) {
-              za[x] = lds_f64(v1_b + (oa >> 1) + (uint32_t)(q * N * 8) * (uint32_t)GS);
-              zb[x] = lds_f64(v1_b + (ob >> 1) + (uint32_t)(q * N * 8) * (uint32_t)GS);
+            if constexpr (SD & 1) za[x] = lds_f64(v1_b + (oa >> 1) + (uint32_t)(q * N * 8) * (uint32_t)GS);
+            if (!same) {
+              tb[x] = lds_f64x2(v2_b + ob + (uint32_t)(q * N * 16) * (uint32_t)GS);
+              if constexpr (SD & 1) zb[x] = lds_f64(v1_b + (ob >> 1) + (uint32_t)(q * N * 8) * (uint32_t)GS);
+            } else {
+              tb[x] = ta[x];
+              if constexpr (SD & 1) zb[x] = za[x];
             }
           }
 #pragma unroll
