@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from .boundary import BoundaryConditions
-from .forms import LaplacianForm, LinearElasticForm, MaskedMassForm
+from .forms import LaplacianForm, LinearElasticForm, MaskedMassForm, MassForm, ScaledForm
 from .regions import evaluate_field
 from .space import FunctionSpace
 
@@ -76,3 +76,19 @@ def poisson(mesh, source=None, bc=None):
 def linear_elastic(mesh, material, bc=None, source=None):
     space = FunctionSpace(mesh, n_components=mesh.spatial_dim)
     return LinearProblem(space, LinearElasticForm(material), source, bc)
+
+
+def projection(mesh, source, bc=None):
+    """L2 projection of `source` onto the P1 space, M u = M f (ref fem/problem.py:236-239)."""
+    space = FunctionSpace(mesh, n_components=1)
+    return LinearProblem(space, MassForm(space.n_components), source, bc)
+
+
+def heat(mesh, source=None, bc=None):
+    """Transient heat: Poisson's operator, to be stepped by a ThetaMethod (ref fem/problem.py:274-282)."""
+    return LinearProblem(FunctionSpace(mesh, n_components=1), LaplacianForm(), source, bc)
+
+
+def wave(mesh, c, bc=None, source=None):
+    """Transient wave with speed c: the Laplacian scaled by c^2, to be Newmark-stepped (ref fem/problem.py:285-294)."""
+    return LinearProblem(FunctionSpace(mesh, n_components=1), ScaledForm(c ** 2, LaplacianForm()), source, bc)

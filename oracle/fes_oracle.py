@@ -547,3 +547,49 @@ def simp_iteration(elem_nodes, geo, K0, rho, penalty, E0, nu, free, fixed, load,
     sens = penalty * rho ** (penalty - 1) * q * chain(comp.sum())
     rho_next = oc_update(rho, filt @ sens, geo.volumes, volume_frac, move=move)
     return u, comp, sens, rho_next
+
+
+# ---------------------------------------------------------------------------------------------
+# time integrators (ref fem/integrators.py:33-120)
+# ---------------------------------------------------------------------------------------------
+def theta_method(M, K, b, free, fixed, fixed_values, u0, dt, steps, theta, solve):
+    """(M + theta dt K) u_{n+1} = (M - (1 - theta) dt K) u_n + dt b with the Dirichlet dofs eliminated
+    (ref fem/integrators.py:48-64).  `solve(A_ff, rhs)` solves the free-free block.  Returns (t, [u_n])."""
+    A = (M + theta * dt * K).tocsr()
+    rhs_op = (M - (1.0 - theta) * dt * K).tocsr()
+    u = np.asarray(u0, dtype=float).copy()
+    ts, us = [0.0], [u.copy()]
+    for i in range(steps):
+        u = constrained_solve(A, free, fixed, fixed_values, rhs_op @ u + dt * b, solve)
+        ts.append(dt * (i + 1))
+        us.append(u.copy())
+    return np.asarray(ts), us
+
+
+def newmark_method(M, K, b, free, fixed, fixed_values, u0, v0, dt, steps, beta, gamma, solve):
+    """Average-acceleration Newmark for M u'' + K u = b (ref fem/integrators.py:86-120): accelerations are
+    solved against M (initial) and M + beta dt^2 K with the fixed dofs pinned to zero.  Returns (t, [u], [v])."""
+    u, v = np.asarray(u0, dtype=float).copy(), np.asarray(v0, dtype=float).copy()
+    if not np.allclose(u[fixed], fixed_values):
+        raise ValueError('u0 disagrees with the Dirichlet values at fixed nodes')
+    if not np.allclose(v[fixed], 0):
+        raise ValueError('v0 must be zero at Dirichlet-fixed nodes')
+    zeros = np.zeros(len(fixed))
+    a = constrained_solve(M.tocsr(), free, fixed, zeros, b - K @ u, solve)
+    Aeff = (M + beta * dt ** 2 * K).tocsr()
+    ts, us, vs = [0.0], [u.copy()], [v.copy()]
+    for i in range(steps):
+        u_pred = u + dt * v + dt ** 2 / 2 * (1 - 2 * beta) * a
+        v_pred = v + dt * (1 - gamma) * a
+        a = constrained_solve(Aeff, free, fixed, zeros, b - K @ u_pred, solve)
+        u = u_pred + beta * dt ** 2 * a
+        v = v_pred + gamma * dt * a
+        ts.append(dt * (i + 1))
+        us.append(u.copy())
+        vs.append(v.copy())
+    return np.asarray(ts), us, vs
+
+
+def wave_energy(M, K, u, v):
+    """(u^T K u + v^T M v) / 2 (ref fem/integrators.py:123-133)."""
+    return float(0.5 * (u @ (K @ u) + v @ (M @ v)))

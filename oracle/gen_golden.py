@@ -4,8 +4,8 @@
 
 Imports janetyq/Finite-Element-Solver from /root/reference through `oracle/ref_shim.py`
 and records its outputs on small deterministic inputs: assembled CSR operators, element
-matrices, constrained solves, the cone filter, the OC update and a 5-iteration SIMP
-trajectory.  The fixtures are committed; this script is how they were made.  Inputs are
+matrices, constrained solves, the cone filter, the OC update, a 5-iteration SIMP
+trajectory and two time-integrator histories (theta method, Newmark).  The fixtures are committed; this script is how they were made.  Inputs are
 stored with the outputs so the tests never need the reference tree.
 """
 import os
@@ -27,7 +27,8 @@ from fem.forms import (LaplacianForm, LinearElasticForm, MaskedMassForm, MassFor
                        PrecomputedForm, ScaledForm)
 from fem.materials import LinearElasticMaterial  # noqa: E402
 from fem.mesh.structured import create_box_mesh, create_rect_mesh  # noqa: E402
-from fem.problem import LinearProblem, linear_elastic  # noqa: E402
+from fem.integrators import NewmarkMethod, ThetaMethod, wave_energy  # noqa: E402
+from fem.problem import LinearProblem, heat, linear_elastic, wave  # noqa: E402
 from fem.regions import everywhere, in_box, intersect, on_plane  # noqa: E402
 from fem.solve import LinearSolve  # noqa: E402
 from fem.solver import Solver  # noqa: E402
@@ -179,9 +180,48 @@ def simp_case():
     print('filter/oc written')
 
 
+def transient_cases():
+    """ThetaMethod on a heat problem (source + nonzero Dirichlet data + Neumann flux) and NewmarkMethod on
+    a wave problem, both with the reference's DirectBackend (ref fem/integrators.py)."""
+    out = {}
+    mesh = create_rect_mesh([[0, 0], [2, 1]], (17, 13))
+    bc = BoundaryConditions()
+    bc.add(BCType.DIRICHLET, on_plane(0, 0.0), [1.5])
+    bc.add(BCType.NEUMANN, on_plane(0, 2.0), [-0.75])
+    prob = heat(mesh, source=lambda p: np.array([np.sin(3 * p[0]) + p[1]]), bc=bc)
+    u0 = 1.5 * np.ones(prob.space.n_dofs)
+    for tag, theta in (('cn', 0.5), ('be', 1.0)):
+        sol = ThetaMethod(dt=0.02, steps=6, theta=theta).run(prob, u0)
+        out[f'heat_{tag}_t'] = np.asarray(sol.t)
+        out[f'heat_{tag}_u'] = np.asarray(sol.u_history if hasattr(sol, 'u_history') else sol.u)
+    free, fixed, vals = prob.constraints
+    out.update(heat_vertices=mesh.vertices, heat_elements=mesh.elements, heat_boundary=mesh.boundary, heat_u0=u0,
+               heat_free=free, heat_fixed=fixed, heat_vals=vals, heat_load=prob.load)
+    out.update(csr_fields('heat_K', prob.tangent(None)))
+    out.update(csr_fields('heat_M', prob.space.mass_matrix))
+
+    bcw = BoundaryConditions()
+    bcw.add(BCType.DIRICHLET, on_plane(0, 0.0), [0.0])
+    bcw.add(BCType.DIRICHLET, on_plane(0, 2.0), [0.0])
+    probw = wave(mesh, 1.7, bcw)
+    x, y = mesh.vertices[:, 0], mesh.vertices[:, 1]
+    w0 = np.sin(np.pi * x / 2.0) * (1 + 0.3 * np.cos(np.pi * y))
+    v0 = 0.2 * np.sin(np.pi * x)
+    sol = NewmarkMethod(dt=0.01, steps=6).run(probw, w0, v0)
+    hist_u = np.asarray(sol.u_history if hasattr(sol, 'u_history') else sol.u)
+    hist_v = np.asarray(sol.dudt_history if hasattr(sol, 'dudt_history') else sol.dudt)
+    freew, fixedw, valsw = probw.constraints
+    out.update(wave_t=np.asarray(sol.t), wave_u=hist_u, wave_v=hist_v, wave_u0=w0, wave_v0=v0, wave_free=freew,
+               wave_fixed=fixedw, wave_vals=valsw, wave_load=probw.load,
+               wave_energy=np.array([wave_energy(probw, hist_u[i], hist_v[i]) for i in range(len(hist_u))]))
+    out.update(csr_fields('wave_K', probw.tangent(None)))
+    np.savez_compressed(os.path.join(OUT, 'transient.npz'), **out)
+
+
 if __name__ == '__main__':
     assembly_case('tri', create_rect_mesh([[0, 0], [2, 1]], (6, 5)))
     assembly_case('tet', create_box_mesh([[0, 0, 0], [1, 2, 1.5]], (3, 4, 3)))
     assembly_case('p2tri', create_rect_mesh([[0, 0], [1.5, 1]], (5, 4)), QuadraticTriangleElement)
     solve_cases()
     simp_case()
+    transient_cases()
