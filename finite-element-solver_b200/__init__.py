@@ -8,7 +8,7 @@ from . import _lib  # noqa: F401
 from .backends import B200Backend, JacobiPCGBackend  # noqa: F401
 from .boundary import BCType, BoundaryConditions  # noqa: F401
 from .csr import DeviceCSR  # noqa: F401
-from .design import optimality_criteria_update  # noqa: F401
+from .design import DesignHistory, DesignOptimizer, SIMPModel, optimality_criteria_update  # noqa: F401
 from .elements import (LinearLineElement, LinearTetrahedralElement, LinearTriangleElement,  # noqa: F401
                        QuadraticLineElement, QuadraticTriangleElement)
 from .equations import LinearElastic, Poisson  # noqa: F401
@@ -18,6 +18,7 @@ from .materials import LinearElasticMaterial  # noqa: F401
 from .mesh import Mesh, create_box_mesh, create_rect_mesh  # noqa: F401
 from .integrators import NewmarkMethod, ThetaMethod, TransientSolution, WaveSolution, wave_energy  # noqa: F401
 from .problem import LinearProblem, heat, linear_elastic, poisson, projection, wave  # noqa: F401
+from .sensitivity import Compliance, DensityField, ModulusField, PointValue, SensitivityAnalysis  # noqa: F401
 from .space import FunctionSpace  # noqa: F401
 from .system import DiscreteSystem  # noqa: F401
 from .topology import TopologyOptimizer, calculate_smoothing_matrix  # noqa: F401

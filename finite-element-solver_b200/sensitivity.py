@@ -1,0 +1,152 @@
+"""Adjoint sensitivity on the device (ref fem/sensitivity.py): the same three parts -- a
+`QuantityOfInterest` (adjoint load), a `Parameterization` (dK/dp turned into a gradient) and
+`SensitivityAnalysis` (forward + adjoint solves on one prepared `DiscreteSystem`).
+
+The element bilinear form lam_e^T K0_e u_e (ref fem/sensitivity.py:305-309) is never formed from
+(n_el, k, k) matrices: the strain-energy kernel `fes_elastic_energy` gives Q(w) = w_e^T K0_e w_e
+per element, and K0_e being symmetric, lam^T K0 u = (Q(u + lam) - Q(u - lam)) / 4; the self-adjoint
+case (lam = u) is one call.  Vectors may be numpy arrays or device tensors; results come back in kind.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .system import DiscreteSystem
+
+
+def _dev(x, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(device)
+
+
+def _like(result, *inputs):
+    """Device tensor if any input was one, numpy otherwise."""
+    return result if any(isinstance(i, torch.Tensor) for i in inputs) else result.cpu().numpy()
+
+
+# -- quantities of interest --------------------------------------------------------------------
+@dataclass(frozen=True)
+class Compliance:
+    """J = f^T u; self-adjoint under homogeneous supports (ref fem/sensitivity.py:72-87)."""
+    self_adjoint: bool = True
+
+    def value(self, problem, u):
+        return float(torch.dot(problem.load_d, _dev(u, problem.load_d.device)))
+
+    def dJ_du(self, problem, u):
+        return problem.load_d
+
+
+@dataclass(frozen=True)
+class PointValue:
+    """J = u[dof]: the unit-load method (ref fem/sensitivity.py:90-107)."""
+    dof: int
+    self_adjoint: bool = False
+
+    def value(self, problem, u):
+        return float(u[self.dof])
+
+    def dJ_du(self, problem, u):
+        e = torch.zeros(problem.space.n_dofs, dtype=torch.float64, device=problem.space.device)
+        e[self.dof] = 1.0
+        return e
+
+
+# -- parameterizations -------------------------------------------------------------------------
+class _ElementModulusParameterization:
+    """Per-element scaling of a solid stiffness K0_e at modulus `_E0` (ref fem/sensitivity.py:288-309)."""
+
+    def _energy(self, w):
+        sp = self.space
+        n_el = len(sp.element_nodes)
+        q = torch.empty(n_el, dtype=torch.float64, device=sp.device)
+        _lib.check(_lib.lib().fes_elastic_energy(sp.element_type.KIND, _lib.ptr(sp._en_d), n_el, _lib.ptr(sp._coords_d),
+                                                 _lib.ptr(w), float(self._E0), float(self.nu), None, _lib.ptr(q), None,
+                                                 None, _lib.stream()))
+        return q
+
+    def _element_quadratic(self, u, lam):
+        """lam_e^T K0_e u_e, one scalar per element (device tensor)."""
+        dev = self.space.device
+        ud = _dev(u, dev)
+        if lam is u:
+            return self._energy(ud)
+        ld = _dev(lam, dev)
+        return (self._energy(ud + ld) - self._energy(ud - ld)) * 0.25
+
+
+class DensityField(_ElementModulusParameterization):
+    """SIMP density E(rho) = rho^p E0: gradient -p rho^(p-1) lam_e^T K0_e u_e (ref fem/sensitivity.py:312-348)."""
+
+    def __init__(self, space, nu, base_E, rho, penalty=3.0):
+        self.space, self.nu, self._E0, self.penalty = space, float(nu), float(base_E), float(penalty)
+        self.rho = _dev(rho, space.device)
+        if self.rho.numel() != len(space.element_nodes):
+            raise ValueError(f'rho has {self.rho.numel()} entries but the mesh has {len(space.element_nodes)} elements')
+
+    @classmethod
+    def create(cls, space, rho, base_E, nu, penalty=3.0):
+        return cls(space, nu, base_E, rho, penalty)
+
+    def with_density(self, rho):
+        return DensityField(self.space, self.nu, self._E0, rho, self.penalty)
+
+    @property
+    def size(self):
+        return int(self.rho.numel())
+
+    def gradient(self, problem, u, lam):
+        quad = self._element_quadratic(u, lam)
+        return _like(-self.penalty * self.rho ** (self.penalty - 1.0) * quad, u, lam)
+
+
+class ModulusField(_ElementModulusParameterization):
+    """A per-element Young's modulus differentiated directly: gradient -lam_e^T K0_e u_e at unit modulus
+    (ref fem/sensitivity.py:351-375)."""
+
+    def __init__(self, space, nu, E):
+        self.space, self.nu, self._E0 = space, float(nu), 1.0
+        self.E = _dev(E, space.device)
+
+    @classmethod
+    def create(cls, space, E, nu):
+        return cls(space, nu, E)
+
+    def with_modulus(self, E):
+        return ModulusField(self.space, self.nu, E)
+
+    @property
+    def size(self):
+        return int(self.E.numel())
+
+    def gradient(self, problem, u, lam):
+        return _like(-self._element_quadratic(u, lam), u, lam)
+
+
+# -- the driver --------------------------------------------------------------------------------
+class SensitivityAnalysis:
+    """Forward solve, adjoint solve and gradient on one prepared system (ref fem/sensitivity.py:380-416)."""
+
+    def __init__(self, problem, backend=None):
+        self.problem = problem
+        _, _, fixed_values = problem.constraints
+        self._homogeneous_supports = bool(np.allclose(fixed_values, 0.0))
+        self._system = DiscreteSystem(problem.tangent(None), problem.constraints, backend)
+
+    def solve_forward(self, device=False, x0=None):
+        """u of K u = f (numpy like the reference; `device=True` keeps it in HBM)."""
+        u = self._system.solve(self.problem.load_d, x0=x0)
+        return u if device else u.cpu().numpy()
+
+    def adjoint(self, qoi, u):
+        if qoi.self_adjoint and self._homogeneous_supports:
+            return u
+        lam = self._system.solve_homogeneous(_dev(qoi.dJ_du(self.problem, u), self.problem.space.device))
+        return _like(lam, u)
+
+    def gradient(self, qoi, parameterization, u):
+        lam = self.adjoint(qoi, u)
+        return parameterization.gradient(self.problem, u, lam)

@@ -593,3 +593,33 @@ def newmark_method(M, K, b, free, fixed, fixed_values, u0, v0, dt, steps, beta, 
 def wave_energy(M, K, u, v):
     """(u^T K u + v^T M v) / 2 (ref fem/integrators.py:123-133)."""
     return float(0.5 * (u @ (K @ u) + v @ (M @ v)))
+
+
+# ---------------------------------------------------------------------------------------------
+# adjoint sensitivity and the design loop (ref fem/sensitivity.py:288-416, fem/design.py:135-192)
+# ---------------------------------------------------------------------------------------------
+def adjoint_gradient(K0, elem_nodes, c, A, free, fixed, fixed_values, load, dJ_du, factor, self_adjoint, solve):
+    """dJ/dp_e = -factor_e lam_e^T K0_e u_e with K^T lam = dJ/du under homogeneous supports; lam = u when the
+    quantity is self-adjoint and the supports are homogeneous (ref fem/sensitivity.py:401-416).
+    Returns (u, lam, gradient)."""
+    u = constrained_solve(A, free, fixed, fixed_values, load, solve)
+    if self_adjoint and np.allclose(fixed_values, 0.0):
+        lam = u
+    else:
+        lam = constrained_solve(A, free, fixed, np.zeros(len(fixed)), dJ_du, solve)
+    return u, lam, -factor * element_quadratic(K0, u, elem_nodes, c, lam)
+
+
+def design_step(elem_nodes, c, n_nodes_total, K0, rho, penalty, free, fixed, fixed_values, load, dJ_du_of, self_adjoint,
+                filt, volumes, volume_frac, move, solve):
+    """One DesignOptimizer.step (ref fem/design.py:160-178): assemble rho^p K0, solve, adjoint gradient of the
+    density parameterization, optional filter, OC update.  Returns (u, gradient, rho_next)."""
+    A = assemble(elem_nodes, c, n_nodes_total, (rho ** penalty)[:, None, None] * K0)
+    u = constrained_solve(A, free, fixed, fixed_values, load, solve)
+    lam = u if (self_adjoint and np.allclose(fixed_values, 0.0)) else \
+        constrained_solve(A, free, fixed, np.zeros(len(fixed)), dJ_du_of(u), solve)
+    grad = -penalty * rho ** (penalty - 1.0) * element_quadratic(K0, u, elem_nodes, c, lam)
+    sens = -grad
+    if filt is not None:
+        sens = filt @ sens
+    return u, grad, oc_update(rho, sens, volumes, volume_frac, move=move)

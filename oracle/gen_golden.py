@@ -5,7 +5,8 @@
 Imports janetyq/Finite-Element-Solver from /root/reference through `oracle/ref_shim.py`
 and records its outputs on small deterministic inputs: assembled CSR operators, element
 matrices, constrained solves, the cone filter, the OC update, a 5-iteration SIMP
-trajectory and two time-integrator histories (theta method, Newmark).  The fixtures are committed; this script is how they were made.  Inputs are
+trajectory, two time-integrator histories (theta method, Newmark), adjoint gradients and a
+DesignOptimizer trajectory.  The fixtures are committed; this script is how they were made.  Inputs are
 stored with the outputs so the tests never need the reference tree.
 """
 import os
@@ -20,7 +21,8 @@ import ref_shim  # noqa: E402
 ref_shim.install()
 
 from fem.boundary import BCType, BoundaryConditions  # noqa: E402
-from fem.design import optimality_criteria_update  # noqa: E402
+from fem.design import DesignOptimizer, SIMPModel, optimality_criteria_update  # noqa: E402
+from fem.sensitivity import Compliance, DensityField, ModulusField, PointValue, SensitivityAnalysis  # noqa: E402
 from fem.elements import QuadraticTriangleElement  # noqa: E402
 from fem.equations import LinearElastic, Poisson  # noqa: E402
 from fem.forms import (LaplacianForm, LinearElasticForm, MaskedMassForm, MassForm,  # noqa: E402
@@ -218,6 +220,44 @@ def transient_cases():
     np.savez_compressed(os.path.join(OUT, 'transient.npz'), **out)
 
 
+def adjoint_cases():
+    """SensitivityAnalysis gradients (Compliance / PointValue x DensityField / ModulusField) and a
+    DesignOptimizer trajectory on a small cantilever (ref fem/sensitivity.py, fem/design.py)."""
+    out = {}
+    mesh = create_rect_mesh([[0, 0], [1, 1]], (9, 9))
+    bc = BoundaryConditions()
+    bc.add(BCType.DIRICHLET, on_plane(0, 0.0), [0.0, 0.0])
+    bc.add(BCType.NEUMANN, on_plane(0, 1.0), [0.0, -1.0])
+    space = FunctionSpace(mesh, n_components=2)
+    n_el = len(mesh.elements)
+    rho = 0.3 + 0.6 * (np.arange(n_el) % 7) / 6.0
+    E_el = 0.5 + (np.arange(n_el) % 5) / 4.0
+    nu, penalty = 0.3, 3.0
+    model = SIMPModel(space, base_E=1.0, nu=nu, bc=bc, penalty=penalty)
+    prob = model.problem(rho)
+    an = SensitivityAnalysis(prob)
+    u = an.solve_forward()
+    tip = int(2 * np.argmax(mesh.vertices[:, 0] + mesh.vertices[:, 1]) + 1)
+    out.update(vertices=mesh.vertices, elements=mesh.elements, boundary=mesh.boundary, rho=rho, E_el=E_el, tip_dof=tip,
+               u_rho=u, load=prob.load, free=prob.constraints[0], fixed=prob.constraints[1], vals=prob.constraints[2],
+               grad_compliance_density=an.gradient(Compliance(), model.parameterization(rho), u),
+               grad_point_density=an.gradient(PointValue(tip), model.parameterization(rho), u),
+               lam_point=an.adjoint(PointValue(tip), u),
+               compliance_value=Compliance().value(prob, u), point_value=PointValue(tip).value(prob, u))
+    probE = LinearProblem(space, LinearElasticForm(LinearElasticMaterial(E_el, nu)), None, bc)
+    anE = SensitivityAnalysis(probE)
+    uE = anE.solve_forward()
+    out.update(u_E=uE, grad_point_modulus=anE.gradient(PointValue(tip), ModulusField.create(space, E_el, nu), uE),
+               grad_compliance_modulus=anE.gradient(Compliance(), ModulusField.create(space, E_el, nu), uE))
+    filt = calculate_smoothing_matrix(mesh, 0.2)
+    modelf = SIMPModel(space, base_E=1.0, nu=nu, bc=bc, penalty=penalty, sensitivity_filter=filt)
+    design = DesignOptimizer(modelf, Compliance(), volume_frac=0.5, iters=5, move=0.1)
+    hist = design.solve()
+    out.update(design_rho=np.asarray(hist.rho), design_u=np.asarray(hist.u), design_objective=np.asarray(hist.objective),
+               design_rho_final=design.rho, filter_radius=0.2)
+    np.savez_compressed(os.path.join(OUT, 'adjoint.npz'), **out)
+
+
 if __name__ == '__main__':
     assembly_case('tri', create_rect_mesh([[0, 0], [2, 1]], (6, 5)))
     assembly_case('tet', create_box_mesh([[0, 0, 0], [1, 2, 1.5]], (3, 4, 3)))
@@ -225,3 +265,4 @@ if __name__ == '__main__':
     solve_cases()
     simp_case()
     transient_cases()
+    adjoint_cases()
