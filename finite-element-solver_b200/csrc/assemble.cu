@@ -119,8 +119,9 @@ __global__ void k_negate(double* __restrict__ v, int64_t n) {
 // Persistent CTAs; each takes tiles of consecutive nodes (= a contiguous range of CSR values).
 //   staging: one producer lane drives three rings of 1-D TMA bulk copies (cp.async.bulk, SASS
 //            UBLKCP) completing on mbarriers: tile headers (3 tiles ahead), the distinct-node list
-//            (2 ahead) and the per-element corner indices / element ids / work-item metadata /
-//            contribution codes (1 ahead).  Nothing the compute threads touch comes from a dependent
+//            (2 ahead), the per-element corner indices / element ids (1 ahead, two buffers) and the
+//            work-item words / contribution codes (one buffer, refilled right after phase 2 so the
+//            copy lands under the next tile's phase 1).  Nothing the compute threads touch comes from a dependent
 //            global load except the node coordinates, and those are fetched one tile ahead into
 //            registers so they fly under phase 2.
 //   phase 1: one thread per DISTINCT element of the tile evaluates the geometry once -- cofactors,
@@ -148,14 +149,11 @@ struct RecLayout {
 };
 
 // CTA size, measured (tools/tune_tiles.sh): 4 warps per CTA and more CTAs per SM win for the gradient
-// forms; the mass form (hardly any arithmetic) prefers 8 warps.  FES_TILE_THREADS overrides both.
+// forms; the mass form (hardly any arithmetic) prefers 8 warps.  The environment variable
+// FES_TILE_THREADS (128 / 256) overrides both at run time.
 template <int FORM>
 constexpr int tile_threads() {
-#ifdef FES_TILE_THREADS
-  return FES_TILE_THREADS;
-#else
   return FORM == FES_FORM_MASS ? 256 : 128;
-#endif
 }
 constexpr int kRecBatch = 2;  // records a thread evaluates per pass of phase 1 (memory-level parallelism)
 constexpr int kHdrRing = 4, kNodRing = 3;
@@ -164,30 +162,29 @@ constexpr int kHdrBytes = fes_plan::kHdrInts * 4;
 
 __host__ __device__ constexpr size_t up16(size_t b) { return (b + 15) & ~(size_t)15; }
 
-// shared-memory carve-up: geometry records, node coordinates, the value image (one copy each), two
-// copies of the per-tile streams, the node-list ring and the header ring
+// shared-memory carve-up: geometry records, node coordinates, the value image, the work-item streams
+// (one copy each), two copies of the per-element streams, the node-list ring and the header ring
 template <int ELEM, int FORM, int C, int SD>
 struct TileSmem {
   using R = RecLayout<ELEM, FORM, C, SD>;
   __host__ __device__ static size_t rec_bytes(int gs) { return up16((size_t)gs * R::DOUBLES * 8); }
-  __host__ __device__ static size_t xyz_bytes() { return (size_t)256 * SD * 8; }   // distinct-node coordinates
+  __host__ __device__ static size_t xyz_bytes(int nmax) { return up16((size_t)nmax * SD * 8); }   // distinct-node coordinates
   __host__ __device__ static size_t out_bytes(int pmax) { return up16(((size_t)pmax * C * C + 2) * 8); }
   static constexpr int L = item_len_of(ET<ELEM>::N);
   __host__ __device__ static size_t meta_bytes(int imax) { return up16((size_t)imax * 4 + 16); }
   __host__ __device__ static size_t code_bytes(int imax) { return up16((size_t)imax * L * 4 + 32); }
   __host__ __device__ static size_t loc_bytes(int rmax) { return up16((size_t)rmax * 4 + 32); }
-  __host__ __device__ static size_t stage_bytes(int rmax, int imax, int cmax) {
-    return meta_bytes(imax) + code_bytes(imax) + 2 * loc_bytes(rmax);
-  }
-  __host__ __device__ static size_t nod_bytes() { return (size_t)256 * 4; }        // distinct-node ids
-  __host__ __device__ static size_t total(int gs, int rmax, int pmax, int imax, int cmax) {
-    return rec_bytes(gs) + xyz_bytes() + out_bytes(pmax) + 2 * stage_bytes(rmax, imax, cmax) + kNodRing * nod_bytes() +
+  __host__ __device__ static size_t stage_bytes(int rmax) { return 2 * loc_bytes(rmax); }   // phase-1 streams (x2)
+  __host__ __device__ static size_t item_bytes(int imax) { return meta_bytes(imax) + code_bytes(imax); }  // phase-2 streams (x1)
+  __host__ __device__ static size_t nod_bytes(int nmax) { return up16((size_t)nmax * 4); }       // distinct-node ids
+  __host__ __device__ static size_t total(int gs, int rmax, int pmax, int imax, int nmax) {
+    return rec_bytes(gs) + xyz_bytes(nmax) + out_bytes(pmax) + 2 * stage_bytes(rmax) + item_bytes(imax) + kNodRing * nod_bytes(nmax) +
            kHdrRing * up16(kHdrBytes);
   }
 };
 
 struct TileDims {
-  int geo_stride, rec_max, pair_max, item_max, con_max;
+  int geo_stride, rec_max, pair_max, item_max, nod_max;  // nod_max: distinct nodes per tile, upper bound
 };
 
 template <int ELEM, int FORM, int C, int SD, int kTileThreads>
@@ -201,20 +198,22 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
   using TS = TileSmem<ELEM, FORM, C, SD>;
   constexpr int N = ET<ELEM>::N, NQ = ET<ELEM>::NQ, RD = ET<ELEM>::RD;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bar_h[kHdrRing], bar_n[kNodRing], bar_s[2];
-  __shared__ uint32_t s_skew[2][4];
+  __shared__ __align__(8) uint64_t bar_h[kHdrRing], bar_n[kNodRing], bar_s[2], bar_c;
+  __shared__ uint32_t s_skew[2], s_skew_c[2];
   const int GS = dims.geo_stride;
   [[maybe_unused]] const uint32_t inv_gs = (uint32_t)(((1u << 24) + (uint32_t)GS - 1u) / (uint32_t)GS);  // a = (i * inv_gs) >> 24 for i = a * GS + slot
   // planes: v2[plane * GS + slot] (double2), then v1[plane * GS + slot] (double)
   double2* v2 = reinterpret_cast<double2*>(smem_raw);
   double* v1 = reinterpret_cast<double*>(smem_raw) + (size_t)2 * R::NV2 * GS;
   unsigned char* sp = smem_raw + TS::rec_bytes(GS);
-  double* s_xyz = reinterpret_cast<double*>(sp);                      sp += TS::xyz_bytes();
+  double* s_xyz = reinterpret_cast<double*>(sp);                      sp += TS::xyz_bytes(dims.nod_max);
   double* s_out = reinterpret_cast<double*>(sp);                      sp += TS::out_bytes(dims.pair_max);
   unsigned char* stage0 = sp;
-  const size_t stage_sz = TS::stage_bytes(dims.rec_max, dims.item_max, dims.con_max);
+  const size_t stage_sz = TS::stage_bytes(dims.rec_max);
   sp += 2 * stage_sz;
-  unsigned char* nod0 = sp;                                           sp += kNodRing * TS::nod_bytes();
+  unsigned char* s_meta = sp;                                         sp += TS::meta_bytes(dims.item_max);
+  unsigned char* s_code = sp;                                         sp += TS::code_bytes(dims.item_max);
+  unsigned char* nod0 = sp;                                           sp += kNodRing * TS::nod_bytes(dims.nod_max);
   unsigned char* hdr0 = sp;
   const bool per_elem = cf.d_E != nullptr || cf.d_scale != nullptr;
   double sq_uniform = 0.0;  // sqrt(w mu ref_measure / NQ) when no per-element coefficient varies it
@@ -235,7 +234,7 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
   if (n_my <= 0) return;
   auto tile_of = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
   auto hdr_of = [&](int k) { return reinterpret_cast<const int4*>(hdr0 + (k & (kHdrRing - 1)) * up16(kHdrBytes)); };
-  auto nod_of = [&](int k) { return reinterpret_cast<const int32_t*>(nod0 + (k % kNodRing) * TS::nod_bytes()); };
+  auto nod_of = [&](int k) { return reinterpret_cast<const int32_t*>(nod0 + (k % kNodRing) * TS::nod_bytes(dims.nod_max)); };
   // the producer is the first lane of the LAST warp: warp 0 gets the longest work items in phase 2
   const bool producer = threadIdx.x == kTileThreads - 32;
 
@@ -252,28 +251,33 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
     mbar_arrive_expect_tx(bar, b_nod);
     if (b_nod) bulk_g2s(const_cast<int32_t*>(nod_of(k)), tile_nodes + (int64_t)tile_of(k) * fes_plan::kTileNodeStride, b_nod, bar);
   };
-  auto issue_rest = [&](int k) {  // its header landed before issue_nod(k) returned
+  auto win = [](uint32_t i0, uint32_t count, uint32_t es) {
+    return (uint32_t)(((((uint64_t)i0 * es) & 15) + (uint64_t)count * es + 15) & ~(uint64_t)15);
+  };
+  auto issue_loc = [&](int k) {  // phase-1 streams of tile k (double-buffered); its header landed before issue_nod(k) returned
     const int buf = k & 1;
-    const int4 h0 = hdr_of(k)[0], h2 = hdr_of(k)[2];
-    unsigned char* st = stage0 + buf * stage_sz;
-    unsigned char* s_code = st + TS::meta_bytes(dims.item_max);
-    unsigned char* s_loc = s_code + TS::code_bytes(dims.item_max);
+    const int4 h0 = hdr_of(k)[0];
+    unsigned char* s_loc = stage0 + buf * stage_sz;
     unsigned char* s_el = s_loc + TS::loc_bytes(dims.rec_max);
     const uint32_t g0 = (uint32_t)h0.x, ne = (uint32_t)h0.y;
-    auto win = [](uint32_t i0, uint32_t count, uint32_t es) {
-      return (uint32_t)(((((uint64_t)i0 * es) & 15) + (uint64_t)count * es + 15) & ~(uint64_t)15);
-    };
+    const uint32_t b_loc = win(g0, ne, 4);
+    uint64_t* bar = &bar_s[buf];
+    mbar_arrive_expect_tx(bar, b_loc * (per_elem ? 2u : 1u));
+    uint32_t t;
+    s_skew[buf] = stage_window<4>(s_loc, rec_local, g0, ne, bar, t);
+    if (per_elem) stage_window<4>(s_el, tile_elems, g0, ne, bar, t);  // same skew as the corner indices
+  };
+  // phase-2 streams of tile k (item words + contribution codes): ONE buffer, refilled as soon as
+  // phase 2 of tile k-1 is over, so the copy lands under phase 1 of tile k
+  auto issue_items = [&](int k) {
+    const int4 h2 = hdr_of(k)[2];
     constexpr uint32_t L = (uint32_t)TS::L;
     const uint32_t i0 = (uint32_t)h2.x, ni = (uint32_t)h2.y;
     const uint32_t b_meta = win(i0, ni, 4), b_code = win(i0 * L, ni * L, 4);
-    const uint32_t b_loc = win(g0, ne, 4);
-    uint64_t* bar = &bar_s[buf];
-    mbar_arrive_expect_tx(bar, b_meta + b_code + b_loc * (per_elem ? 2u : 1u));
+    mbar_arrive_expect_tx(&bar_c, b_meta + b_code);
     uint32_t t;
-    s_skew[buf][1] = stage_window<4>(s_loc, rec_local, g0, ne, bar, t);
-    if (per_elem) stage_window<4>(s_el, tile_elems, g0, ne, bar, t);  // same skew as the corner indices
-    s_skew[buf][2] = stage_window<4>(st, pair_meta, i0, ni, bar, t);
-    s_skew[buf][0] = stage_window<4>(s_code, pair_codes, i0 * L, ni * L, bar, t);
+    s_skew_c[1] = stage_window<4>(s_meta, pair_meta, i0, ni, &bar_c, t);
+    s_skew_c[0] = stage_window<4>(s_code, pair_codes, i0 * L, ni * L, &bar_c, t);
   };
 
   // coordinates of a tile's distinct nodes: global -> registers (<= 255 nodes: a node or two per
@@ -316,10 +320,12 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
     for (int i = 0; i < kNodRing; ++i) mbar_init(&bar_n[i], 1);
     mbar_init(&bar_s[0], 1);
     mbar_init(&bar_s[1], 1);
+    mbar_init(&bar_c, 1);
     for (int k = 0; k < 3 && k < n_my; ++k) issue_hdr(k);
     issue_nod(0);
     if (n_my > 1) issue_nod(1);
-    issue_rest(0);
+    issue_loc(0);
+    issue_items(0);
   }
   __syncthreads();
   mbar_wait(&bar_h[0], 0);
@@ -337,19 +343,17 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
     if (producer) {
       if (k + 3 < n_my) issue_hdr(k + 3);
       if (k + 2 < n_my) issue_nod(k + 2);
-      if (has_next) issue_rest(k + 1);
+      if (has_next) issue_loc(k + 1);
     }
     const int4 h0 = hdr_of(k)[0], h2 = hdr_of(k)[2];
     const int32_t ne = h0.y, n_pairs = h0.w, n_items = h2.y;
     const int64_t val0 = (int64_t)C * C * h0.z;          // first CSR value of the tile
     const int skew_d = (int)(val0 & 1);                   // image slot i <-> values[val0 + i]; equal 16-byte phase
-    unsigned char* st = stage0 + buf * stage_sz;
-    unsigned char* s_code = st + TS::meta_bytes(dims.item_max);
-    unsigned char* s_loc = s_code + TS::code_bytes(dims.item_max);
+    unsigned char* s_loc = stage0 + buf * stage_sz;
     unsigned char* s_el = s_loc + TS::loc_bytes(dims.rec_max);
     mbar_wait(&bar_s[buf], (uint32_t)(k >> 1) & 1u);  // issued a whole tile ago
-    const uint32_t* locs = reinterpret_cast<const uint32_t*>(s_loc + s_skew[buf][1]);
-    const uint32_t* elems = reinterpret_cast<const uint32_t*>(s_el + s_skew[buf][1]);
+    const uint32_t* locs = reinterpret_cast<const uint32_t*>(s_loc + s_skew[buf]);
+    const uint32_t* elems = reinterpret_cast<const uint32_t*>(s_el + s_skew[buf]);
 
     // ---- phase 1: one geometry record per distinct element (corner coordinates from shared memory).
     // Pass b starts at thread b*T/2, so a short last pass does not land on warp 0 every time.
@@ -430,8 +434,9 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
     }
 
     // ---- phase 2: one thread per work item (explicit shared addresses, bases in registers)
-    const uint32_t code_b = smem_u32(s_code) + s_skew[buf][0];
-    const uint32_t meta_b = smem_u32(st) + s_skew[buf][2];
+    mbar_wait(&bar_c, (uint32_t)k & 1u);  // issued before phase 1 of this tile
+    const uint32_t code_b = smem_u32(s_code) + s_skew_c[0];
+    const uint32_t meta_b = smem_u32(s_meta) + s_skew_c[1];
     static_assert(TS::L % 2 == 0, "item codes are fetched two at a time");
     const uint32_t img_b = smem_u32(s_out) + 8u * (uint32_t)skew_d;
     // A chunk of CH contributions: S += g~_a (x) g~_b each.  A code holds the byte offsets of the two
@@ -564,9 +569,10 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
     // ---- store: the image is the tile's contiguous slice of `values`
     const int n_out = C * C * n_pairs;
     double* img = s_out + skew_d;
+    fence_proxy_async_smem();  // generic-proxy accesses (image writes, item reads) ordered before the async proxy's
+    __syncthreads();           // phase 2 is over: the image is complete, the item buffer is free
+    if (producer && has_next) issue_items(k + 1);
     if (use_tma_store) {
-      fence_proxy_async_smem();  // generic-proxy writes to the image -> visible to the async proxy
-      __syncthreads();
       if (producer) {
         const int head = skew_d;                           // an odd first slot is 16-byte misaligned on both sides
         const int body = (n_out - head) & ~1, tail = n_out - head - body;
@@ -575,7 +581,6 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
         if (tail) values[val0 + n_out - 1] = img[n_out - 1];
       }
     } else {
-      __syncthreads();
       for (int i = threadIdx.x; i < n_out; i += kTileThreads) values[val0 + i] = img[i];
       __syncthreads();
     }
@@ -634,6 +639,48 @@ struct Job {
   bool untiled = false;  // force the reference-order (untiled) kernel
 };
 
+template <int ELEM, int FORM, int C, int SD, int kTileThreads>
+int launch_tiles(const Job& j) {
+  const fes_plan* P = j.plan;
+  const TileDims dims{P->geo_stride, P->rec_max, P->pair_max, P->item_max, P->nod_max};
+  const size_t smem = TileSmem<ELEM, FORM, C, SD>::total(dims.geo_stride, dims.rec_max, dims.pair_max, dims.item_max,
+                                                         dims.nod_max);
+  static size_t configured = 0;  // per template instantiation: largest opt-in so far
+  static size_t occ_smem = 0;
+  static int per_sm = 0, sms = 0;
+  if (per_sm == 0 || smem != occ_smem) {
+    if (smem > configured && smem + 1024 > 48 * 1024)  // static smem counts toward the 48 KB default
+      FES_CUDA(cudaFuncSetAttribute(k_assemble_tiles<ELEM, FORM, C, SD, kTileThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+    configured = std::max(configured, smem);
+    int dev = 0;
+    FES_CUDA(cudaGetDevice(&dev));
+    FES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_tiles<ELEM, FORM, C, SD, kTileThreads>,
+                                                           kTileThreads, smem));
+    occ_smem = smem;
+    if (per_sm < 1) {
+      per_sm = 0;
+      return set_error(FES_ERR_CUDA, "assembly kernel does not fit on an SM (%zu B smem)", smem);
+    }
+    if (getenv("FES_PLAN_DEBUG"))
+      fprintf(stderr, "[fes assemble] threads=%d smem=%zu B CTAs/SM=%d\n", kTileThreads, smem, per_sm);
+  }
+  Coeffs cf = j.cf;
+  if (FORM != FES_FORM_MASS && cf.factor < 0.0) { cf.factor = -cf.factor; cf.sign = -1.0; }
+  const int64_t grid = std::min<int64_t>(P->n_tiles, (int64_t)sms * per_sm);  // persistent CTAs
+  static const bool no_tma = getenv("FES_NO_TMA_STORE") != nullptr;  // tuning knob: plain coalesced stores
+  const int use_tma = (!no_tma && (reinterpret_cast<uintptr_t>(j.out) & 15) == 0) ? 1 : 0;
+  k_assemble_tiles<ELEM, FORM, C, SD, kTileThreads><<<(unsigned)grid, kTileThreads, smem, j.stream>>>(
+      P->tile_hdr.p, (int)P->n_tiles, P->tile_elems.p, P->rec_local.p, P->tile_nodes.p, P->pair_meta.p,
+      P->pair_codes.p, j.coords, cf, dims, use_tma, j.out);
+  if (cf.sign < 0.0) {  // a negative global factor (ScaledForm): the kernel ran with |factor|
+    FES_LAUNCH_CHECK();
+    k_negate<<<grid_for(P->nnz, 256), 256, 0, j.stream>>>(j.out, P->nnz);
+  }
+  return FES_OK;
+}
+
 template <int ELEM, int FORM, int C, int SD>
 int run(const Job& j) {
   constexpr int N = ET<ELEM>::N;
@@ -645,39 +692,10 @@ int run(const Job& j) {
     const fes_plan* P = j.plan;
     if (P->n_pairs == 0) return FES_OK;
     if (P->tiled && !j.untiled) {
-      const TileDims dims{P->geo_stride, P->rec_max, P->pair_max, P->item_max, P->con_max};
-      const size_t smem = TileSmem<ELEM, FORM, C, SD>::total(dims.geo_stride, dims.rec_max, dims.pair_max, dims.item_max,
-                                                             dims.con_max);
-      constexpr int kTileThreads = tile_threads<FORM>();
-      static size_t configured = 0;  // per template instantiation: largest opt-in so far
-      static int per_sm = 0, sms = 0;
-      if (per_sm == 0 || smem > configured) {
-        if (smem + 1024 > 48 * 1024)  // static smem counts toward the 48 KB default
-          FES_CUDA(cudaFuncSetAttribute(k_assemble_tiles<ELEM, FORM, C, SD, kTileThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-        configured = std::max(configured, smem);
-        int dev = 0;
-        FES_CUDA(cudaGetDevice(&dev));
-        FES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        FES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_tiles<ELEM, FORM, C, SD, kTileThreads>,
-                                                               kTileThreads, smem));
-        if (per_sm < 1) {
-          per_sm = 0;
-          return set_error(FES_ERR_CUDA, "assembly kernel does not fit on an SM (%zu B smem)", smem);
-        }
-      }
-      Coeffs cf = j.cf;
-      if (FORM != FES_FORM_MASS && cf.factor < 0.0) { cf.factor = -cf.factor; cf.sign = -1.0; }
-      const int64_t grid = std::min<int64_t>(P->n_tiles, (int64_t)sms * per_sm);  // persistent CTAs
-      static const bool no_tma = getenv("FES_NO_TMA_STORE") != nullptr;  // tuning knob: plain coalesced stores
-      const int use_tma = (!no_tma && (reinterpret_cast<uintptr_t>(j.out) & 15) == 0) ? 1 : 0;
-      k_assemble_tiles<ELEM, FORM, C, SD, kTileThreads><<<(unsigned)grid, kTileThreads, smem, j.stream>>>(
-          P->tile_hdr.p, (int)P->n_tiles, P->tile_elems.p, P->rec_local.p, P->tile_nodes.p, P->pair_meta.p,
-          P->pair_codes.p, j.coords, cf, dims, use_tma, j.out);
-      if (cf.sign < 0.0) {  // a negative global factor (ScaledForm): the kernel ran with |factor|
-        FES_LAUNCH_CHECK();
-        k_negate<<<grid_for(P->nnz, 256), 256, 0, j.stream>>>(j.out, P->nnz);
-      }
+      static const int env_threads = getenv("FES_TILE_THREADS") ? atoi(getenv("FES_TILE_THREADS")) : 0;  // tuning knob
+      const int threads = env_threads ? env_threads : tile_threads<FORM>();
+      if (threads == 256) FES_TRY((launch_tiles<ELEM, FORM, C, SD, 256>(j)));
+      else FES_TRY((launch_tiles<ELEM, FORM, C, SD, 128>(j)));
     } else {
       k_assemble_pairs<ELEM, FORM, C, SD><<<grid_for(P->n_pairs, kBlock), kBlock, 0, j.stream>>>(
           P->n_pairs, P->pair_start.p, P->pair_row.p, P->node_ptr.p, P->contrib.p, P->indptr.p, j.en, j.coords, j.cf,

@@ -159,11 +159,15 @@ __global__ void __launch_bounds__(256)
 k_tile_build(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__ ne_ptr,
              const uint32_t* __restrict__ ne_code, const int32_t* __restrict__ en, int N, int n_corner,
              uint32_t* __restrict__ tile_elems, uint32_t* __restrict__ rec_local, int32_t* __restrict__ tile_nodes,
-             int32_t* __restrict__ tile_cnt, int* __restrict__ bad) {
+             int32_t* __restrict__ tile_cnt, int colour_groups, int* __restrict__ bad) {
   __shared__ uint32_t ids[kTileIdCap];
   __shared__ uint32_t uniq[kTileIdCap];
   __shared__ uint32_t s_el[kTileRecCap];
   __shared__ int s_cnt[257];
+  __shared__ int s_mptr[257];             // node -> its (wavefront group, corner) memberships
+  __shared__ uint16_t s_mlist[kTileIdCap];
+  __shared__ int s_used[kTileIdCap * 2];   // [group * n_corner + corner][residue]: reads already on that bank
+  __shared__ uint8_t s_li[256];
   const int t = blockIdx.x;
   const int32_t g0 = ne_ptr[tile_node0[t]], g1 = ne_ptr[tile_node0[t + 1]];
   const int n_rec = g1 - g0;  // <= inc_max <= kTileRecCap
@@ -192,20 +196,82 @@ k_tile_build(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__
     if (nd > 255) atomicExch(bad, 1);
   }
   if (nd > 255) return;
-  for (int i = threadIdx.x; i < nd; i += blockDim.x)
-    tile_nodes[(int64_t)t * fes_plan::kTileNodeStride + i] = (int32_t)uniq[i];
-  for (int r = threadIdx.x; r < ne; r += blockDim.x) {
-    const int64_t e = s_el[r];
-    uint32_t packed = 0;
-    for (int k = 0; k < n_corner; ++k) {
-      const uint32_t node = (uint32_t)en[e * N + k];
-      int lo = 0, hi = nd;
-      while (lo < hi) {
-        const int m = (lo + hi) >> 1;
-        if (uniq[m] < node) lo = m + 1; else hi = m;
-      }
-      packed |= (uint32_t)lo << (8 * k);
+  // corner ranks (index into the sorted distinct-node list) of every record
+  for (int i = threadIdx.x; i < n_ids; i += blockDim.x) {
+    const int r = i / n_corner, k = i - r * n_corner;
+    const uint32_t node = (uint32_t)en[(int64_t)s_el[r] * N + k];
+    int lo = 0, hi = nd;
+    while (lo < hi) {
+      const int m = (lo + hi) >> 1;
+      if (uniq[m] < node) lo = m + 1; else hi = m;
     }
+    ids[i] = (uint32_t)lo;
+  }
+  __syncthreads();
+  // Local index of each distinct node = its slot in the kernel's shared-memory coordinate table.
+  // Phase 1 of the assembly kernel reads corner k of G consecutive records per LSU wavefront (a
+  // quarter-warp of 16-byte (x, y) pairs, or a half-warp of 8-byte components in 3D), and the
+  // address decides the bank: slot mod G.  Sorted ranks collide (the nodes of neighbouring mesh rows
+  // sit a row length apart), so the slots come from a greedy colouring instead: nodes in ascending
+  // order, each takes the residue that adds the fewest same-bank reads to the wavefronts it is part
+  // of (ties: the emptiest residue), slot = residue + G * (nodes already holding that residue).
+  const int G = colour_groups;                 // 8 or 16 records per wavefront; 0 = keep sorted ranks
+  int n_slots = nd;
+  if (G > 0) {
+    const int n_groups = (ne + G - 1) / G;     // <= 128
+    const int cap = min((nd + G - 1) / G + 2, 256 / G);
+    for (int i = threadIdx.x; i < n_groups * n_corner * G; i += blockDim.x) s_used[i] = 0;
+    for (int i = threadIdx.x; i <= nd; i += blockDim.x) s_mptr[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_ids; i += blockDim.x) atomicAdd(&s_mptr[ids[i] + 1], 1);
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int i = 0; i < nd; ++i) s_mptr[i + 1] += s_mptr[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < nd; i += blockDim.x) s_cnt[i] = s_mptr[i];  // fill cursors (nd <= 255)
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_ids; i += blockDim.x) {
+      const int r = i / n_corner, k = i - r * n_corner;
+      const int at = atomicAdd(&s_cnt[ids[i]], 1);
+      s_mlist[at] = (uint16_t)((r / G) * n_corner + k);  // (wavefront group, corner): order within a node is irrelevant
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      int fill = 0, max_fill = 0;  // lane c < G counts the nodes holding residue c
+      for (int n = 0; n < nd; ++n) {
+        const int m0 = s_mptr[n], m1 = s_mptr[n + 1];
+        uint32_t cost = 0xffffffffu;
+        if (lane < G && fill < cap) {
+          uint32_t hits = 0;
+          for (int m = m0; m < m1; ++m) hits += s_used[(int)s_mlist[m] * G + lane];
+          cost = (hits << 16) | ((uint32_t)fill << 8) | (uint32_t)lane;
+        }
+        for (int o = 16; o > 0; o >>= 1) cost = min(cost, __shfl_xor_sync(0xffffffffu, cost, o));
+        const int best = (int)(cost & 255u);
+        const int before = __shfl_sync(0xffffffffu, fill, best);
+        if (lane == 0) s_li[n] = (uint8_t)(best + G * before);
+        if (lane == best) ++fill;
+        max_fill = max(max_fill, before + 1);
+        for (int m = m0 + lane; m < m1; m += 32) atomicAdd(&s_used[(int)s_mlist[m] * G + best], 1);  // a node can be two corners of one group
+        __syncwarp();
+      }
+      if (lane == 0) s_cnt[256] = G * max_fill;
+    }
+    __syncthreads();
+    n_slots = s_cnt[256];
+  } else {
+    for (int i = threadIdx.x; i < nd; i += blockDim.x) s_li[i] = (uint8_t)i;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tile_cnt[2 * t + 1] = n_slots;
+  int32_t* my_nodes = tile_nodes + (int64_t)t * fes_plan::kTileNodeStride;
+  for (int i = threadIdx.x; i < n_slots; i += blockDim.x) my_nodes[i] = (int32_t)uniq[0];  // unused slots: any valid node
+  __syncthreads();
+  for (int i = threadIdx.x; i < nd; i += blockDim.x) my_nodes[s_li[i]] = (int32_t)uniq[i];
+  for (int r = threadIdx.x; r < ne; r += blockDim.x) {
+    uint32_t packed = 0;
+    for (int k = 0; k < n_corner; ++k) packed |= (uint32_t)s_li[ids[r * n_corner + k]] << (8 * k);
     rec_local[g0 + r] = packed;
   }
 }
@@ -356,12 +422,18 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
   P->inc_max = inc_max;
   // a tile's value image stays under 32 KB of shared memory, its packed offsets under 16 bits
   const int pair_cap = std::min(32768 / (8 * c * c), 65535 / c);
+  // Boundary nodes carry more pairs per incident element than interior ones, so a run of them within
+  // the incidence budget would hold far more pairs than a typical tile -- and the kernel sizes its
+  // value image (shared memory, hence CTAs per SM) for the LARGEST tile.  Keep every tile within
+  // 1.25x the mesh-average pairs of a full tile (a single node always fits).
+  const int pair_soft = (int)(1.25 * (double)np_ / (double)P->n_geo * inc_max) + 8;
   std::vector<int32_t> tiles;
   tiles.push_back(0);
   int64_t v0 = 0;
   for (int64_t v = 0; v < nn; ++v) {
     if (h_ne[v + 1] - h_ne[v] > inc_max || h_np[v + 1] - h_np[v] > pair_cap) return FES_OK;  // one node overflows a tile
-    if (h_ne[v + 1] - h_ne[v0] > inc_max || h_np[v + 1] - h_np[v0] > pair_cap || v - v0 >= 255) {
+    if (h_ne[v + 1] - h_ne[v0] > inc_max || h_np[v + 1] - h_np[v0] > pair_cap || v - v0 >= 255 ||
+        (h_np[v + 1] - h_np[v0] > pair_soft && v > v0)) {
       tiles.push_back((int32_t)v);
       v0 = v;
     }
@@ -385,8 +457,12 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
   FES_CUDA(P->rec_local.alloc(P->n_geo + 16));
   FES_CUDA(P->tile_nodes.alloc((size_t)nt * fes_plan::kTileNodeStride + 64));
   FES_CUDA(P->tile_cnt.alloc(2 * nt));
+  // coordinate-table slots coloured for 8 records per wavefront (16-byte xy pairs) or 16 (tets: 8-byte components)
+  static const bool no_colour = getenv("FES_PLAN_NO_COLOUR") != nullptr;  // tuning knob: sorted ranks
+  const int colour_groups = no_colour ? 0 : (N == 4 ? 16 : 8);
   k_tile_build<<<(unsigned)nt, 256, 0, stream>>>(P->tile_node0.p, P->ne_ptr.p, P->ne_code.p, d_elem_nodes, N, P->n_corner,
-                                                 P->tile_elems.p, P->rec_local.p, P->tile_nodes.p, P->tile_cnt.p, bad.p);
+                                                 P->tile_elems.p, P->rec_local.p, P->tile_nodes.p, P->tile_cnt.p,
+                                                 colour_groups, bad.p);
   FES_LAUNCH_CHECK();
   int h_bad = 0;
   FES_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -418,25 +494,26 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
   FES_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
   FES_CUDA(cudaStreamSynchronize(stream));
   if (h_bad) return FES_OK;
-  int rmax = 0, pmax = 0, cmax = 0, imax = 0;
+  int rmax = 0, pmax = 0, cmax = 0, imax = 0, nmax = 0;
   int64_t rd = 0, items = 0;
   for (int64_t t = 0; t < nt; ++t) {
     int32_t* h = hdr.data() + t * HI;
-    rmax = std::max(rmax, h[1]); pmax = std::max(pmax, h[3]); cmax = std::max(cmax, h[5]); imax = std::max(imax, h[9]);
+    rmax = std::max(rmax, h[1]); pmax = std::max(pmax, h[3]); cmax = std::max(cmax, h[5]); imax = std::max(imax, h[9]); nmax = std::max(nmax, h[6]);
     h[8] = (int32_t)items;
     items += h[9];
     rd += 4 * HI + (int64_t)h[9] * 4 * (1 + L) + (int64_t)h[1] * 4 + (int64_t)h[6] * 4;
   }
   if (imax > 65535 || rmax > kTileRecCap || items * L >= ((int64_t)1 << 32)) return FES_OK;
   P->rec_max = rmax; P->pair_max = pmax; P->con_max = cmax; P->item_max = imax; P->n_items = items;
+  P->nod_max = (nmax + 3) & ~3;
   // plane stride 1 (mod 8): plane n sits n x 16 B further in bank space, so pairs that read different
   // nodes of the SAME record do not collide; slots are swizzled inside aligned groups of 8
   P->geo_stride = ((rmax + 7) & ~7) + 1;
   if ((int64_t)N * P->geo_stride * 16 > 65535) return FES_OK;  // 16-bit byte offsets in the codes
   P->tile_read_bytes = rd;
   if (getenv("FES_PLAN_DEBUG"))
-    fprintf(stderr, "[fes plan] N=%d c=%d nodes=%lld pairs=%lld tiles=%lld inc_max=%d rec_max=%d pair_max=%d item_max=%d con_max=%d items=%lld gs=%d\n",
-            N, c, (long long)nn, (long long)np_, (long long)nt, inc_max, rmax, pmax, imax, cmax, (long long)items, P->geo_stride);
+    fprintf(stderr, "[fes plan] N=%d c=%d nodes=%lld pairs=%lld tiles=%lld inc_max=%d rec_max=%d pair_max=%d item_max=%d con_max=%d nod_max=%d items=%lld gs=%d\n",
+            N, c, (long long)nn, (long long)np_, (long long)nt, inc_max, rmax, pmax, imax, cmax, P->nod_max, (long long)items, P->geo_stride);
   FES_CUDA(cudaMemcpyAsync(P->tile_hdr.p, hdr.data(), hdr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
   P->item_len = (int)L;
   FES_CUDA(P->pair_meta.alloc(items + 16));

@@ -26,7 +26,7 @@ struct fes_plan {
   int64_t n_tiles = 0, n_geo = 0, tile_read_bytes = 0;
   int inc_max = 0;                     // (node, incident element) records per tile: the tiling budget
   int geo_stride = 0;                  // shared-memory plane stride of the records: 1 (mod 8), > rec_max
-  int rec_max = 0, pair_max = 0, con_max = 0, item_max = 0;  // distinct elements / pairs / contributions / work items per tile, upper bounds
+  int rec_max = 0, pair_max = 0, con_max = 0, item_max = 0, nod_max = 0;  // distinct elements / pairs / contributions / work items / distinct nodes per tile, upper bounds
   int64_t n_items = 0;
   int item_len = 0;                    // contribution codes per work item (= tile_item_len(N))
   fes::DevBuf<int32_t> ne_ptr;         // n_nodes + 1 : incident-element ranges per node
@@ -77,7 +77,7 @@ inline int tile_inc_budget(int N) {
   switch (N) {
     case 2: return 256;
     case 3: return 384;    // P1 triangle (6 doubles per element record) or P2 line; settles at 336 on row-numbered meshes
-    case 4: return 512;    // P1 tet (12 doubles)
+    case 4: return 400;    // P1 tet (12 doubles per element record): 3 CTAs per SM (measured: 512 -> 2 CTAs, 7 % slower)
     default: return 96;    // P2 triangle (36 doubles per element record): small tiles keep 5+ CTAs per SM
   }
 }
