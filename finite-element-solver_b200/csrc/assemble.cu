@@ -155,7 +155,7 @@ template <int FORM>
 constexpr int tile_threads() {
   return FORM == FES_FORM_MASS ? 256 : 128;
 }
-constexpr int kRecBatch = 2;  // records a thread evaluates per pass of phase 1 (memory-level parallelism)
+template <int T> constexpr int rec_batch() { return T >= 256 ? 1 : 2; }  // records a thread evaluates per pass of phase 1 (memory-level parallelism)
 constexpr int kHdrRing = 4, kNodRing = 3;
 __host__ __device__ constexpr int item_len_of(int N) { return (N == 3) ? 2 : (N == 4) ? 6 : 2; }  // = tile_item_len(N)
 constexpr int kHdrBytes = fes_plan::kHdrInts * 4;
@@ -197,6 +197,7 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
   using R = RecLayout<ELEM, FORM, C, SD>;
   using TS = TileSmem<ELEM, FORM, C, SD>;
   constexpr int N = ET<ELEM>::N, NQ = ET<ELEM>::NQ, RD = ET<ELEM>::RD;
+  constexpr int kRecBatch = rec_batch<kTileThreads>();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_h[kHdrRing], bar_n[kNodRing], bar_s[2], bar_c;
   __shared__ uint32_t s_skew[2], s_skew_c[2];
@@ -235,8 +236,16 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
   auto tile_of = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
   auto hdr_of = [&](int k) { return reinterpret_cast<const int4*>(hdr0 + (k & (kHdrRing - 1)) * up16(kHdrBytes)); };
   auto nod_of = [&](int k) { return reinterpret_cast<const int32_t*>(nod0 + (k % kNodRing) * TS::nod_bytes(dims.nod_max)); };
-  // the producer is the first lane of the LAST warp: warp 0 gets the longest work items in phase 2
-  const bool producer = threadIdx.x == kTileThreads - 32;
+  // Producer duties are spread over the first lanes of different warps, so no warp carries the whole
+  // serial issue sequence into the barriers: the LAST warp owns the image store (and the wait for
+  // its reads; warp 0 gets the longest work items in phase 2), the others fill the rings.
+  constexpr int kWarps = kTileThreads / 32;
+  const bool lane0 = (threadIdx.x & 31) == 0;
+  const int warp_id = threadIdx.x >> 5;
+  const bool producer = threadIdx.x == kTileThreads - 32;                 // image store
+  const bool p_ring = lane0 && warp_id == (kWarps > 2 ? kWarps - 2 : 0);  // headers + node lists
+  const bool p_loc = lane0 && warp_id == (kWarps > 3 ? kWarps - 3 : 0);   // per-element streams
+  const bool p_items = lane0 && warp_id == (kWarps > 2 ? 1 : 0);          // work-item streams
 
   // ---- producer side: ring fills
   auto issue_hdr = [&](int k) {
@@ -340,10 +349,13 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
   for (int k = 0; k < n_my; ++k) {
     const int buf = k & 1;
     const bool has_next = k + 1 < n_my;
-    if (producer) {
+    if (p_ring) {
       if (k + 3 < n_my) issue_hdr(k + 3);
       if (k + 2 < n_my) issue_nod(k + 2);
-      if (has_next) issue_loc(k + 1);
+    }
+    if (p_loc && has_next) {
+      mbar_wait(&bar_h[(k + 1) & (kHdrRing - 1)], (uint32_t)((k + 1) >> 2) & 1u);  // its header: issued three tiles ago
+      issue_loc(k + 1);
     }
     const int4 h0 = hdr_of(k)[0], h2 = hdr_of(k)[2];
     const int32_t ne = h0.y, n_pairs = h0.w, n_items = h2.y;
@@ -422,7 +434,7 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
         }
       }
     }
-    if (producer) bulk_wait_read_all();  // the previous tile's store has finished reading the image
+    if (producer && !(use_tma_store & 2)) bulk_wait_read_all();  // the previous tile's store has finished reading the image
     __syncthreads();                     // records visible, image free, coordinates consumed
 
     int nd_next = 0;
@@ -571,8 +583,8 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
     double* img = s_out + skew_d;
     fence_proxy_async_smem();  // generic-proxy accesses (image writes, item reads) ordered before the async proxy's
     __syncthreads();           // phase 2 is over: the image is complete, the item buffer is free
-    if (producer && has_next) issue_items(k + 1);
-    if (use_tma_store) {
+    if (p_items && has_next) issue_items(k + 1);
+    if (use_tma_store & 1) {
       if (producer) {
         const int head = skew_d;                           // an odd first slot is 16-byte misaligned on both sides
         const int body = (n_out - head) & ~1, tail = n_out - head - body;
@@ -670,7 +682,8 @@ int launch_tiles(const Job& j) {
   if (FORM != FES_FORM_MASS && cf.factor < 0.0) { cf.factor = -cf.factor; cf.sign = -1.0; }
   const int64_t grid = std::min<int64_t>(P->n_tiles, (int64_t)sms * per_sm);  // persistent CTAs
   static const bool no_tma = getenv("FES_NO_TMA_STORE") != nullptr;  // tuning knob: plain coalesced stores
-  const int use_tma = (!no_tma && (reinterpret_cast<uintptr_t>(j.out) & 15) == 0) ? 1 : 0;
+  static const bool exp_nowait = getenv("FES_EXP_NOWAIT") != nullptr;  // timing experiment only: WRONG results
+  const int use_tma = ((!no_tma && (reinterpret_cast<uintptr_t>(j.out) & 15) == 0) ? 1 : 0) | (exp_nowait ? 2 : 0);
   k_assemble_tiles<ELEM, FORM, C, SD, kTileThreads><<<(unsigned)grid, kTileThreads, smem, j.stream>>>(
       P->tile_hdr.p, (int)P->n_tiles, P->tile_elems.p, P->rec_local.p, P->tile_nodes.p, P->pair_meta.p,
       P->pair_codes.p, j.coords, cf, dims, use_tma, j.out);
