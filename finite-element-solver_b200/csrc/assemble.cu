@@ -184,7 +184,7 @@ struct TileSmem {
 };
 
 struct TileDims {
-  int geo_stride, rec_max, pair_max, item_max, nod_max;  // nod_max: distinct nodes per tile, upper bound
+  int geo_stride, rec_max, pair_max, item_max, nod_max, slot_mode;  // nod_max: distinct nodes per tile, upper bound
 };
 
 template <int ELEM, int FORM, int C, int SD, int kTileThreads>
@@ -397,7 +397,7 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
         if (!live[r]) continue;
         Material m; double w;
         element_coeffs(cf, e[r], m, w);
-        const int rec = (int)rec_slot((uint32_t)gi[r]);
+        const int rec = (int)rec_slot((uint32_t)gi[r], dims.slot_mode);
         if constexpr (FORM == FES_FORM_MASS) {
           Geom<RD, SD> g;
           make_geom<RD, SD>(X[r], g);
@@ -654,7 +654,7 @@ struct Job {
 template <int ELEM, int FORM, int C, int SD, int kTileThreads>
 int launch_tiles(const Job& j) {
   const fes_plan* P = j.plan;
-  const TileDims dims{P->geo_stride, P->rec_max, P->pair_max, P->item_max, P->nod_max};
+  const TileDims dims{P->geo_stride, P->rec_max, P->pair_max, P->item_max, P->nod_max, P->slot_mode};
   const size_t smem = TileSmem<ELEM, FORM, C, SD>::total(dims.geo_stride, dims.rec_max, dims.pair_max, dims.item_max,
                                                          dims.nod_max);
   static size_t configured = 0;  // per template instantiation: largest opt-in so far

@@ -322,7 +322,7 @@ __global__ void k_tile_hdr(const int32_t* __restrict__ tile_node0, int64_t n_til
 __global__ void k_tile_emit(const int32_t* __restrict__ hdr, int64_t n_tiles, const int32_t* __restrict__ node_ptr,
                             const int32_t* __restrict__ pair_row, const int32_t* __restrict__ node_adj,
                             const uint32_t* __restrict__ pair_start, const uint32_t* __restrict__ contrib,
-                            const uint32_t* __restrict__ tile_elems, int N, int c, int gs, uint32_t L,
+                            const uint32_t* __restrict__ tile_elems, int N, int c, int gs, int slot_mode, uint32_t L,
                             uint32_t* __restrict__ meta, uint32_t* __restrict__ codes, int* __restrict__ bad) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
@@ -367,7 +367,7 @@ __global__ void k_tile_emit(const int32_t* __restrict__ hdr, int64_t n_tiles, co
                   const int mid = (lo + hi_) >> 1;
                   if (tile_elems[g0 + mid] < e) lo = mid + 1; else hi_ = mid;
                 }
-                const uint32_t slot = rec_slot((uint32_t)lo);
+                const uint32_t slot = rec_slot((uint32_t)lo, slot_mode);
                 out = ((a * (uint32_t)gs + slot) << 4) | ((b * (uint32_t)gs + slot) << 20);
               }
               codes[wa * L + x] = out;
@@ -516,10 +516,11 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
             N, c, (long long)nn, (long long)np_, (long long)nt, inc_max, rmax, pmax, imax, cmax, P->nod_max, (long long)items, P->geo_stride);
   FES_CUDA(cudaMemcpyAsync(P->tile_hdr.p, hdr.data(), hdr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
   P->item_len = (int)L;
+  P->slot_mode = getenv("FES_SLOT_MODE") ? atoi(getenv("FES_SLOT_MODE")) : tile_slot_mode(N);  // env: tuning knob
   FES_CUDA(P->pair_meta.alloc(items + 16));
   FES_CUDA(P->pair_codes.alloc(items * L + 32));
   k_tile_emit<<<grid_for(nt, 64), 64, 0, stream>>>(P->tile_hdr.p, nt, P->node_ptr.p, P->pair_row.p, P->node_adj.p,
-                                                   P->pair_start.p, P->contrib.p, P->tile_elems.p, N, c, P->geo_stride, L,
+                                                   P->pair_start.p, P->contrib.p, P->tile_elems.p, N, c, P->geo_stride, P->slot_mode, L,
                                                    P->pair_meta.p, P->pair_codes.p, bad.p);
   FES_LAUNCH_CHECK();
   FES_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));

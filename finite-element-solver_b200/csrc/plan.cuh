@@ -26,6 +26,7 @@ struct fes_plan {
   int64_t n_tiles = 0, n_geo = 0, tile_read_bytes = 0;
   int inc_max = 0;                     // (node, incident element) records per tile: the tiling budget
   int geo_stride = 0;                  // shared-memory plane stride of the records: 1 (mod 8), > rec_max
+  int slot_mode = 0;                   // rec_slot mode the codes were emitted with
   int rec_max = 0, pair_max = 0, con_max = 0, item_max = 0, nod_max = 0;  // distinct elements / pairs / contributions / work items / distinct nodes per tile, upper bounds
   int64_t n_items = 0;
   int item_len = 0;                    // contribution codes per work item (= tile_item_len(N))
@@ -56,10 +57,14 @@ struct fes_plan {
 };
 
 namespace fes {
-// Shared-memory slot of a tile's r-th distinct element: an XOR swizzle of the low three bits, so
-// strided record sequences (the k-th element of consecutive nodes) spread over the banks.  Baked
-// into the contribution codes at plan time; phase 1 of the kernel applies it when it writes.
-__host__ __device__ inline uint32_t rec_slot(uint32_t r) { return r ^ ((r >> 3) & 7u); }
+// Shared-memory slot of a tile's r-th distinct element.  Mode 0: an XOR swizzle of the low three
+// bits, so strided record sequences (the k-th element of consecutive nodes; stride 2 or 4 records on
+// triangle meshes) spread over the banks.  Mode 1: the identity -- on tetrahedral meshes the strides
+// are 3 and 6 records, which the swizzle turns into 3-way conflicts (offline bank model and ncu:
+// gathers 2.36x / 3.05x of their conflict-free wavefronts with the swizzle, 2.14x / 2.27x without).
+// Baked into the contribution codes at plan time; phase 1 of the kernel applies it when it writes.
+__host__ __device__ inline uint32_t rec_slot(uint32_t r, int mode) { return mode ? r : r ^ ((r >> 3) & 7u); }
+inline int tile_slot_mode(int N) { return N == 4 ? 1 : 0; }
 
 // contributions one lane gathers at most (longer pairs are split over 2^lg lanes): about the count of
 // an interior off-diagonal pair of that element type

@@ -1,3 +1,8 @@
 cd /root/repo
 python -m pytest tests/test_gpu_assembly.py tests/test_gpu_assembly_paths.py -m gpu -x -q 2>&1 | tail -2
-python tools/time_assembly.py c1,c2,c3,c4,tet 2>&1 | sed -e 's/.*"case": "\([^"]*\)".*"ms": \([0-9.]*\).*"hbm_frac": \([0-9.]*\).*/\1: ms=\2 frac=\3/'
+t() { echo -n "$*: "; env "${@:2}" python tools/time_assembly.py $1 2>&1 | grep "elastic" | sed -e 's/.*"ms": \([0-9.]*\).*"hbm_frac": \([0-9.]*\).*/ms=\1 frac=\2/' | tr '\n' ' '; echo; }
+t tet A=1
+t tet FES_SLOT_MODE=0
+t c3 FES_SLOT_MODE=0
+t c3 FES_SLOT_MODE=1
+t c2 A=1
