@@ -142,9 +142,15 @@ __global__ void k_negate(double* __restrict__ v, int64_t n) {
 template <int ELEM, int FORM, int C, int SD>
 struct RecLayout {
   static constexpr int N = ET<ELEM>::N, NQ = ET<ELEM>::NQ;
-  // per (quadrature point, node): one double2 plane (x, y) + a double plane (z) in 3D; mass: one weight
-  static constexpr int NV2 = (FORM == FES_FORM_MASS) ? 0 : NQ * N * (SD / 2);
-  static constexpr int NV1 = (FORM == FES_FORM_MASS) ? 1 : NQ * N * (SD & 1);
+  // P2 gradient forms: the element is affine, so every shape gradient at every quadrature point is a
+  // fixed combination of the RD rows of the inverse Jacobian -- the record holds just those rows
+  // (4 doubles for the 6-node triangle instead of 36) and phase 2 contracts them with the constant
+  // per-node-pair table c_p2tri_pair
+  static constexpr bool kRows = ET<ELEM>::P2 && FORM != FES_FORM_MASS;
+  static constexpr int NG = kRows ? ET<ELEM>::RD : NQ * N;  // gradient vectors per record
+  // per gradient vector: one double2 plane (x, y) + a double plane (z) in 3D; mass: one weight
+  static constexpr int NV2 = (FORM == FES_FORM_MASS) ? 0 : NG * (SD / 2);
+  static constexpr int NV1 = (FORM == FES_FORM_MASS) ? 1 : NG * (SD & 1);
   static constexpr int DOUBLES = 2 * NV2 + NV1;
 };
 
@@ -420,6 +426,11 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
           for (int i = 0; i < RD; ++i)
 #pragma unroll
             for (int s = 0; s < SD; ++s) cof[i][s] *= f;
+          if constexpr (R::kRows) {
+            static_assert(SD == 2, "row records are implemented for the P2 triangle");
+#pragma unroll
+            for (int rr = 0; rr < RD; ++rr) v2[rr * GS + rec] = make_double2(cof[rr][0], cof[rr][1]);
+          } else
 #pragma unroll
           for (int q = 0; q < NQ; ++q)
 #pragma unroll
@@ -456,12 +467,43 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
     // loads of a chunk are issued before its FMAs; a lane with fewer contributions reads the
     // all-zero record instead of branching (fma(0, 0, acc) == acc, bit for bit).
     constexpr int kItemLen = TS::L;
-    constexpr int CH = (NQ > 1 || FORM == FES_FORM_MASS) ? 1 : (SD == 3 ? 2 : kItemLen);
+    constexpr int CH = FORM == FES_FORM_MASS ? 1 : (R::kRows ? kItemLen : (NQ > 1 ? 1 : (SD == 3 ? 2 : kItemLen)));
     auto gather_chunk = [&](const uint32_t (&code)[CH], double (&acc)[C][C]) {
       if constexpr (FORM == FES_FORM_MASS) {
         const uint32_t ia = (code[0] & 0xffffu) >> 4, ib = code[0] >> 20;
         const uint32_t a = (uint32_t)(((uint64_t)ia * inv_gs) >> 24), b = (uint32_t)(((uint64_t)ib * inv_gs) >> 24);
         acc[0][0] = fma(lds_f64(v1_b + 8u * (ia - a * (uint32_t)GS)), mass_ref<ELEM>((int)a, (int)b), acc[0][0]);
+      } else if constexpr (R::kRows) {
+        // S += sum_rs M_ab[r][s] G_r (x) G_s: two gradient rows per contribution (one LDS.128 each) and
+        // the pair's 2 x 2 table from constant memory (neighbouring lanes mostly share (a, b))
+        double2 g0[CH], g1[CH];
+        uint32_t ab[CH];
+#pragma unroll
+        for (int x = 0; x < CH; ++x) {
+          const uint32_t oa = code[x] & 0xffffu, ia = oa >> 4, ib = code[x] >> 20;
+          const uint32_t a = (uint32_t)(((uint64_t)ia * inv_gs) >> 24), b = (uint32_t)(((uint64_t)ib * inv_gs) >> 24);
+          const uint32_t so = oa - 16u * a * (uint32_t)GS;  // byte offset of the record's slot in plane 0
+          g0[x] = lds_f64x2(v2_b + so);
+          g1[x] = lds_f64x2(v2_b + so + 16u * (uint32_t)GS);
+          ab[x] = a * 6u + b;
+        }
+#pragma unroll
+        for (int x = 0; x < CH; ++x) {
+          const double* m = c_p2tri_pair.m[ab[x]];
+          const double m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
+          // P_s = sum_r M[r][s] G_r ;  S += P_0 (x) G_0 + P_1 (x) G_1
+          const double p0x = fma(m10, g1[x].x, m00 * g0[x].x), p0y = fma(m10, g1[x].y, m00 * g0[x].y);
+          const double p1x = fma(m11, g1[x].x, m01 * g0[x].x), p1y = fma(m11, g1[x].y, m01 * g0[x].y);
+          if constexpr (FORM == FES_FORM_LAPLACIAN) {
+            acc[0][0] = fma(p0x, g0[x].x, acc[0][0]); acc[0][0] = fma(p0y, g0[x].y, acc[0][0]);
+            acc[0][0] = fma(p1x, g1[x].x, acc[0][0]); acc[0][0] = fma(p1y, g1[x].y, acc[0][0]);
+          } else {
+            acc[0][0] = fma(p0x, g0[x].x, acc[0][0]); acc[0][0] = fma(p1x, g1[x].x, acc[0][0]);
+            acc[0][1] = fma(p0x, g0[x].y, acc[0][1]); acc[0][1] = fma(p1x, g1[x].y, acc[0][1]);
+            acc[1][0] = fma(p0y, g0[x].x, acc[1][0]); acc[1][0] = fma(p1y, g1[x].x, acc[1][0]);
+            acc[1][1] = fma(p0y, g0[x].y, acc[1][1]); acc[1][1] = fma(p1y, g1[x].y, acc[1][1]);
+          }
+        }
       } else {
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {

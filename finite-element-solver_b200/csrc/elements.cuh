@@ -34,6 +34,44 @@ static __constant__ double c_p2tri_dshape[3][6][2] = {
     FES_P2G(1.0 - 1.0 / 6 - 1.0 / 6, 1.0 / 6, 1.0 / 6),
     FES_P2G(1.0 - 2.0 / 3 - 1.0 / 6, 2.0 / 3, 1.0 / 6),
     FES_P2G(1.0 - 1.0 / 6 - 2.0 / 3, 1.0 / 6, 2.0 / 3)};
+// The same table as a constexpr function, and its quadrature-summed products
+//   M_ab[r][s] = sum_q dshape[q][a][r] * dshape[q][b][s]
+// (the three Strang points carry equal weights).  On an affine element the physical gradient of
+// shape function a at point q is dshape[q][a][0] G_0 + dshape[q][a][1] G_1 with G_r the rows of the
+// inverse Jacobian, so  sum_q grad(phi_a) (x) grad(phi_b) = sum_rs M_ab[r][s] G_r (x) G_s: the tiled
+// assembly kernel stores only G_0, G_1 per element and contracts with this 2 x 2 table per node pair.
+constexpr double p2tri_dshape(int q, int a, int r) {
+  const double L1 = (q == 1) ? 2.0 / 3 : 1.0 / 6, L2 = (q == 2) ? 2.0 / 3 : 1.0 / 6, L0 = 1.0 - L1 - L2;
+  switch (a * 2 + r) {
+    case 0: case 1: return -(4.0 * L0 - 1.0);
+    case 2: return 4.0 * L1 - 1.0;
+    case 3: return 0.0;
+    case 4: return 0.0;
+    case 5: return 4.0 * L2 - 1.0;
+    case 6: return 4.0 * L2;
+    case 7: return 4.0 * L1;
+    case 8: return -4.0 * L2;
+    case 9: return 4.0 * L0 - 4.0 * L2;
+    case 10: return 4.0 * L0 - 4.0 * L1;
+    default: return -4.0 * L1;
+  }
+}
+struct P2TriPairTable {
+  double m[36][4];  // [a * 6 + b][r * 2 + s]
+};
+constexpr P2TriPairTable make_p2tri_pair_table() {
+  P2TriPairTable t{};
+  for (int a = 0; a < 6; ++a)
+    for (int b = 0; b < 6; ++b)
+      for (int r = 0; r < 2; ++r)
+        for (int s = 0; s < 2; ++s) {
+          double acc = 0.0;
+          for (int q = 0; q < 3; ++q) acc += p2tri_dshape(q, a, r) * p2tri_dshape(q, b, s);
+          t.m[a * 6 + b][r * 2 + s] = acc;
+        }
+  return t;
+}
+static __constant__ P2TriPairTable c_p2tri_pair = make_p2tri_pair_table();
 // Mass per unit measure: P2 triangle (k/180) and P2 line (k/30), exact rationals; the
 // divisions are folded at compile time so no kernel divides per contribution.
 #define FES_M180(a, b, c, d, e, f) {(a) / 180.0, (b) / 180.0, (c) / 180.0, (d) / 180.0, (e) / 180.0, (f) / 180.0}
