@@ -194,7 +194,7 @@ struct TileDims {
 };
 
 template <int ELEM, int FORM, int C, int SD, int kTileThreads>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, kTileThreads >= 256 ? 3 : 1)
 k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32_t* __restrict__ tile_elems,
                  const uint32_t* __restrict__ rec_local, const int32_t* __restrict__ tile_nodes,
                  const uint32_t* __restrict__ pair_meta, const uint32_t* __restrict__ pair_codes,

@@ -158,8 +158,9 @@ __device__ int sort_unique(uint32_t* ids, uint32_t* out, int n, int* s_cnt) {
 __global__ void __launch_bounds__(256)
 k_tile_build(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__ ne_ptr,
              const uint32_t* __restrict__ ne_code, const int32_t* __restrict__ en, int N, int n_corner,
-             uint32_t* __restrict__ tile_elems, uint32_t* __restrict__ rec_local, int32_t* __restrict__ tile_nodes,
-             int32_t* __restrict__ tile_cnt, int colour_groups, int* __restrict__ bad) {
+             uint32_t* __restrict__ tile_elems, uint32_t* __restrict__ elems_sorted, uint16_t* __restrict__ slot_of,
+             uint32_t* __restrict__ rec_local, int32_t* __restrict__ tile_nodes,
+             int32_t* __restrict__ tile_cnt, int colour_groups, int slot_mode, int* __restrict__ bad) {
   __shared__ uint32_t ids[kTileIdCap];
   __shared__ uint32_t uniq[kTileIdCap];
   __shared__ uint32_t s_el[kTileRecCap];
@@ -168,6 +169,7 @@ k_tile_build(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__
   __shared__ uint16_t s_mlist[kTileIdCap];
   __shared__ int s_used[kTileIdCap * 2];   // [group * n_corner + corner][residue]: reads already on that bank
   __shared__ uint8_t s_li[256];
+  __shared__ uint16_t s_slot[kTileRecCap];  // record (rank in ascending element id) -> position in the kernel's tables
   const int t = blockIdx.x;
   const int32_t g0 = ne_ptr[tile_node0[t]], g1 = ne_ptr[tile_node0[t + 1]];
   const int n_rec = g1 - g0;  // <= inc_max <= kTileRecCap
@@ -176,9 +178,47 @@ k_tile_build(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__
   const int ne = sort_unique(ids, uniq, n_rec, s_cnt);
   for (int i = threadIdx.x; i < ne; i += blockDim.x) {
     s_el[i] = uniq[i];
-    tile_elems[g0 + i] = uniq[i];
+    elems_sorted[g0 + i] = uniq[i];
   }
   __syncthreads();
+  // Position of every record in the kernel's tables (= its shared-memory slot, up to the swizzle).
+  // Modes 0 / 1: ascending element id.  Mode 2: order of first appearance when the tile's nodes are
+  // swept incidence-major -- the k-th incident element of node v0, of v0+1, ..., then the (k+1)-th --
+  // so on a regularly numbered mesh the k-th elements of consecutive nodes sit in consecutive slots
+  // whatever the element numbering's stride is (3 and 6 records on Kuhn tetrahedra), and the
+  // quarter-warp gathers of phase 2 fall into distinct banks.
+  if (slot_mode == 2) {
+    const int32_t v0 = tile_node0[t], v1 = tile_node0[t + 1], nn = v1 - v0;
+    for (int i = threadIdx.x; i < ne; i += blockDim.x) ids[i] = 0xffffffffu;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_rec; i += blockDim.x) {
+      int lo = v0, hi = v1;  // node of incidence g0 + i: the last v with ne_ptr[v] <= g0 + i
+      while (hi - lo > 1) {
+        const int m = (lo + hi) >> 1;
+        if (ne_ptr[m] <= g0 + i) lo = m; else hi = m;
+      }
+      const uint32_t pos = (uint32_t)(g0 + i - ne_ptr[lo]) * (uint32_t)nn + (uint32_t)(lo - v0);
+      const uint32_t e = ne_code[g0 + i] >> 3;
+      int a = 0, b = ne;
+      while (a < b) {
+        const int m = (a + b) >> 1;
+        if (s_el[m] < e) a = m + 1; else b = m;
+      }
+      atomicMin(&ids[a], pos);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ne; i += blockDim.x) ids[i] = (ids[i] << 10) | (uint32_t)i;  // pos < 2^18, i < 2^10: unique
+    __syncthreads();
+    sort_unique(ids, uniq, ne, s_cnt);
+    for (int i = threadIdx.x; i < ne; i += blockDim.x) s_slot[uniq[i] & 1023u] = (uint16_t)i;
+  } else {
+    for (int i = threadIdx.x; i < ne; i += blockDim.x) s_slot[i] = (uint16_t)i;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+    tile_elems[g0 + s_slot[i]] = s_el[i];
+    slot_of[g0 + i] = s_slot[i];
+  }
   const int n_ids = ne * n_corner;
   if (n_ids > kTileIdCap) {  // uniform across the CTA
     if (threadIdx.x == 0) { atomicExch(bad, 1); tile_cnt[2 * t] = ne; tile_cnt[2 * t + 1] = 0; }
@@ -233,7 +273,7 @@ k_tile_build(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__
     for (int i = threadIdx.x; i < n_ids; i += blockDim.x) {
       const int r = i / n_corner, k = i - r * n_corner;
       const int at = atomicAdd(&s_cnt[ids[i]], 1);
-      s_mlist[at] = (uint16_t)((r / G) * n_corner + k);  // (wavefront group, corner): order within a node is irrelevant
+      s_mlist[at] = (uint16_t)(((int)s_slot[r] / G) * n_corner + k);  // (wavefront group, corner): order within a node is irrelevant
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -272,7 +312,7 @@ k_tile_build(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__
   for (int r = threadIdx.x; r < ne; r += blockDim.x) {
     uint32_t packed = 0;
     for (int k = 0; k < n_corner; ++k) packed |= (uint32_t)s_li[ids[r * n_corner + k]] << (8 * k);
-    rec_local[g0 + r] = packed;
+    rec_local[g0 + s_slot[r]] = packed;
   }
 }
 
@@ -322,7 +362,8 @@ __global__ void k_tile_hdr(const int32_t* __restrict__ tile_node0, int64_t n_til
 __global__ void k_tile_emit(const int32_t* __restrict__ hdr, int64_t n_tiles, const int32_t* __restrict__ node_ptr,
                             const int32_t* __restrict__ pair_row, const int32_t* __restrict__ node_adj,
                             const uint32_t* __restrict__ pair_start, const uint32_t* __restrict__ contrib,
-                            const uint32_t* __restrict__ tile_elems, int N, int c, int gs, int slot_mode, uint32_t L,
+                            const uint32_t* __restrict__ elems_sorted, const uint16_t* __restrict__ slot_of, int N, int c, int gs,
+                            int slot_mode, uint32_t L,
                             uint32_t* __restrict__ meta, uint32_t* __restrict__ codes, int* __restrict__ bad) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
@@ -365,9 +406,9 @@ __global__ void k_tile_emit(const int32_t* __restrict__ hdr, int64_t n_tiles, co
                 int lo = 0, hi_ = ne;  // record of element e: its rank among the tile's distinct elements
                 while (lo < hi_) {
                   const int mid = (lo + hi_) >> 1;
-                  if (tile_elems[g0 + mid] < e) lo = mid + 1; else hi_ = mid;
+                  if (elems_sorted[g0 + mid] < e) lo = mid + 1; else hi_ = mid;
                 }
-                const uint32_t slot = rec_slot((uint32_t)lo, slot_mode);
+                const uint32_t slot = rec_slot((uint32_t)slot_of[g0 + lo], slot_mode);
                 out = ((a * (uint32_t)gs + slot) << 4) | ((b * (uint32_t)gs + slot) << 20);
               }
               codes[wa * L + x] = out;
@@ -454,6 +495,9 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
   FES_CUDA(bad.alloc(1));
   FES_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), stream));
   FES_CUDA(P->tile_elems.alloc(P->n_geo + 16));
+  FES_CUDA(P->elems_sorted.alloc(P->n_geo + 16));
+  FES_CUDA(P->slot_of.alloc(P->n_geo + 16));
+  P->slot_mode = getenv("FES_SLOT_MODE") ? atoi(getenv("FES_SLOT_MODE")) : tile_slot_mode(N);  // env: tuning knob
   FES_CUDA(P->rec_local.alloc(P->n_geo + 16));
   FES_CUDA(P->tile_nodes.alloc((size_t)nt * fes_plan::kTileNodeStride + 64));
   FES_CUDA(P->tile_cnt.alloc(2 * nt));
@@ -461,8 +505,8 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
   static const bool no_colour = getenv("FES_PLAN_NO_COLOUR") != nullptr;  // tuning knob: sorted ranks
   const int colour_groups = no_colour ? 0 : (N == 4 ? 16 : 8);
   k_tile_build<<<(unsigned)nt, 256, 0, stream>>>(P->tile_node0.p, P->ne_ptr.p, P->ne_code.p, d_elem_nodes, N, P->n_corner,
-                                                 P->tile_elems.p, P->rec_local.p, P->tile_nodes.p, P->tile_cnt.p,
-                                                 colour_groups, bad.p);
+                                                 P->tile_elems.p, P->elems_sorted.p, P->slot_of.p, P->rec_local.p,
+                                                 P->tile_nodes.p, P->tile_cnt.p, colour_groups, P->slot_mode, bad.p);
   FES_LAUNCH_CHECK();
   int h_bad = 0;
   FES_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -516,16 +560,17 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
             N, c, (long long)nn, (long long)np_, (long long)nt, inc_max, rmax, pmax, imax, cmax, P->nod_max, (long long)items, P->geo_stride);
   FES_CUDA(cudaMemcpyAsync(P->tile_hdr.p, hdr.data(), hdr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
   P->item_len = (int)L;
-  P->slot_mode = getenv("FES_SLOT_MODE") ? atoi(getenv("FES_SLOT_MODE")) : tile_slot_mode(N);  // env: tuning knob
   FES_CUDA(P->pair_meta.alloc(items + 16));
   FES_CUDA(P->pair_codes.alloc(items * L + 32));
   k_tile_emit<<<grid_for(nt, 64), 64, 0, stream>>>(P->tile_hdr.p, nt, P->node_ptr.p, P->pair_row.p, P->node_adj.p,
-                                                   P->pair_start.p, P->contrib.p, P->tile_elems.p, N, c, P->geo_stride, P->slot_mode, L,
+                                                   P->pair_start.p, P->contrib.p, P->elems_sorted.p, P->slot_of.p, N, c, P->geo_stride, P->slot_mode, L,
                                                    P->pair_meta.p, P->pair_codes.p, bad.p);
   FES_LAUNCH_CHECK();
   FES_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
   FES_CUDA(cudaStreamSynchronize(stream));  // also keeps `hdr` alive until the upload is done
   if (h_bad) return FES_OK;  // offsets beyond 16 bits: keep the untiled kernel
+  P->elems_sorted.release();  // plan-time lookups only
+  P->slot_of.release();
   P->tiled = true;
   return FES_OK;
 }

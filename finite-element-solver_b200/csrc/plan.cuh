@@ -37,7 +37,9 @@ struct fes_plan {
   // element's corner nodes as indices into the tile's sorted distinct-node list
   static constexpr int kTileNodeStride = 256;
   int n_corner = 0;                    // corner nodes stored per record (N, or 3 for the 6-node triangle)
-  fes::DevBuf<uint32_t> tile_elems;    // n_geo (+pad)
+  fes::DevBuf<uint32_t> tile_elems;    // n_geo (+pad) : element ids in table order (see rec_slot)
+  fes::DevBuf<uint32_t> elems_sorted;  // n_geo (+pad) : the same ids ascending   } plan-time lookups, released once the
+  fes::DevBuf<uint16_t> slot_of;       // n_geo (+pad) : table position by rank   } work items are emitted
   fes::DevBuf<uint32_t> rec_local;     // n_geo (+pad) : corner k's index in the tile list at bits [8k, 8k+8)
   fes::DevBuf<int32_t> tile_nodes;     // n_tiles * 256 : sorted distinct node ids (first nd valid)
   fes::DevBuf<int32_t> tile_cnt;       // n_tiles * 2 : {distinct elements, distinct nodes}
@@ -57,14 +59,19 @@ struct fes_plan {
 };
 
 namespace fes {
-// Shared-memory slot of a tile's r-th distinct element.  Mode 0: an XOR swizzle of the low three
-// bits, so strided record sequences (the k-th element of consecutive nodes; stride 2 or 4 records on
-// triangle meshes) spread over the banks.  Mode 1: the identity -- on tetrahedral meshes the strides
-// are 3 and 6 records, which the swizzle turns into 3-way conflicts (offline bank model and ncu:
-// gathers 2.36x / 3.05x of their conflict-free wavefronts with the swizzle, 2.14x / 2.27x without).
+// Shared-memory slot of the record at position r of a tile's element tables.
+//   mode 0: tables in ascending element id, slot = an XOR swizzle of the low three bits, so strided
+//           record sequences (the k-th element of consecutive nodes: stride 2 or 4 records on triangle
+//           meshes) spread over the banks;
+//   mode 1: ascending element id, slot = position;
+//   mode 2: tables in incidence-major first-appearance order (k_tile_build), slot = position -- the
+//           k-th elements of consecutive nodes sit in consecutive slots whatever the stride of the
+//           element numbering.  Tetrahedral meshes (strides 3 and 6 records): gathers at 2.36x / 3.05x
+//           of their conflict-free wavefronts in mode 0, 2.14x / 2.27x in mode 1, 1.31x / 1.56x in
+//           mode 2 (tools/bank_sim.py model; the first two confirmed by ncu).
 // Baked into the contribution codes at plan time; phase 1 of the kernel applies it when it writes.
 __host__ __device__ inline uint32_t rec_slot(uint32_t r, int mode) { return mode ? r : r ^ ((r >> 3) & 7u); }
-inline int tile_slot_mode(int N) { return N == 4 ? 1 : 0; }
+inline int tile_slot_mode(int N) { return N == 4 ? 2 : 0; }
 
 // contributions one lane gathers at most (longer pairs are split over 2^lg lanes): about the count of
 // an interior off-diagonal pair of that element type
