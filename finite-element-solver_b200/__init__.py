@@ -12,8 +12,8 @@ from .design import DesignHistory, DesignOptimizer, SIMPModel, optimality_criter
 from .elements import (LinearLineElement, LinearTetrahedralElement, LinearTriangleElement,  # noqa: F401
                        QuadraticLineElement, QuadraticTriangleElement)
 from .equations import LinearElastic, Poisson  # noqa: F401
-from .forms import (LaplacianForm, LinearElasticForm, MaskedMassForm, MassForm, PrecomputedForm,  # noqa: F401
-                    ScaledForm)
+from .forms import (DiffusionForm, ElasticFields, GeometricStiffnessForm, LaplacianForm,  # noqa: F401
+                    LinearElasticForm, LinearForm, MaskedMassForm, MassForm, PrecomputedForm, ScaledForm)
 from .materials import LinearElasticMaterial  # noqa: F401
 from .mesh import Mesh, create_box_mesh, create_rect_mesh  # noqa: F401
 from .integrators import NewmarkMethod, ThetaMethod, TransientSolution, WaveSolution, wave_energy  # noqa: F401

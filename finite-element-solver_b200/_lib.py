@@ -71,6 +71,12 @@ SIGNATURES = {
     'fes_simp_sensitivity': (_int, [_p, _p, _dbl, _dbl, _i64, _p, _p]),
     'fes_oc_update': (_int, [_p, _p, _p, _i64, _dbl, _dbl, _int, _dbl, _p, C.POINTER(_int), _p]),
     'fes_dot': (_int, [_p, _p, _i64, C.POINTER(_dbl), _p]),
+    'fes_node_scatter': (_int, [_p, _p, _int, _p, _p]),
+    'fes_quadrature_size': (_int, [_int, _int]),
+    'fes_quadrature_points': (_int, [_int, _int, _int, _p, _i64, _p, _p, _p, _p]),
+    'fes_element_loads': (_int, [_int, _int, _int, _p, _i64, _p, _p, _int, _p, _p]),
+    'fes_weighted_gradient_matrices': (_int, [_int, _int, _int, _int, _p, _i64, _p, _p, _p, _p, _p]),
+    'fes_elastic_fields': (_int, [_int, _p, _i64, _p, _p, _p, _dbl, _dbl, _int, _p, _p, _p, _p]),
 }
 
 _lib = None

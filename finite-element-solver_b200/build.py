@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libfes_b200.so')
-SOURCES = ['core.cu', 'plan.cu', 'assemble.cu', 'pcg.cu', 'simp.cu']
+SOURCES = ['core.cu', 'plan.cu', 'assemble.cu', 'pcg.cu', 'simp.cu', 'fields.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

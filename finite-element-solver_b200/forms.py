@@ -83,6 +83,26 @@ class LinearElasticForm(_Form):
             return Lowered(_lib.FORM_ELASTIC, E=1.0, nu=float(m.nu), E_elem=E)
         return Lowered(_lib.FORM_ELASTIC, E=float(m.E), nu=float(m.nu))
 
+    def derived_fields(self, space, u):
+        """Element strain, stress (full 3x3 tensors, plane-strain lift in 2D) and compliance from the
+        DOF vector `u`, at the first quadrature point of the space's default rule
+        (ref fem/forms.py:335-374).  Device tensors."""
+        m = self.material
+        n_el = len(space.element_nodes)
+        ud = u if isinstance(u, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(u, dtype=np.float64))
+        ud = ud.to(device=space.device, dtype=torch.float64).contiguous().reshape(-1)
+        if ud.numel() != space.n_nodes * space.spatial_dim:
+            raise ValueError(f'expected {space.n_nodes * space.spatial_dim} displacement DOFs, got {ud.numel()}')
+        E_elem = _per_element(m.E, n_el, space.device, 'per-element modulus') if m.per_element() else None
+        eps = torch.empty((n_el, 3, 3), dtype=torch.float64, device=space.device)
+        sig = torch.empty_like(eps)
+        comp = torch.empty(n_el, dtype=torch.float64, device=space.device)
+        _lib.check(_lib.lib().fes_elastic_fields(
+            space.element_type.KIND, _lib.ptr(space._en_d), n_el, _lib.ptr(space._coords_d), _lib.ptr(ud),
+            _lib.ptr(E_elem), 0.0 if m.per_element() else float(m.E), float(m.nu),
+            space.element_type.default_quadrature_degree(), _lib.ptr(eps), _lib.ptr(sig), _lib.ptr(comp), _lib.stream()))
+        return ElasticFields(eps, sig, comp)
+
 
 @dataclass(frozen=True, eq=False)
 class ScaledForm(_Form):
@@ -93,6 +113,96 @@ class ScaledForm(_Form):
         low = self.form.lower(space, boundary)
         low.factor *= float(self.factor)
         return low
+
+
+def _sample_field(field, space, n_components, degree):
+    """The field at every quadrature point, (n_el, n_qp, n_components) on the device: constants are
+    broadcast, callables are evaluated on the host over the flattened points exactly as the reference's
+    `_sample_field` does (ref fem/forms.py:261-271)."""
+    from .regions import evaluate_field
+    points, _ = space.quadrature(degree)
+    n_el, n_qp, sd = points.shape
+    if callable(field):
+        values = evaluate_field(field, points.reshape(n_el * n_qp, sd).cpu().numpy(), n_components)
+    else:
+        values = evaluate_field(field, np.zeros((1, sd)), n_components)
+        values = np.broadcast_to(values, (n_el * n_qp, n_components))
+    return torch.as_tensor(np.ascontiguousarray(values, dtype=np.float64)).to(space.device).reshape(n_el, n_qp, n_components)
+
+
+class _MatrixForm:
+    """Forms whose element matrices are computed by their own (unfused) kernel and scattered by the
+    bit-exact gather of `fes_assemble_precomputed`."""
+    precomputed = True
+
+    def lower(self, space, boundary=False):
+        return None
+
+
+@dataclass(frozen=True, eq=False)
+class DiffusionForm(_MatrixForm):
+    """Variable-coefficient diffusion, kappa sampled at the quadrature points (ref fem/forms.py:273-293)."""
+    coefficient: object
+    quadrature_degree: int = 2
+
+    def element_matrices(self, space, boundary=False):
+        if boundary:
+            raise NotImplementedError('DiffusionForm is a volume form')
+        kappa = _sample_field(self.coefficient, space, 1, self.quadrature_degree)[..., 0].contiguous()
+        n_el, k = len(space.element_nodes), space.element_type.N * space.n_components
+        out = torch.empty((n_el, k, k), dtype=torch.float64, device=space.device)
+        _lib.check(_lib.lib().fes_weighted_gradient_matrices(
+            space.element_type.KIND, space.spatial_dim, space.n_components, self.quadrature_degree,
+            _lib.ptr(space._en_d), n_el, _lib.ptr(space._coords_d), _lib.ptr(kappa), None, _lib.ptr(out), _lib.stream()))
+        return out
+
+
+@dataclass(frozen=True, eq=False)
+class GeometricStiffnessForm(_MatrixForm):
+    """Initial-stress stiffness from a per-element prestress (n_el, d, d) (ref fem/forms.py:401-441)."""
+    prestress: object
+
+    def element_matrices(self, space, boundary=False):
+        if boundary:
+            raise NotImplementedError('GeometricStiffnessForm is a volume form')
+        d, n_el = space.spatial_dim, len(space.element_nodes)
+        sigma = self.prestress if isinstance(self.prestress, torch.Tensor) else \
+            torch.as_tensor(np.ascontiguousarray(self.prestress, dtype=np.float64))
+        if tuple(sigma.shape) != (n_el, d, d):
+            raise ValueError(f'prestress must be ({n_el}, {d}, {d}) for this mesh, got shape {tuple(sigma.shape)}')
+        sigma = sigma.to(device=space.device, dtype=torch.float64).contiguous()
+        k = space.element_type.N * space.n_components
+        out = torch.empty((n_el, k, k), dtype=torch.float64, device=space.device)
+        _lib.check(_lib.lib().fes_weighted_gradient_matrices(
+            space.element_type.KIND, d, space.n_components, space.element_type.default_quadrature_degree(),
+            _lib.ptr(space._en_d), n_el, _lib.ptr(space._coords_d), None, _lib.ptr(sigma), _lib.ptr(out), _lib.stream()))
+        return out
+
+
+@dataclass(frozen=True, eq=False)
+class LinearForm:
+    """L(v) = int f.v with f sampled at the quadrature points (ref fem/forms.py:296-315)."""
+    field: object
+    n_components: int = 1
+    quadrature_degree: int = 2
+
+    def element_vectors(self, space):
+        """(n_el, N * n_components) element load vectors on the device, DOFs interleaved per node."""
+        f = _sample_field(self.field, space, self.n_components, self.quadrature_degree)
+        n_el, N = len(space.element_nodes), space.element_type.N
+        out = torch.empty((n_el, N * self.n_components), dtype=torch.float64, device=space.device)
+        _lib.check(_lib.lib().fes_element_loads(
+            space.element_type.KIND, space.spatial_dim, self.quadrature_degree, _lib.ptr(space._en_d), n_el,
+            _lib.ptr(space._coords_d), _lib.ptr(f), self.n_components, _lib.ptr(out), _lib.stream()))
+        return out
+
+
+@dataclass(frozen=True)
+class ElasticFields:
+    """Per-element strain / stress as (n_el, 3, 3) tensors and compliance (ref fem/forms.py:153-173)."""
+    strain: object
+    stress: object
+    compliance: object
 
 
 @dataclass(frozen=True, eq=False)

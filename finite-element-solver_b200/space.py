@@ -210,7 +210,7 @@ class FunctionSpace:
         conn, etype = self._conn(boundary)
         values = out if out is not None else torch.empty(plan.nnz, dtype=torch.float64, device=self.device)
         L = _lib.lib()
-        if isinstance(form, PrecomputedForm):
+        if isinstance(form, PrecomputedForm) or getattr(form, 'precomputed', False):
             Ke = form.element_matrices(self, boundary)
             if not isinstance(Ke, torch.Tensor):
                 Ke = torch.as_tensor(np.ascontiguousarray(Ke, dtype=np.float64))
@@ -218,7 +218,7 @@ class FunctionSpace:
             if Ke.numel() != plan.n_entries:
                 raise ValueError(f'expected element matrices covering {plan.n_entries} entries, got '
                                  f'{Ke.numel()} (shape {tuple(Ke.shape)})')
-            scale = form.scale
+            scale = getattr(form, 'scale', None)
             if scale is not None and not isinstance(scale, torch.Tensor):
                 scale = torch.as_tensor(np.ascontiguousarray(scale, dtype=np.float64)).to(self.device)
             _lib.check(L.fes_assemble_precomputed(plan.handle, _lib.ptr(Ke), _lib.ptr(scale), 1.0,
@@ -243,6 +243,118 @@ class FunctionSpace:
         values = self._assemble_values(form, boundary)
         indptr, indices = plan.host_pattern()
         return csr_array((values.cpu().numpy(), indices, indptr), shape=(self.n_dofs, self.n_dofs))
+
+    # -- quadrature-tabulated loads and nodal recovery -----------------
+    def quadrature(self, min_degree):
+        """(points (n_el, n_qp, sd), weight_detJ (n_el, n_qp)) of the volume elements at the cheapest
+        tabulated rule of degree >= min_degree, cached per rule (ref fem/space.py:412-425)."""
+        cache = self.__dict__.setdefault('_quad_cache', {})
+        L = _lib.lib()
+        nq = int(L.fes_quadrature_size(self.element_type.KIND, int(min_degree)))
+        if nq == 0:
+            raise NotImplementedError(f'no quadrature rule of degree >= {min_degree} for '
+                                      f'reference_dim={self.element_type.REF_DIM}')
+        if nq not in cache:
+            n_el = len(self.element_nodes)
+            pts = torch.empty((n_el, nq, self.spatial_dim), dtype=torch.float64, device=self.device)
+            wdet = torch.empty((n_el, nq), dtype=torch.float64, device=self.device)
+            _lib.check(L.fes_quadrature_points(self.element_type.KIND, self.spatial_dim, int(min_degree),
+                                               _lib.ptr(self._en_d), n_el, _lib.ptr(self._coords_d), _lib.ptr(pts),
+                                               _lib.ptr(wdet), _lib.stream()))
+            cache[nq] = (pts, wdet)
+        return cache[nq]
+
+    def node_scatter(self, element_values, m):
+        """Sum (n_el, N, m) per-(element, local node) values into (n_nodes, m), each node in ascending
+        element id: bit-identical to the reference's bincount / np.add.at scatters
+        (ref fem/space.py:148-184, 578-596)."""
+        vals = element_values.to(device=self.device, dtype=torch.float64).contiguous()
+        n_el, N = self._en_d.shape
+        if vals.numel() != n_el * N * m:
+            raise ValueError(f'expected element vectors covering {n_el * N * m} entries, got {vals.numel()} '
+                             f'(shape {tuple(vals.shape)})')
+        out = torch.empty((self.n_nodes, m), dtype=torch.float64, device=self.device)
+        _lib.check(_lib.lib().fes_node_scatter(self.plan().handle, _lib.ptr(vals), int(m), _lib.ptr(out), _lib.stream()))
+        return out
+
+    def assemble_load_d(self, form):
+        if form.n_components != self.n_components:
+            raise ValueError(f'LinearForm({form.n_components}) on a space with {self.n_components} components')
+        return self.node_scatter(form.element_vectors(self), self.n_components).reshape(-1)
+
+    def assemble_load(self, form):
+        """Scatter a LinearForm's element vectors into the global load vector (ref fem/space.py:698-708)."""
+        return self.assemble_load_d(form).cpu().numpy()
+
+    def recover_nodal(self, values, method='average'):
+        """A continuous nodal field from a per-element one (ref fem/space.py:545-616): 'average' is the
+        volume-weighted nodal average (summed in the reference's order), 'l2' the global L2 projection
+        (mass solve by Jacobi-PCG to rtol 1e-13 instead of a sparse LU)."""
+        host = not isinstance(values, torch.Tensor)
+        v = torch.as_tensor(np.asarray(values, dtype=np.float64)) if host else values
+        v = v.to(device=self.device, dtype=torch.float64)
+        n_el, N = self._en_d.shape
+        if v.shape[0] != n_el:
+            raise ValueError(f'expected one value per element ({n_el}), got {v.shape[0]}')
+        trailing = tuple(v.shape[1:])
+        flat = v.reshape(n_el, -1)
+        m = flat.shape[1]
+        if method == 'average':
+            w = self.element_volumes_d
+            weighted = (flat * w[:, None])[:, None, :].expand(n_el, N, m)
+            sums = self.node_scatter(weighted, m)
+            norms = self.node_scatter(w[:, None, None].expand(n_el, N, 1), 1)
+            norms = torch.where(norms > 0, norms, torch.ones_like(norms))
+            out = (sums / norms).reshape((self.n_nodes,) + trailing)
+        elif method == 'l2':
+            ones = self._element_loads(torch.ones((n_el, self._default_nq(), 1), dtype=torch.float64, device=self.device),
+                                       self.element_type.default_quadrature_degree())   # (n_el, N, 1): int_e phi_n
+            contrib = ones * flat[:, None, :]                      # (n_el, N, m): f_e * int_e phi_n
+            load = self.node_scatter(contrib, m)
+            out = self._nodal_mass_solve(load).reshape((self.n_nodes,) + trailing)
+        else:
+            raise ValueError(f"unknown recovery method {method!r}; use 'average' or 'l2'")
+        return out.cpu().numpy() if host else out
+
+    def _default_nq(self):
+        return int(_lib.lib().fes_quadrature_size(self.element_type.KIND, self.element_type.default_quadrature_degree()))
+
+    def _element_loads(self, f_qp, degree):
+        """(n_el, N, m) = sum_q w_eq phi_n(q) f[e, q, :] (ref fem/forms.py:310-315)."""
+        n_el, N = self._en_d.shape
+        m = f_qp.shape[2]
+        out = torch.empty((n_el, N, m), dtype=torch.float64, device=self.device)
+        _lib.check(_lib.lib().fes_element_loads(self.element_type.KIND, self.spatial_dim, int(degree), _lib.ptr(self._en_d),
+                                                n_el, _lib.ptr(self._coords_d), _lib.ptr(f_qp.contiguous()), m,
+                                                _lib.ptr(out), _lib.stream()))
+        return out
+
+    def project_to_nodal(self, values_qp, degree=None):
+        """L2-project a per-quadrature-point field (n_el, n_qp, *shape) sampled at the rule of `degree`
+        (default: the space's own) onto the nodal space (ref fem/space.py:618-640)."""
+        host = not isinstance(values_qp, torch.Tensor)
+        v = torch.as_tensor(np.asarray(values_qp, dtype=np.float64)) if host else values_qp
+        v = v.to(device=self.device, dtype=torch.float64)
+        degree = self.element_type.default_quadrature_degree() if degree is None else degree
+        trailing = tuple(v.shape[2:])
+        flat = v.reshape(v.shape[0], v.shape[1], -1)
+        load = self.node_scatter(self._element_loads(flat, degree), flat.shape[2])
+        out = self._nodal_mass_solve(load).reshape((self.n_nodes,) + trailing)
+        return out.cpu().numpy() if host else out
+
+    def _nodal_mass_solve(self, load):
+        """M q = load for every column, M the scalar consistent mass matrix (ref fem/space.py:655-667)."""
+        from .backends import JacobiPCGBackend
+        if '_nodal_mass_solver' not in self.__dict__:
+            scalar = self if self.n_components == 1 else FunctionSpace(self.mesh, self.element_type, 1, self.device)
+            self.__dict__['_nodal_mass_solver'] = JacobiPCGBackend(rtol=1e-13).prepare(scalar.mass_matrix_d)
+        solver = self.__dict__['_nodal_mass_solver']
+        cols = []
+        for j in range(load.shape[1]):
+            x = torch.zeros(self.n_nodes, dtype=torch.float64, device=self.device)
+            solver.solve_device(load[:, j].contiguous(), x, warm_start=False)
+            cols.append(x)
+        return torch.stack(cols, dim=1)
 
     @cached_property
     def mass_matrix_d(self):

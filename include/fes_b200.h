@@ -209,6 +209,36 @@ int fes_oc_update(const double* d_rho, const double* d_sens, const double* d_vol
 /* deterministic reductions used by the drivers: sum(a*b) (b NULL -> sum(a)) */
 int fes_dot(const double* d_a, const double* d_b, int64_t n, double* h_out, void* stream);
 
+/* ---- quadrature-tabulated forms and nodal recovery ------------------ */
+/* _VectorScatterPlan.scatter (ref fem/space.py:148-184) and the np.add.at of recover_nodal
+ * (ref fem/space.py:578-596): d_elem_values is (n_el, nodes_per_elem, m); d_out (n_nodes, m)
+ * receives, per node, the sum over its incident (element, local node) entries in ascending
+ * element id -- np.bincount's order, so the result is bit-identical to the reference's. */
+int fes_node_scatter(const fes_plan* plan, const double* d_elem_values, int m, double* d_out, void* stream);
+/* points of the cheapest tabulated rule of degree >= min_degree (ref fem/quadrature.py:54-114); 0 = none */
+int fes_quadrature_size(int elem_kind, int min_degree);
+/* ElementGeometry.points (n_el, nq, spatial_dim) and weight_detJ (n_el, nq) at that rule
+ * (ref fem/elements.py:174-212); either output may be NULL. Volume elements only. */
+int fes_quadrature_points(int elem_kind, int spatial_dim, int min_degree, const int32_t* d_elem_nodes,
+                          int64_t n_el, const double* d_coords, double* d_points, double* d_wdet, void* stream);
+/* LinearForm.element_vectors (ref fem/forms.py:296-315): d_f_qp is the field sampled at the rule's
+ * points, (n_el, nq, n_comp); d_out is (n_el, nodes_per_elem, n_comp). */
+int fes_element_loads(int elem_kind, int spatial_dim, int min_degree, const int32_t* d_elem_nodes, int64_t n_el,
+                      const double* d_coords, const double* d_f_qp, int n_comp, double* d_out, void* stream);
+/* K[(a,i),(b,j)] = delta_ij sum_q w_q kappa_q grad(phi_a)^T T grad(phi_b):  DiffusionForm (d_kappa_qp
+ * (n_el, nq), d_tensor NULL; ref fem/forms.py:273-293) and GeometricStiffnessForm (d_tensor (n_el, d, d)
+ * prestress, d_kappa_qp NULL; ref fem/forms.py:401-441).  d_Ke is (n_el, k, k), k = nodes * n_comp;
+ * scatter it with fes_assemble_precomputed. */
+int fes_weighted_gradient_matrices(int elem_kind, int spatial_dim, int n_comp, int min_degree,
+                                   const int32_t* d_elem_nodes, int64_t n_el, const double* d_coords,
+                                   const double* d_kappa_qp, const double* d_tensor, double* d_Ke, void* stream);
+/* LinearElasticForm.derived_fields (ref fem/forms.py:335-374): (n_el, 3, 3) strain and stress at the
+ * first point of the rule (plane-strain lift in 2D) and compliance = stress:strain * volume.  d_E NULL ->
+ * uniform modulus E.  Outputs may be NULL. */
+int fes_elastic_fields(int elem_kind, const int32_t* d_elem_nodes, int64_t n_el, const double* d_coords,
+                       const double* d_u, const double* d_E, double E, double nu, int min_degree,
+                       double* d_strain, double* d_stress, double* d_compliance, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

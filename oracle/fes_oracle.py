@@ -623,3 +623,67 @@ def design_step(elem_nodes, c, n_nodes_total, K0, rho, penalty, free, fixed, fix
     if filt is not None:
         sens = filt @ sens
     return u, grad, oc_update(rho, sens, volumes, volume_frac, move=move)
+
+
+# --------------------------------------------------------------------------------------
+# quadrature-tabulated forms and nodal recovery
+# --------------------------------------------------------------------------------------
+def node_scatter(elem_nodes, values, n_nodes_total):
+    """Sum (n_el, N, m) per-(element, local node) values into (n_nodes, m) with np.bincount, the
+    reference's scatter (ref: fem/space.py:148-184 _VectorScatterPlan, :590-591 np.add.at)."""
+    values = np.asarray(values, dtype=float)
+    flat = np.asarray(elem_nodes).ravel()
+    vals = values.reshape(len(flat), -1)
+    return np.column_stack([np.bincount(flat, weights=vals[:, j], minlength=n_nodes_total)
+                            for j in range(vals.shape[1])])
+
+
+def element_loads(geo, f_qp):
+    """b[e,n,c] = sum_q w_eq phi_n(q) f[e,q,c] (ref: fem/forms.py:310-315)."""
+    return np.einsum('eq,qn,eqc->enc', geo.wdet, geo.shape, np.asarray(f_qp, dtype=float))
+
+
+def assemble_load(elem_nodes, n_nodes_total, geo, f_qp):
+    """LinearForm load vector, DOFs interleaved per node (ref: fem/space.py:698-708)."""
+    return node_scatter(elem_nodes, element_loads(geo, f_qp), n_nodes_total).ravel()
+
+
+def ke_diffusion(geo, kappa_qp):
+    """ref: fem/forms.py:289-293."""
+    return np.einsum('eqid,eqjd,eq->eij', geo.grad, geo.grad, geo.wdet * np.asarray(kappa_qp, dtype=float))
+
+
+def ke_geometric(geo, prestress):
+    """sum_q w_q G^T (I (x) sigma0) G: the scalar g_a^T sigma0 g_b on each component's diagonal
+    (ref: fem/forms.py:74-94, 425-441)."""
+    d = geo.grad.shape[-1]
+    s = np.einsum('eqai,eij,eqbj,eq->eab', geo.grad, np.asarray(prestress, dtype=float), geo.grad, geo.wdet)
+    n_el, N, _ = s.shape
+    K = np.zeros((n_el, N * d, N * d))
+    for c in range(d):
+        K[:, c::d, c::d] = s
+    return K
+
+
+def recover_nodal_average(elem_nodes, volumes, values, n_nodes_total):
+    """Volume-weighted nodal average (ref: fem/space.py:578-596)."""
+    values = np.asarray(values, dtype=float)
+    n_el, N = np.asarray(elem_nodes).shape
+    trailing = values.shape[1:]
+    flat = values.reshape(n_el, -1) * volumes[:, None]
+    sums = node_scatter(elem_nodes, np.repeat(flat[:, None, :], N, axis=1), n_nodes_total)
+    norms = node_scatter(elem_nodes, np.repeat(volumes[:, None, None], N, axis=1), n_nodes_total)
+    norms = np.where(norms > 0, norms, 1.0)
+    return (sums / norms).reshape((n_nodes_total,) + trailing)
+
+
+def recover_nodal_l2(elem_nodes, geo, values, n_nodes_total, mass, solve):
+    """Global L2 projection of an element-constant field: M q = sum_e f_e int_e phi (ref: fem/space.py:598-616)."""
+    values = np.asarray(values, dtype=float)
+    n_el = len(values)
+    trailing = values.shape[1:]
+    shape_integral = np.einsum('eq,qn->en', geo.wdet, geo.shape)
+    contrib = shape_integral[:, :, None] * values.reshape(n_el, 1, -1)
+    load = node_scatter(elem_nodes, contrib, n_nodes_total)
+    q = np.column_stack([solve(mass, load[:, j]) for j in range(load.shape[1])])
+    return q.reshape((n_nodes_total,) + trailing)

@@ -25,8 +25,8 @@ from fem.design import DesignOptimizer, SIMPModel, optimality_criteria_update  #
 from fem.sensitivity import Compliance, DensityField, ModulusField, PointValue, SensitivityAnalysis  # noqa: E402
 from fem.elements import QuadraticTriangleElement  # noqa: E402
 from fem.equations import LinearElastic, Poisson  # noqa: E402
-from fem.forms import (LaplacianForm, LinearElasticForm, MaskedMassForm, MassForm,  # noqa: E402
-                       PrecomputedForm, ScaledForm)
+from fem.forms import (DiffusionForm, GeometricStiffnessForm, LaplacianForm, LinearElasticForm,  # noqa: E402
+                       LinearForm, MaskedMassForm, MassForm, PrecomputedForm, ScaledForm)
 from fem.materials import LinearElasticMaterial  # noqa: E402
 from fem.mesh.structured import create_box_mesh, create_rect_mesh  # noqa: E402
 from fem.integrators import NewmarkMethod, ThetaMethod, wave_energy  # noqa: E402
@@ -258,6 +258,71 @@ def adjoint_cases():
     np.savez_compressed(os.path.join(OUT, 'adjoint.npz'), **out)
 
 
+def _jitter(mesh, seed, amp):
+    """Interior vertices moved by a seeded random offset, so no two elements are congruent."""
+    rng = np.random.default_rng(seed)
+    v = mesh.vertices.copy()
+    interior = np.setdiff1d(np.arange(len(v)), mesh.boundary_idxs)
+    v[interior] += rng.uniform(-amp, amp, (len(interior), v.shape[1]))
+    return type(mesh)(v, mesh.elements, mesh.boundary)
+
+
+def fields_cases():
+    """LinearForm loads, DiffusionForm / GeometricStiffnessForm operators, nodal recovery and
+    LinearElasticForm.derived_fields on jittered P1-tri, P2-tri and P1-tet meshes
+    (ref fem/forms.py:273-441, fem/space.py:545-708)."""
+    out = {}
+    kappa = lambda p: [1.0 + p[0] ** 2 + 0.5 * p[1]]                                  # noqa: E731
+    cases = {
+        'tri': (_jitter(create_rect_mesh([[0, 0], [2, 1]], (6, 5)), 3, 0.04), None),
+        'p2tri': (_jitter(create_rect_mesh([[0, 0], [1.5, 1]], (5, 4)), 4, 0.04), QuadraticTriangleElement),
+        'tet': (_jitter(create_box_mesh([[0, 0, 0], [1, 2, 1.5]], (3, 4, 3)), 5, 0.05), None),
+    }
+    for name, (mesh, etype) in cases.items():
+        d = mesh.spatial_dim
+        rng = np.random.default_rng(11 + d + (etype is not None))
+        V1 = FunctionSpace(mesh, etype, n_components=1)
+        Vd = FunctionSpace(mesh, etype, n_components=d)
+        n_el = len(V1.element_nodes)
+        pre = {f'{name}_{k}': v for k, v in space_fields(V1).items()}
+        out.update(pre)
+        # loads: a scalar field (degree 2) and a vector field (the highest tabulated degree)
+        f1 = (lambda p: [np.sin(p[0]) + p[1] ** 2]) if d == 2 else (lambda p: [np.sin(p[0]) + p[1] * p[2]])
+        fd = (lambda p: [p[0] * p[1], 1.0 + p[0]]) if d == 2 else (lambda p: [p[0] * p[1], 1.0 + p[2], p[1] - p[0]])
+        hi = 4 if d == 2 else 2
+        out[f'{name}_load1'] = V1.assemble_load(LinearForm(f1, 1, 2))
+        out[f'{name}_loadd'] = Vd.assemble_load(LinearForm(fd, d, hi))
+        out[f'{name}_loadd_degree'] = hi
+        out[f'{name}_points2'] = V1.geometry_at(2).points
+        out[f'{name}_wdet2'] = V1.geometry_at(2).weight_detJ
+        # operators
+        out.update(csr_fields(f'{name}_diff', V1.assemble(DiffusionForm(kappa if d == 2 else (lambda p: [1.0 + p[0] ** 2 + 0.5 * p[2]])))))
+        sym = rng.normal(size=(n_el, d, d))
+        prestress = sym + np.transpose(sym, (0, 2, 1))
+        out[f'{name}_prestress'] = prestress
+        out.update(csr_fields(f'{name}_geom', Vd.assemble(GeometricStiffnessForm(prestress))))
+        # nodal recovery
+        vals = rng.normal(size=n_el)
+        tens = rng.normal(size=(n_el, 2, 2))
+        out[f'{name}_vals'], out[f'{name}_tens'] = vals, tens
+        out[f'{name}_avg'] = V1.recover_nodal(vals)
+        out[f'{name}_avg_tens'] = V1.recover_nodal(tens)
+        out[f'{name}_l2'] = V1.recover_nodal(vals, method='l2')
+        out[f'{name}_l2_tens'] = Vd.recover_nodal(tens, method='l2')
+        # derived fields of a random displacement, uniform and per-element modulus
+        u = rng.normal(size=Vd.n_dofs) * 0.01
+        out[f'{name}_u'] = u
+        ue = u.reshape(-1, d)[Vd.element_nodes]
+        E_var = np.linspace(50.0, 200.0, n_el)
+        out[f'{name}_E_var'] = E_var
+        for tag, E in (('uni', 200.0), ('var', E_var)):
+            fields = LinearElasticForm(LinearElasticMaterial(E, 0.3)).derived_fields(Vd.geometry, ue)
+            out[f'{name}_strain_{tag}'], out[f'{name}_stress_{tag}'] = fields.strain, fields.stress
+            out[f'{name}_compliance_{tag}'] = fields.compliance
+    np.savez_compressed(os.path.join(OUT, 'fields.npz'), **out)
+    print('fields cases written')
+
+
 if __name__ == '__main__':
     assembly_case('tri', create_rect_mesh([[0, 0], [2, 1]], (6, 5)))
     assembly_case('tet', create_box_mesh([[0, 0, 0], [1, 2, 1.5]], (3, 4, 3)))
@@ -266,3 +331,4 @@ if __name__ == '__main__':
     simp_case()
     transient_cases()
     adjoint_cases()
+    fields_cases()
