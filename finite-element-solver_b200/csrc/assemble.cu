@@ -342,6 +342,12 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
     issue_loc(0);
     issue_items(0);
   }
+  // Programmatic dependent launch: the next kernel of the stream may be scheduled as this grid's CTAs
+  // retire (its prologue -- barrier init and the first plan-stream copies above, which read only the
+  // immutable plan -- then overlaps this grid's tail); nothing a previous kernel may have written
+  // (coordinates, per-element coefficients, the CSR values) is touched before the wait below.
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
   mbar_wait(&bar_h[0], 0);
   mbar_wait(&bar_n[0], 0);
@@ -726,9 +732,21 @@ int launch_tiles(const Job& j) {
   static const bool no_tma = getenv("FES_NO_TMA_STORE") != nullptr;  // tuning knob: plain coalesced stores
   static const bool exp_nowait = getenv("FES_EXP_NOWAIT") != nullptr;  // timing experiment only: WRONG results
   const int use_tma = ((!no_tma && (reinterpret_cast<uintptr_t>(j.out) & 15) == 0) ? 1 : 0) | (exp_nowait ? 2 : 0);
-  k_assemble_tiles<ELEM, FORM, C, SD, kTileThreads><<<(unsigned)grid, kTileThreads, smem, j.stream>>>(
-      P->tile_hdr.p, (int)P->n_tiles, P->tile_elems.p, P->rec_local.p, P->tile_nodes.p, P->pair_meta.p,
-      P->pair_codes.p, j.coords, cf, dims, use_tma, j.out);
+  static const bool no_pdl = getenv("FES_NO_PDL") != nullptr;  // tuning knob
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)grid);
+  lc.blockDim = dim3(kTileThreads);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = j.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = no_pdl ? 0 : 1;
+  FES_CUDA(cudaLaunchKernelEx(&lc, k_assemble_tiles<ELEM, FORM, C, SD, kTileThreads>, (const int32_t*)P->tile_hdr.p,
+                              (int)P->n_tiles, (const uint32_t*)P->tile_elems.p, (const uint32_t*)P->rec_local.p,
+                              (const int32_t*)P->tile_nodes.p, (const uint32_t*)P->pair_meta.p,
+                              (const uint32_t*)P->pair_codes.p, (const double*)j.coords, cf, dims, use_tma, j.out));
   if (cf.sign < 0.0) {  // a negative global factor (ScaledForm): the kernel ran with |factor|
     FES_LAUNCH_CHECK();
     k_negate<<<grid_for(P->nnz, 256), 256, 0, j.stream>>>(j.out, P->nnz);
