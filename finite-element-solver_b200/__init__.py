@@ -18,7 +18,8 @@ from .materials import LinearElasticMaterial  # noqa: F401
 from .mesh import Mesh, create_box_mesh, create_rect_mesh  # noqa: F401
 from .integrators import NewmarkMethod, ThetaMethod, TransientSolution, WaveSolution, wave_energy  # noqa: F401
 from .problem import LinearProblem, heat, linear_elastic, poisson, projection, wave  # noqa: F401
-from .sensitivity import Compliance, DensityField, ModulusField, PointValue, SensitivityAnalysis  # noqa: F401
+from .sensitivity import (Compliance, DensityField, MeanStress, ModulusField, PointValue,  # noqa: F401
+                          SensitivityAnalysis, SoftMaxStress)
 from .space import FunctionSpace  # noqa: F401
 from .system import DiscreteSystem  # noqa: F401
 from .topology import TopologyOptimizer, calculate_smoothing_matrix  # noqa: F401

@@ -438,3 +438,77 @@ extern "C" int fes_elastic_fields(int elem_kind, const int32_t* en, int64_t n_el
   FES_LAUNCH_CHECK();
   return FES_OK;
 }
+
+// ---- von Mises stress and its derivative with respect to the element DOFs (plane strain) -------
+// ref fem/sensitivity.py:137-199 (_VonMisesStress._voigt_stress / _Q / _dvm_du): s = D B u_e at the
+// first quadrature point, sigma_zz = nu (s_xx + s_yy), vm = sqrt(Q), dvm/du_e = (D B)^T dQ/ds / (2 vm).
+namespace fes {
+namespace {
+template <int ELEM>
+__global__ void __launch_bounds__(kBlock)
+k_von_mises_gradient(const int32_t* __restrict__ en, int64_t n_el, const double* __restrict__ coords,
+                     const double* __restrict__ u, const double* __restrict__ d_E, double E, double nu, Rule rule,
+                     double* __restrict__ vm_out, double* __restrict__ dvm_du) {
+  constexpr int N = ET<ELEM>::N, SD = 2;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_el) return;
+  double X[3][SD];
+  load_corners<ELEM, SD>(en + e * N, coords, X);
+  Geom<2, SD> g;
+  make_geom<2, SD>(X, g);
+  double d[N][2];
+  dshape_at<ELEM>(rule.pts[0], d);
+  double gn[N][SD];
+  double exx = 0.0, eyy = 0.0, gxy = 0.0;  // Voigt strain (engineering shear)
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+#pragma unroll
+    for (int x = 0; x < SD; ++x) gn[n][x] = d[n][0] * g.Jinv[0][x] + d[n][1] * g.Jinv[1][x];
+    const int64_t v = en[e * N + n];
+    const double ux = __ldg(u + 2 * v), uy = __ldg(u + 2 * v + 1);
+    exx += gn[n][0] * ux;
+    eyy += gn[n][1] * uy;
+    gxy += gn[n][1] * ux + gn[n][0] * uy;
+  }
+  const Material m = lame(d_E ? __ldg(d_E + e) : E, nu);
+  const double sxx = (m.lam + 2.0 * m.mu) * exx + m.lam * eyy, syy = m.lam * exx + (m.lam + 2.0 * m.mu) * eyy,
+               sxy = m.mu * gxy, szz = nu * (sxx + syy);
+  const double Q = sxx * sxx + syy * syy + szz * szz - sxx * syy - syy * szz - szz * sxx + 3.0 * sxy * sxy;
+  const double vm = sqrt(fmax(Q, 0.0));
+  if (vm_out) vm_out[e] = vm;
+  if (!dvm_du) return;
+  double ds[3] = {0.0, 0.0, 0.0};
+  if (vm > 0.0) {
+    ds[0] = (2 * sxx - syy - szz + nu * (2 * szz - syy - sxx)) / (2.0 * vm);
+    ds[1] = (2 * syy - sxx - szz + nu * (2 * szz - sxx - syy)) / (2.0 * vm);
+    ds[2] = 6.0 * sxy / (2.0 * vm);
+  }
+  // (D B)^T ds: t = D ds (D symmetric), then B^T t
+  const double txx = (m.lam + 2.0 * m.mu) * ds[0] + m.lam * ds[1], tyy = m.lam * ds[0] + (m.lam + 2.0 * m.mu) * ds[1],
+               txy = m.mu * ds[2];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    dvm_du[(e * N + n) * 2 + 0] = gn[n][0] * txx + gn[n][1] * txy;
+    dvm_du[(e * N + n) * 2 + 1] = gn[n][1] * tyy + gn[n][0] * txy;
+  }
+}
+}  // namespace
+}  // namespace fes
+
+extern "C" int fes_von_mises_gradient(int elem_kind, const int32_t* en, int64_t n_el, const double* coords,
+                                      const double* d_u, const double* d_E, double E, double nu, int min_degree,
+                                      double* d_vm, double* d_dvm_du, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  Rule r;
+  FES_TRY(rule_for(elem_kind, min_degree, r));
+  if (n_el == 0) return FES_OK;
+  const int g = grid_for(n_el, kBlock);
+  if (elem_kind == FES_P1_TRI)
+    k_von_mises_gradient<FES_P1_TRI><<<g, kBlock, 0, st>>>(en, n_el, coords, d_u, d_E, E, nu, r, d_vm, d_dvm_du);
+  else if (elem_kind == FES_P2_TRI)
+    k_von_mises_gradient<FES_P2_TRI><<<g, kBlock, 0, st>>>(en, n_el, coords, d_u, d_E, E, nu, r, d_vm, d_dvm_du);
+  else
+    return set_error(FES_ERR_UNSUPPORTED, "stress quantities of interest are plane-strain 2D only (element kind %d)", elem_kind);
+  FES_LAUNCH_CHECK();
+  return FES_OK;
+}

@@ -200,38 +200,47 @@ __global__ void k_elastic_energy(const int32_t* __restrict__ en, int64_t n_el, c
   if (e >= n_el) return;
   Geom<ET<ELEM>::RD, SD> g;
   load_geom<ELEM, SD>(en + e * N, coords, g);
-  double H[SD][SD];  // displacement gradient du_i/dx_s at the first quadrature point
+  // u_e^T K0_e u_e = sum_q w_q (lam tr(eps_q)^2 + 2 mu eps_q:eps_q) over the element's stiffness rule (one
+  // point for P1, the three Strang points for P2; equal weights).  The per-element compliance and
+  // von Mises outputs are the reference's first-point quantities (ref fem/forms.py:335-374), so H, tr
+  // and ee of point 0 are kept.
+  constexpr int NQ = ET<ELEM>::NQ;
+  const double vol = g.scale * ref_measure(ET<ELEM>::RD);
+  double H[SD][SD], tr = 0.0, ee = 0.0, q = 0.0;
 #pragma unroll
-  for (int i = 0; i < SD; ++i)
+  for (int qp = NQ - 1; qp >= 0; --qp) {  // point 0 last: its H, tr, ee stay live for the outputs below
 #pragma unroll
-    for (int s = 0; s < SD; ++s) H[i][s] = 0.0;
+    for (int i = 0; i < SD; ++i)
 #pragma unroll
-  for (int a = 0; a < N; ++a) {
-    double ga[SD];
-    shape_grad<ELEM, SD>(g, 0, a, ga);
-    const int64_t v = en[e * N + a];
+      for (int s = 0; s < SD; ++s) H[i][s] = 0.0;
+#pragma unroll
+    for (int a = 0; a < N; ++a) {
+      double ga[SD];
+      shape_grad<ELEM, SD>(g, qp, a, ga);
+      const int64_t v = en[e * N + a];
+#pragma unroll
+      for (int i = 0; i < SD; ++i) {
+        const double ui = u[v * SD + i];
+#pragma unroll
+        for (int s = 0; s < SD; ++s) H[i][s] += ui * ga[s];
+      }
+    }
+    tr = 0.0; ee = 0.0;
 #pragma unroll
     for (int i = 0; i < SD; ++i) {
-      const double ui = u[v * SD + i];
+      tr += H[i][i];
 #pragma unroll
-      for (int s = 0; s < SD; ++s) H[i][s] += ui * ga[s];
+      for (int s = 0; s < SD; ++s) {
+        const double eps = 0.5 * (H[i][s] + H[s][i]);
+        ee += eps * eps;
+      }
     }
+    q += (vol / (double)NQ) * (lam0 * tr * tr + 2.0 * mu0 * ee);
   }
-  double tr = 0.0, ee = 0.0;
-#pragma unroll
-  for (int i = 0; i < SD; ++i) {
-    tr += H[i][i];
-#pragma unroll
-    for (int s = 0; s < SD; ++s) {
-      const double eps = 0.5 * (H[i][s] + H[s][i]);
-      ee += eps * eps;
-    }
-  }
-  const double vol = g.scale * ref_measure(ET<ELEM>::RD);
-  const double q = vol * (lam0 * tr * tr + 2.0 * mu0 * ee);  // u_e^T K0_e u_e
+  const double q0 = vol * (lam0 * tr * tr + 2.0 * mu0 * ee);  // sigma:eps * vol at the first point
   const double sc = scale ? scale[e] : 1.0;
   if (q_out) q_out[e] = q;
-  if (comp_out) comp_out[e] = sc * q;
+  if (comp_out) comp_out[e] = sc * q0;
   if (vm_out) {
     // sigma = sc (lam0 tr I + 2 mu0 eps), with sigma_zz = sc lam0 tr under plane strain
     const double mean = sc * (lam0 * tr + 2.0 * mu0 * tr / 3.0);  // tr(sigma)/3, eps_zz = 0 in 2D

@@ -55,6 +55,93 @@ class PointValue:
         return e
 
 
+# -- stress-based quantities of interest (plane strain; ref fem/sensitivity.py:108-276) --------
+class _VonMisesStress:
+    """Per-element von Mises stress and d(von Mises)/du_e from `fes_von_mises_gradient`; the adjoint
+    load is scattered with the reference's own summation order (`fes_node_scatter`)."""
+
+    def __init__(self, space, material, region=None):
+        if space.spatial_dim != 2 or space.n_components != 2:
+            raise NotImplementedError('stress quantities of interest handle the plane-strain 2D case only')
+        self.space, self.material = space, material
+        self.region = None if region is None else np.asarray(region, dtype=bool)
+
+    def evaluate(self, u, gradient=True):
+        sp, m = self.space, self.material
+        n_el, N = sp._en_d.shape
+        ud = _dev(u, sp.device).reshape(-1)
+        E_elem = None
+        if m.per_element():
+            E_elem = _dev(m.E, sp.device)
+            if E_elem.numel() != n_el:
+                raise ValueError(f'per-element modulus has {E_elem.numel()} entries but the mesh has {n_el} elements')
+        vm = torch.empty(n_el, dtype=torch.float64, device=sp.device)
+        dvm = torch.empty((n_el, N, 2), dtype=torch.float64, device=sp.device) if gradient else None
+        _lib.check(_lib.lib().fes_von_mises_gradient(
+            sp.element_type.KIND, _lib.ptr(sp._en_d), n_el, _lib.ptr(sp._coords_d), _lib.ptr(ud), _lib.ptr(E_elem),
+            0.0 if m.per_element() else float(m.E), float(m.nu), sp.element_type.default_quadrature_degree(),
+            _lib.ptr(vm), _lib.ptr(dvm), _lib.stream()))
+        return vm, dvm
+
+    def weights(self):
+        vol = self.space.element_volumes_d
+        if self.region is not None:
+            vol = torch.where(torch.as_tensor(self.region, device=vol.device), vol, torch.zeros_like(vol))
+        return vol / vol.sum()
+
+    def scatter(self, per_element):
+        return self.space.node_scatter(per_element, 2).reshape(-1)
+
+
+@dataclass(frozen=True, eq=False)
+class MeanStress:
+    """Volume-weighted mean von Mises stress over a region (ref fem/sensitivity.py:202-227)."""
+    space: object
+    material: object
+    region: object = None
+    self_adjoint: bool = False
+
+    def _stress(self):
+        return _VonMisesStress(self.space, self.material, self.region)
+
+    def value(self, problem, u):
+        s = self._stress()
+        return float(torch.dot(s.weights(), s.evaluate(u, gradient=False)[0]))
+
+    def dJ_du(self, problem, u):
+        s = self._stress()
+        _, dvm = s.evaluate(u)
+        return s.scatter(s.weights()[:, None, None] * dvm)
+
+
+@dataclass(frozen=True, eq=False)
+class SoftMaxStress:
+    """The volume-weighted p-norm of the von Mises stress, a smooth peak (ref fem/sensitivity.py:230-276)."""
+    space: object
+    material: object
+    region: object = None
+    p: float = 8.0
+    self_adjoint: bool = False
+
+    def _stress(self):
+        return _VonMisesStress(self.space, self.material, self.region)
+
+    def value(self, problem, u):
+        s = self._stress()
+        vm = s.evaluate(u, gradient=False)[0]
+        return float(torch.dot(s.weights(), vm ** self.p) ** (1.0 / self.p))
+
+    def dJ_du(self, problem, u):
+        s = self._stress()
+        w = s.weights()
+        vm, dvm = s.evaluate(u)
+        total = float(torch.dot(w, vm ** self.p))
+        if total <= 0.0:
+            return torch.zeros(self.space.n_dofs, dtype=torch.float64, device=self.space.device)
+        dJ_dvm = total ** (1.0 / self.p - 1.0) * w * vm ** (self.p - 1.0)
+        return s.scatter(dJ_dvm[:, None, None] * dvm)
+
+
 # -- parameterizations -------------------------------------------------------------------------
 class _ElementModulusParameterization:
     """Per-element scaling of a solid stiffness K0_e at modulus `_E0` (ref fem/sensitivity.py:288-309)."""

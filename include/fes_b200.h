@@ -194,8 +194,10 @@ void fes_filter_destroy(fes_filter* f);
 int64_t fes_filter_nnz(const fes_filter* f);
 int fes_filter_export_csr(const fes_filter* f, int64_t* h_indptr, int64_t* h_indices, double* h_data);
 int fes_filter_apply(const fes_filter* f, const double* d_in, double* d_out, void* stream);
-/* per element: q = u_e^T K0_e u_e (solid modulus E0), compliance = scale_e * q, optional
- * von Mises of the stress at modulus scale_e*E0 (NULL to skip).  d_scale = rho^p. */
+/* per element: q = u_e^T K0_e u_e (solid modulus E0; summed over the element's stiffness rule),
+ * compliance = scale_e * sigma:eps * volume and the von Mises stress at modulus scale_e*E0, both at
+ * the first quadrature point like LinearElasticForm.derived_fields (equal to scale_e * q for P1).
+ * Outputs may be NULL.  d_scale = rho^p. */
 int fes_elastic_energy(int elem_kind, const int32_t* d_elem_nodes, int64_t n_el, const double* d_coords,
                        const double* d_u, double E0, double nu, const double* d_scale,
                        double* d_q, double* d_compliance, double* d_von_mises, void* stream);
@@ -238,6 +240,13 @@ int fes_weighted_gradient_matrices(int elem_kind, int spatial_dim, int n_comp, i
 int fes_elastic_fields(int elem_kind, const int32_t* d_elem_nodes, int64_t n_el, const double* d_coords,
                        const double* d_u, const double* d_E, double E, double nu, int min_degree,
                        double* d_strain, double* d_stress, double* d_compliance, void* stream);
+/* _VonMisesStress (ref fem/sensitivity.py:137-199): per-element plane-strain von Mises stress at the first
+ * point of the rule and d(von Mises)/d(u_e), (n_el, nodes_per_elem, 2); either output may be NULL.
+ * Scatter the weighted derivative with fes_node_scatter to get the adjoint load of MeanStress /
+ * SoftMaxStress (ref fem/sensitivity.py:202-276). */
+int fes_von_mises_gradient(int elem_kind, const int32_t* d_elem_nodes, int64_t n_el, const double* d_coords,
+                           const double* d_u, const double* d_E, double E, double nu, int min_degree,
+                           double* d_von_mises, double* d_dvm_du, void* stream);
 
 #ifdef __cplusplus
 }

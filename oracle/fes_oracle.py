@@ -687,3 +687,46 @@ def recover_nodal_l2(elem_nodes, geo, values, n_nodes_total, mass, solve):
     load = node_scatter(elem_nodes, contrib, n_nodes_total)
     q = np.column_stack([solve(mass, load[:, j]) for j in range(load.shape[1])])
     return q.reshape((n_nodes_total,) + trailing)
+
+
+# --------------------------------------------------------------------------------------
+# stress quantities of interest, plane strain (ref: fem/sensitivity.py:108-276)
+# --------------------------------------------------------------------------------------
+def von_mises_gradient(geo, u, elem_nodes, E, nu):
+    """(vm (n_el,), dvm/du_e (n_el, N*2)) from the in-plane Voigt stress at the first quadrature point,
+    sigma_zz = nu (s_xx + s_yy) (ref: fem/sensitivity.py:151-189)."""
+    n_el = len(elem_nodes)
+    B = voigt_B(geo.grad[:, 0])
+    mu, lam = lame(np.broadcast_to(np.asarray(E, float), (n_el,)), nu)
+    D = mu[:, None, None] * hooke(2, 1.0, 0.0) + lam[:, None, None] * hooke(2, 0.0, 1.0)
+    DB = np.einsum('est,etk->esk', D, B)
+    s = np.einsum('esk,ek->es', DB, element_vectors(u, elem_nodes, 2))
+    sxx, syy, sxy = s[:, 0], s[:, 1], s[:, 2]
+    szz = nu * (sxx + syy)
+    Q = sxx ** 2 + syy ** 2 + szz ** 2 - sxx * syy - syy * szz - szz * sxx + 3.0 * sxy ** 2
+    vm = np.sqrt(np.maximum(Q, 0.0))
+    dQ = np.empty_like(s)
+    dQ[:, 0] = 2 * sxx - syy - szz + nu * (2 * szz - syy - sxx)
+    dQ[:, 1] = 2 * syy - sxx - szz + nu * (2 * szz - sxx - syy)
+    dQ[:, 2] = 6.0 * sxy
+    dvm_ds = np.zeros_like(s)
+    safe = vm > 0
+    dvm_ds[safe] = dQ[safe] / (2.0 * vm[safe, None])
+    return vm, np.einsum('esk,es->ek', DB, dvm_ds)
+
+
+def stress_qoi(geo, u, elem_nodes, n_nodes_total, E, nu, region=None, p=None):
+    """(value, dJ/du) of MeanStress (p None) or SoftMaxStress (p-norm) with volume weights over `region`
+    (ref: fem/sensitivity.py:191-276)."""
+    vm, dvm_du = von_mises_gradient(geo, u, elem_nodes, E, nu)
+    vol = geo.volumes
+    w = np.where(np.ones(len(vol), bool) if region is None else np.asarray(region), vol, 0.0)
+    w = w / w.sum()
+    N = np.asarray(elem_nodes).shape[1]
+    if p is None:
+        value, per_element = float(w @ vm), w[:, None] * dvm_du
+    else:
+        total = float(w @ vm ** p)
+        value = total ** (1.0 / p)
+        per_element = (total ** (1.0 / p - 1.0) * w * vm ** (p - 1.0))[:, None] * dvm_du
+    return value, node_scatter(elem_nodes, per_element.reshape(len(vol), N, 2), n_nodes_total).ravel()

@@ -22,7 +22,8 @@ ref_shim.install()
 
 from fem.boundary import BCType, BoundaryConditions  # noqa: E402
 from fem.design import DesignOptimizer, SIMPModel, optimality_criteria_update  # noqa: E402
-from fem.sensitivity import Compliance, DensityField, ModulusField, PointValue, SensitivityAnalysis  # noqa: E402
+from fem.sensitivity import (Compliance, DensityField, MeanStress, ModulusField, PointValue,  # noqa: E402
+                             SensitivityAnalysis, SoftMaxStress)
 from fem.elements import QuadraticTriangleElement  # noqa: E402
 from fem.equations import LinearElastic, Poisson  # noqa: E402
 from fem.forms import (DiffusionForm, GeometricStiffnessForm, LaplacianForm, LinearElasticForm,  # noqa: E402
@@ -258,6 +259,40 @@ def adjoint_cases():
     np.savez_compressed(os.path.join(OUT, 'adjoint.npz'), **out)
 
 
+def stress_qoi_cases():
+    """MeanStress / SoftMaxStress values, adjoint loads and density gradients on a jittered cantilever,
+    P1 and P2 (ref fem/sensitivity.py:108-276)."""
+    out = {}
+    for name, etype in (('p1', None), ('p2', QuadraticTriangleElement)):
+        mesh = _jitter(create_rect_mesh([[0, 0], [1, 1]], (9, 9) if etype is None else (6, 6)), 9, 0.02)
+        bc = BoundaryConditions()
+        bc.add(BCType.DIRICHLET, on_plane(0, 0.0), [0.0, 0.0])
+        bc.add(BCType.NEUMANN, on_plane(0, 1.0), [0.0, -1.0])
+        space = FunctionSpace(mesh, etype, n_components=2)
+        n_el = len(mesh.elements)
+        rho = 0.3 + 0.6 * (np.arange(n_el) % 7) / 6.0
+        E_el = 0.5 + (np.arange(n_el) % 5) / 4.0
+        nu, penalty = 0.3, 3.0
+        model = SIMPModel(space, base_E=1.0, nu=nu, bc=bc, penalty=penalty)
+        prob = model.problem(rho)
+        an = SensitivityAnalysis(prob)
+        u = an.solve_forward()
+        region = (np.arange(n_el) % 3 != 1)
+        mat_u, mat_v = LinearElasticMaterial(1.0, nu), LinearElasticMaterial(E_el, nu)
+        out.update({f'{name}_vertices': mesh.vertices, f'{name}_elements': mesh.elements, f'{name}_boundary': mesh.boundary,
+                    f'{name}_rho': rho, f'{name}_E_el': E_el, f'{name}_u': u, f'{name}_region': region})
+        for tag, qoi in (('mean', MeanStress(space, mat_u)), ('mean_region_var', MeanStress(space, mat_v, region)),
+                         ('soft', SoftMaxStress(space, mat_u, None, 8.0)),
+                         ('soft_region_var', SoftMaxStress(space, mat_v, region, 6.0))):
+            out[f'{name}_{tag}_value'] = qoi.value(prob, u)
+            out[f'{name}_{tag}_dJ_du'] = qoi.dJ_du(prob, u)
+            out[f'{name}_{tag}_grad'] = an.gradient(qoi, model.parameterization(rho), u)
+        out[f'{name}_vm_u'] = MeanStress(space, mat_u)._stress().von_mises(u)
+        out[f'{name}_vm_v'] = MeanStress(space, mat_v)._stress().von_mises(u)
+    np.savez_compressed(os.path.join(OUT, 'stress_qoi.npz'), **out)
+    print('stress qoi cases written')
+
+
 def _jitter(mesh, seed, amp):
     """Interior vertices moved by a seeded random offset, so no two elements are congruent."""
     rng = np.random.default_rng(seed)
@@ -332,3 +367,4 @@ if __name__ == '__main__':
     transient_cases()
     adjoint_cases()
     fields_cases()
+    stress_qoi_cases()
