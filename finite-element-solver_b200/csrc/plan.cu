@@ -363,7 +363,7 @@ __global__ void k_tile_emit(const int32_t* __restrict__ hdr, int64_t n_tiles, co
                             const int32_t* __restrict__ pair_row, const int32_t* __restrict__ node_adj,
                             const uint32_t* __restrict__ pair_start, const uint32_t* __restrict__ contrib,
                             const uint32_t* __restrict__ elems_sorted, const uint16_t* __restrict__ slot_of, int N, int c, int gs,
-                            int slot_mode, uint32_t L,
+                            int slot_mode, int by_degree, uint32_t L,
                             uint32_t* __restrict__ meta, uint32_t* __restrict__ codes, int* __restrict__ bad) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
@@ -382,12 +382,21 @@ __global__ void k_tile_emit(const int32_t* __restrict__ hdr, int64_t n_tiles, co
   for (int32_t v = v0; v < v1; ++v) max_deg = max(max_deg, node_ptr[v + 1] - node_ptr[v]);
   if (max_deg > 4095 || h[9] > 65535) { atomicExch(bad, 1); return; }
   int64_t wa = h[8];
+  // by_degree: within a class, nodes of equal degree go together (ascending degree), so neighbouring
+  // lanes hold the same relative neighbour of nodes with the SAME stencil (a criss-cross triangulation
+  // alternates 4- and 8-valent nodes).  Degrees above 63 share one bucket.
+  uint64_t deg_mask = by_degree ? 0ull : 1ull;
+  if (by_degree)
+    for (int32_t v = v0; v < v1; ++v) deg_mask |= 1ull << min(63, node_ptr[v + 1] - node_ptr[v]);
   while (hi > 0) {
     uint32_t next = 0;
+    for (uint64_t dm = deg_mask; dm; dm &= dm - 1) {
+    const int32_t dsel = __ffsll((long long)dm) - 1;
     for (int32_t sl = 0; sl < max_deg; ++sl)
       for (int32_t v = v0; v < v1; ++v) {
         const int32_t npv = node_ptr[v], degv = node_ptr[v + 1] - npv;
         if (sl >= degv) continue;
+        if (by_degree && min(63, degv) != dsel) continue;
         const int32_t p = npv + sl;
         const uint32_t k0 = pair_start[p], cnt = pair_start[p + 1] - k0;
         uint32_t lg, m;
@@ -418,6 +427,7 @@ __global__ void k_tile_emit(const int32_t* __restrict__ hdr, int64_t n_tiles, co
           next = max(next, key);
         }
       }
+    }
     hi = next;
   }
 }
@@ -563,7 +573,8 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
   FES_CUDA(P->pair_meta.alloc(items + 16));
   FES_CUDA(P->pair_codes.alloc(items * L + 32));
   k_tile_emit<<<grid_for(nt, 64), 64, 0, stream>>>(P->tile_hdr.p, nt, P->node_ptr.p, P->pair_row.p, P->node_adj.p,
-                                                   P->pair_start.p, P->contrib.p, P->elems_sorted.p, P->slot_of.p, N, c, P->geo_stride, P->slot_mode, L,
+                                                   P->pair_start.p, P->contrib.p, P->elems_sorted.p, P->slot_of.p, N, c, P->geo_stride, P->slot_mode,
+                                                   getenv("FES_ITEM_BY_DEGREE") ? atoi(getenv("FES_ITEM_BY_DEGREE")) : 0, L,
                                                    P->pair_meta.p, P->pair_codes.p, bad.p);
   FES_LAUNCH_CHECK();
   FES_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));

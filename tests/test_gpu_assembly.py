@@ -243,6 +243,39 @@ def test_full_size_cantilever_properties():
     close(Ke_g, Ke_o)
 
 
+def test_full_size_p2_properties():
+    """Config 3 of BASELINE.json (P2 elasticity + mass on 708^2 vertices, 999 698 six-node triangles): the
+    fused kernel (two inverse-Jacobian rows per record contracted with the per-node-pair table) against
+    size-independent properties -- rigid translations AND the rigid rotation (a linear field, exactly
+    representable in P2) in the null space, symmetry via x^T A y, the mass of the domain -- and against the
+    unfused element-matrix kernel and the oracle on a window of elements."""
+    F = fes()
+    mesh = F.create_rect_mesh([[0, 0], [1, 1]], (708, 708))
+    V = F.FunctionSpace(mesh, F.QuadraticTriangleElement, n_components=2)
+    form = F.LinearElasticForm(F.LinearElasticMaterial(200.0, 0.3))
+    A = V.assemble_device(form)
+    n = V.n_dofs
+    assert V._n_elements() == 999698 and A.nnz == 4 * V.plan().n_pairs
+    scale = float(A.data_d.abs().max())
+    X = torch.as_tensor(V.node_coords, device=A.device)
+    for t in (torch.stack([torch.ones_like(X[:, 0]), torch.zeros_like(X[:, 0])], 1),
+              torch.stack([torch.zeros_like(X[:, 0]), torch.ones_like(X[:, 0])], 1),
+              torch.stack([-X[:, 1], X[:, 0]], 1)):
+        assert float(A.matvec(t.reshape(-1).contiguous()).abs().max()) < 1e-9 * scale
+    gen = torch.Generator(device='cpu').manual_seed(1)
+    x = torch.rand(n, generator=gen, dtype=torch.float64).to(A.device)
+    y = torch.rand(n, generator=gen, dtype=torch.float64).to(A.device)
+    assert abs(float(x @ A.matvec(y)) - float(y @ A.matvec(x))) < 1e-9 * float(x @ A.matvec(x))
+    assert float(V.mass_matrix_d.data_d.sum()) == pytest.approx(2 * 1.0, rel=1e-12)
+    # fused assembly == deterministic scatter of the unfused element matrices (different kernels, same operator)
+    Ke = form.element_matrices(V)
+    B = V.assemble_device(F.PrecomputedForm(Ke))
+    assert float((A.data_d - B.data_d).abs().max()) < 1e-12 * scale
+    win = np.arange(500000, 502000)
+    geo = fo.geometry(fo.P2_TRI, V.node_coords[V.element_nodes[win]])
+    close(Ke[win].cpu().numpy(), fo.ke_elastic(geo, 200.0, 0.3))
+
+
 def test_full_size_tet_pattern_properties():
     """Config 5 scale check on one GPU at 101^3 nodes (6 M tets): pattern counts follow the closed
     form for a Kuhn mesh and the operator annihilates rigid translations."""
