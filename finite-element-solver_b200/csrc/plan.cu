@@ -354,8 +354,8 @@ __global__ void k_tile_hdr(const int32_t* __restrict__ tile_node0, int64_t n_til
 // are padded with the all-zero record, so the kernel's gather loop has no trip count at all).
 // A pair with more than L contributions is split over a power-of-two group of adjacent lanes (a
 // diagonal pair of a triangle mesh: 6-8 contributions over 4 lanes).  Order: descending group size
-// (keeps groups aligned), descending trips, then slot-in-row, then node -- so neighbouring threads
-// handle the SAME relative neighbour of consecutive nodes.  On a regularly numbered mesh their
+// (keeps groups aligned), descending trips, then node degree, slot-in-row, node -- so neighbouring threads
+// handle the SAME relative neighbour of consecutive nodes with the same stencil.  On a regularly numbered mesh their
 // record indices then form a constant-stride sequence, which the rec_slot swizzle spreads over all
 // banks (conflict-free gathers); on an irregular mesh any order is equally random.
 //   meta = q (16) | deg (12) | lg (3) | writer (1);  code = byte offset of g~_a | byte offset of g~_b << 16
@@ -481,12 +481,19 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
   std::vector<int32_t> tiles;
   tiles.push_back(0);
   int64_t v0 = 0;
+  // Runs whose length is a multiple of `node_mult` keep the lane groups of phase 2 (same relative neighbour of
+  // consecutive nodes) aligned to quarter- and half-warps.  Tets: 16-node runs gather at 1.18x / 1.31x of their
+  // conflict-free wavefronts, 17-node runs at 1.43x / 1.79x (tools/bank_sim.py model).
+  const int64_t node_mult = getenv("FES_TILE_NODE_MULT") ? atoi(getenv("FES_TILE_NODE_MULT")) : tile_node_multiple(N);
   for (int64_t v = 0; v < nn; ++v) {
     if (h_ne[v + 1] - h_ne[v] > inc_max || h_np[v + 1] - h_np[v] > pair_cap) return FES_OK;  // one node overflows a tile
     if (h_ne[v + 1] - h_ne[v0] > inc_max || h_np[v + 1] - h_np[v0] > pair_cap || v - v0 >= 255 ||
         (h_np[v + 1] - h_np[v0] > pair_soft && v > v0)) {
-      tiles.push_back((int32_t)v);
-      v0 = v;
+      int64_t cut = v;
+      if (node_mult > 1 && v - v0 > node_mult) cut = v0 + (v - v0) / node_mult * node_mult;
+      tiles.push_back((int32_t)cut);
+      v0 = cut;
+      v = cut - 1;  // re-scan from the cut
     }
   }
   tiles.push_back((int32_t)nn);
@@ -574,7 +581,7 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
   FES_CUDA(P->pair_codes.alloc(items * L + 32));
   k_tile_emit<<<grid_for(nt, 64), 64, 0, stream>>>(P->tile_hdr.p, nt, P->node_ptr.p, P->pair_row.p, P->node_adj.p,
                                                    P->pair_start.p, P->contrib.p, P->elems_sorted.p, P->slot_of.p, N, c, P->geo_stride, P->slot_mode,
-                                                   getenv("FES_ITEM_BY_DEGREE") ? atoi(getenv("FES_ITEM_BY_DEGREE")) : 0, L,
+                                                   getenv("FES_ITEM_BY_DEGREE") ? atoi(getenv("FES_ITEM_BY_DEGREE")) : 1, L,
                                                    P->pair_meta.p, P->pair_codes.p, bad.p);
   FES_LAUNCH_CHECK();
   FES_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));

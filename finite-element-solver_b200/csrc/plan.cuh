@@ -72,6 +72,9 @@ namespace fes {
 // Baked into the contribution codes at plan time; phase 1 of the kernel applies it when it writes.
 __host__ __device__ inline uint32_t rec_slot(uint32_t r, int mode) { return mode ? r : r ^ ((r >> 3) & 7u); }
 inline int tile_slot_mode(int N) { return N == 4 ? 2 : 0; }
+// preferred run length multiple of a tile (see build_tiles); measured: no effect on the B200 (tets 0.5695 ms with 16,
+// 0.5699 without -- the tet kernel is bound by fp64 / LDS latency at 12 warps per SM, not by the conflicts), so off
+inline int tile_node_multiple(int N) { (void)N; return 1; }
 
 // contributions one lane gathers at most (longer pairs are split over 2^lg lanes): about the count of
 // an interior off-diagonal pair of that element type
