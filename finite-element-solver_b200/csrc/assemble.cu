@@ -162,6 +162,9 @@ constexpr int tile_threads() {
   return FORM == FES_FORM_MASS ? 256 : 128;
 }
 template <int T> constexpr int rec_batch() { return T >= 256 ? 1 : 2; }  // records a thread evaluates per pass of phase 1 (memory-level parallelism)
+#ifndef FES_TET_CH
+#define FES_TET_CH 2  // contributions gathered per chunk on tets (loads issued before their FMAs)
+#endif
 constexpr int kHdrRing = 4, kNodRing = 3;
 __host__ __device__ constexpr int item_len_of(int N) { return (N == 3) ? 2 : (N == 4) ? 6 : 2; }  // = tile_item_len(N)
 constexpr int kHdrBytes = fes_plan::kHdrInts * 4;
@@ -473,7 +476,7 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
     // loads of a chunk are issued before its FMAs; a lane with fewer contributions reads the
     // all-zero record instead of branching (fma(0, 0, acc) == acc, bit for bit).
     constexpr int kItemLen = TS::L;
-    constexpr int CH = FORM == FES_FORM_MASS ? 1 : (R::kRows ? kItemLen : (NQ > 1 ? 1 : (SD == 3 ? 2 : kItemLen)));
+    constexpr int CH = FORM == FES_FORM_MASS ? 1 : (R::kRows ? kItemLen : (NQ > 1 ? 1 : (SD == 3 ? FES_TET_CH : kItemLen)));
     auto gather_chunk = [&](const uint32_t (&code)[CH], double (&acc)[C][C]) {
       if constexpr (FORM == FES_FORM_MASS) {
         const uint32_t ia = (code[0] & 0xffffu) >> 4, ib = code[0] >> 20;

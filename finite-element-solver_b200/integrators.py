@@ -7,27 +7,13 @@ sum is an axpy of two value arrays), the system goes through `DiscreteSystem` on
 is device work only: one SpMV for the right-hand side and one Jacobi-PCG solve warm-started from the
 previous state.  Histories are returned as host arrays like the reference's solutions.
 """
-from dataclasses import dataclass
-
 import numpy as np
 import torch
 
 from .system import DiscreteSystem
 
 
-@dataclass(frozen=True, eq=False)
-class TransientSolution:
-    """A time series: the times t and the field u at each step (ref fem/solution.py:266-269)."""
-    mesh: object
-    n_components: int
-    t: np.ndarray
-    u: list
-
-
-@dataclass(frozen=True, eq=False)
-class WaveSolution(TransientSolution):
-    """A time series that also carries du/dt at each step (ref fem/solution.py:272-275)."""
-    dudt: list = None
+from .solution import TransientSolution, WaveSolution  # noqa: E402,F401  (typed solutions live in solution.py)
 
 
 def _dev(x, device):

@@ -293,6 +293,26 @@ def stress_qoi_cases():
     print('stress qoi cases written')
 
 
+def io_cases():
+    """Files written by the reference's own fem.io (ref fem/io.py:52-147): a mesh JSON, an ElasticSolution
+    archive (P2, so the element type is stored) and a WaveSolution archive."""
+    from fem.io import save_mesh, save_solution
+    from fem.solution import ElasticSolution
+    mesh = _jitter(create_rect_mesh([[0, 0], [1.5, 1]], (4, 3)), 7, 0.03)
+    save_mesh(mesh, os.path.join(OUT, 'io_mesh.json'))
+    space = FunctionSpace(mesh, QuadraticTriangleElement, n_components=2)
+    u = np.random.default_rng(3).normal(size=space.n_dofs) * 0.01
+    sol = ElasticSolution.from_solve(space, u, LinearElasticForm(LinearElasticMaterial(200.0, 0.3)))
+    save_solution(sol, os.path.join(OUT, 'io_elastic_p2.npz'))
+    bc = BoundaryConditions()
+    bc.add(BCType.DIRICHLET, on_plane(0, 0.0), 0.0)
+    prob = wave(create_rect_mesh([[0, 0], [1, 1]], (4, 4)), 1.5, bc)
+    x = prob.space.node_coords
+    hist = NewmarkMethod(dt=0.05, steps=3).run(prob, np.sin(np.pi * x[:, 0]) * x[:, 1], np.zeros(len(x)))
+    save_solution(hist, os.path.join(OUT, 'io_wave.npz'))
+    print('io cases written')
+
+
 def _jitter(mesh, seed, amp):
     """Interior vertices moved by a seeded random offset, so no two elements are congruent."""
     rng = np.random.default_rng(seed)
@@ -368,3 +388,4 @@ if __name__ == '__main__':
     adjoint_cases()
     fields_cases()
     stress_qoi_cases()
+    io_cases()
