@@ -69,7 +69,7 @@ struct fes_solver {
   fes::DevBuf<double> own_data;
   fes::DevBuf<double> dinv, r, p, q, partials, hb, hx;
   fes::DevBuf<PcgState> state;
-  int lanes = 8, grid = 0, block = 0;
+  int lanes = 8, grid = 0, block = 0, grid_fused = -1;
   // block-row source layout: c = 1 means plain CSR rows (row_ptr = indptr, cols = indices)
   int c = 1;
   int64_t n_brow = 0;
@@ -101,7 +101,7 @@ struct PcgArgs {
   double* r;
   double* p;
   double* q;
-  double* partials;  // [4][kMaxGrid]
+  double* partials;  // [8][kMaxGrid]
   PcgState* state;
   double rtol;
   long long maxiter;
@@ -120,6 +120,7 @@ struct PcgArgs {
   const int32_t* send_src;           // local dof to read
   const int32_t* send_dst;           // dof index in the receiver's local numbering
   unsigned recv_mask, send_mask;     // bit r: this rank receives from / sends to rank r
+  int fused;                         // single-GPU: one reduction + two grid barriers per iteration (see k_pcg)
 };
 
 constexpr long long kSpinLimit = 40000000000LL;  // ~20 s of SM clocks: a lost peer traps instead of hanging
@@ -191,10 +192,11 @@ __device__ __forceinline__ bool is_free(const uint8_t* mask, int64_t i) { return
 
 // y = A vec on the free rows (0 on fixed rows); returns this thread's share of vec . y.
 // RESIDUAL writes b - A vec instead.  MASKED_X treats vec as zero on fixed dofs (warm start).
-template <int C, bool MASKED_X, bool RESIDUAL>
+template <int C, bool MASKED_X, bool RESIDUAL, bool DOTS = false>
 __device__ __forceinline__ double sparse_product(const PcgArgs& A, int64_t tid, int64_t nth, const double* vec,
-                                                 double* y) {
+                                                 double* y, double* dots = nullptr) {
   double partial = 0.0;
+  [[maybe_unused]] double d_rho = 0.0, d_s1 = 0.0, d_s2 = 0.0, d_rr = 0.0, d_t1 = 0.0, d_t2 = 0.0;
   for (int64_t slot = tid; slot < A.n_slots; slot += nth) {
     const int lane = (int)(slot & 31);
     const int64_t slice = slot >> 5;
@@ -236,19 +238,38 @@ __device__ __forceinline__ double sparse_product(const PcgArgs& A, int64_t tid, 
         const int64_t row = (int64_t)C * brow + i;
         if (RESIDUAL) y[row] = fr[i] ? A.b[row] - acc[i] : 0.0;
         else {
-          y[row] = fr[i] ? acc[i] : 0.0;
+          const double qi = fr[i] ? acc[i] : 0.0;
+          y[row] = qi;
           partial += fr[i] ? vec[row] * acc[i] : 0.0;
+          if constexpr (DOTS) {  // fixed rows carry r = dinv = 0
+            const double ri = A.r[row], di = A.dinv[row];
+            d_rho += di * ri * ri; d_s1 += di * ri * qi; d_s2 += di * qi * qi;
+            d_rr += ri * ri;       d_t1 += ri * qi;      d_t2 += qi * qi;
+          }
         }
       }
     }
   }
+  if constexpr (DOTS) {
+    dots[0] = d_rho; dots[1] = d_s1; dots[2] = d_s2; dots[3] = d_rr; dots[4] = d_t1; dots[5] = d_t2;
+  }
   return partial;
 }
 
-template <int C, bool DIST>
-__global__ void __launch_bounds__(kPcgBlock, (C == 3 || DIST) ? 2 : 3) k_pcg(PcgArgs A) {
+#ifndef FES_PCG_FUSED_BLOCKS
+#define FES_PCG_FUSED_BLOCKS 3
+#endif
+// FUSED (single GPU, FES_PCG_FUSED=1): one reduction and two grid barriers per iteration; its own
+// instantiation, so the register allocation of each loop is independent of the other's.  Measured on the
+// B200 (bench.py extras): config 2 179 us / iteration against 172 for the three-barrier loop, config 4
+// SIMP 1.49 against 1.68 design iterations / s, config 5 tets 1237 against 1031 us -- the six extra dot
+// products and the two extra vector reads inside the product phase cost the HBM-bound SpMV more than the
+// barrier and the reduction they remove, so the textbook loop stays the default.
+template <int C, bool DIST, bool FUSED>
+__global__ void __launch_bounds__(kPcgBlock, (C == 3 || DIST) ? 2 : (FUSED ? FES_PCG_FUSED_BLOCKS : 3)) k_pcg(PcgArgs A) {
+  static_assert(!(DIST && FUSED), "the fused loop is the single-GPU variant");
   cg::grid_group grid = cg::this_grid();
-  __shared__ double sm[3 * 33];
+  __shared__ double sm[7 * 33];
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
 
@@ -282,7 +303,7 @@ __global__ void __launch_bounds__(kPcgBlock, (C == 3 || DIST) ? 2 : 3) k_pcg(Pcg
     double ri = bi;
     if (A.warm) ri = A.r[i];  // the residual product already wrote 0 on fixed rows
     else { A.r[i] = bi; if (fr) A.x[i] = 0.0; }
-    A.p[i] = 0.0;
+    A.p[i] = FUSED ? A.dinv[i] * ri : 0.0;  // fused variant: p0 = z0 before the first product
     A.q[i] = 0.0;
     v3[0] += bi * bi;
     v3[1] += ri * ri;
@@ -299,6 +320,42 @@ __global__ void __launch_bounds__(kPcgBlock, (C == 3 || DIST) ? 2 : 3) k_pcg(Pcg
     for (int64_t i = lo + tid; i < hi; i += nth)
       if (is_free(A.mask, i)) A.x[i] = 0.0;
     rr = 0.0;
+  } else if constexpr (FUSED) {
+    // One reduction and two grid barriers per iteration.  The product phase also accumulates, over
+    // the rows it just produced,  rho = sum dinv r^2, s1 = sum dinv r q, s2 = sum dinv q^2 and the same
+    // three sums without dinv; then  alpha = rho / p.q  and the NEXT residual's norms follow without
+    // touching memory:  (r - alpha q)^T D (r - alpha q) = rho - 2 alpha s1 + alpha^2 s2, so beta is
+    // known before the vector phase, which does x += alpha p, r -= alpha q, p = D r + beta p in one
+    // pass.  rho is re-summed from the stored residual every iteration (no drift); only beta and the
+    // stopping test use the one-step prediction, whose cancellation error is eps * rho_k / rho_{k+1}.
+    for (;;) {
+      if (sqrt(rr) < A.rtol * sqrt(bb)) break;
+      if (it >= A.maxiter) { status = 1; break; }
+      long long c0 = clock64();
+      double v7[7];
+      v7[0] = sparse_product<C, false, false, true>(A, tid, nth, A.p, A.q, v7 + 1);
+      long long c1 = clock64(); cyc[2] += c1 - c0;
+      grid_sum<7>(grid, v7, A.partials, 0, sm);
+      c0 = clock64(); cyc[3] += c0 - c1;
+      const double pq = v7[0], rho_k = v7[1];
+      if (!(pq > 0.0)) { status = 2; break; }
+      const double alpha = rho_k / pq;
+      const double rho_next = fmax(fma(alpha, fma(alpha, v7[3], -2.0 * v7[2]), rho_k), 0.0);
+      const double rr_next = fmax(fma(alpha, fma(alpha, v7[6], -2.0 * v7[5]), v7[4]), 0.0);
+      const double beta = rho_next / rho_k;
+      for (int64_t i = lo + tid; i < hi; i += nth) {
+        const double pi = A.p[i];
+        if (pi != 0.0) A.x[i] = fma(alpha, pi, A.x[i]);  // fixed rows (p = 0) keep their prescribed value
+        const double ri = A.r[i] - alpha * A.q[i];
+        A.r[i] = ri;
+        A.p[i] = fma(beta, pi, A.dinv[i] * ri);
+      }
+      c1 = clock64(); cyc[4] += c1 - c0;
+      grid.sync();
+      cyc[0] += clock64() - c1;
+      rr = rr_next;
+      ++it;
+    }
   } else {
     for (;;) {
       if (sqrt(rr) < A.rtol * sqrt(bb)) break;
@@ -439,22 +496,31 @@ int pick_lanes(int64_t n, int64_t nnz) {
   return 32;
 }
 
-template <int C, bool DIST>
-int launch_pcg(fes_solver* s, PcgArgs& args, cudaStream_t st) {
-  if (s->grid == 0) {
+template <int C, bool DIST, bool FUSED>
+int launch_pcg_variant(fes_solver* s, PcgArgs& args, cudaStream_t st) {
+  if (s->grid == 0 || s->grid_fused != (FUSED ? 1 : 0)) {
+    s->grid_fused = FUSED ? 1 : 0;
     int dev = 0, sms = 0, per_sm = 0;
     FES_CUDA(cudaGetDevice(&dev));
     FES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    FES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<C, DIST>, kPcgBlock, 0));
+    FES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<C, DIST, FUSED>, kPcgBlock, 0));
     if (per_sm < 1) return set_error(FES_ERR_CUDA, "PCG kernel does not fit on an SM");
     s->grid = sms * per_sm;
     if (s->grid > kMaxGrid) s->grid = kMaxGrid;
     s->block = kPcgBlock;
   }
   void* params[] = {&args};
-  FES_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<C, DIST>, dim3(s->grid), dim3(s->block), params, 0, st));
+  FES_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<C, DIST, FUSED>, dim3(s->grid), dim3(s->block), params, 0, st));
   count_launch();
   return FES_OK;
+}
+
+template <int C, bool DIST>
+int launch_pcg(fes_solver* s, PcgArgs& args, cudaStream_t st) {
+  if constexpr (!DIST) {
+    if (args.fused) return launch_pcg_variant<C, false, true>(s, args, st);
+  }
+  return launch_pcg_variant<C, DIST, false>(s, args, st);
 }
 
 // SELL-32-sigma structure over block rows: the row order and slice offsets are computed on the
@@ -525,7 +591,7 @@ int init_solver(fes_solver* s, cudaStream_t st) {
   FES_CUDA(s->r.alloc(s->n));
   FES_CUDA(s->p.alloc(s->n));
   FES_CUDA(s->q.alloc(s->n));
-  FES_CUDA(s->partials.alloc(4 * kMaxGrid));
+  FES_CUDA(s->partials.alloc(8 * kMaxGrid));
   FES_CUDA(s->state.alloc(1));
   s->n_free = s->n;
   if (s->mask) {
@@ -747,7 +813,8 @@ extern "C" int fes_solver_solve(fes_solver* s, const double* d_b, double* d_x, d
             (long long)maxiter, warm_start ? 1 : 0, s->n_slices * 32, s->sell_row.p, s->sell_slice_ptr.p,
             s->sell_cols.p, s->sell_vals.p, s->row_begin, s->row_end, dist ? s->comm->world : 1,
             dist ? s->comm->rank : 0, dist ? s->comm->base : nullptr, dist ? s->comm->d_peer.p : nullptr,
-            s->send_ptr.p, s->send_src.p, s->send_dst.p, s->recv_mask, s->send_mask};
+            s->send_ptr.p, s->send_src.p, s->send_dst.p, s->recv_mask, s->send_mask,
+            getenv("FES_PCG_FUSED") ? 1 : 0};  // env: the single-reduction loop (A-B knob; measured slower, see k_pcg)
   if (dist) {
     if (s->c == 2) FES_TRY((launch_pcg<2, true>(s, a, st)));
     else if (s->c == 3) FES_TRY((launch_pcg<3, true>(s, a, st)));
