@@ -186,8 +186,13 @@ struct TileSmem {
   __host__ __device__ static size_t stage_bytes(int rmax) { return 2 * loc_bytes(rmax); }   // phase-1 streams (x2)
   __host__ __device__ static size_t item_bytes(int imax) { return meta_bytes(imax) + code_bytes(imax); }  // phase-2 streams (x1)
   __host__ __device__ static size_t nod_bytes(int nmax) { return up16((size_t)nmax * 4); }       // distinct-node ids
+  // The mass form's phase 1 is a handful of instructions, so a copy issued after phase 2 does not land under
+  // it: mass double-buffers the work-item streams (P2 vector mass 0.190 -> 0.178 ms).  The P2 gradient forms
+  // show the same wait (ncu: 10 % of the samples) but lose more to the CTA the second buffer costs
+  // (0.243 vs 0.238 ms), so they keep one buffer like the P1 forms.
+  static constexpr int kItemBufs = (FORM == FES_FORM_MASS) ? 2 : 1;
   __host__ __device__ static size_t total(int gs, int rmax, int pmax, int imax, int nmax) {
-    return rec_bytes(gs) + xyz_bytes(nmax) + out_bytes(pmax) + 2 * stage_bytes(rmax) + item_bytes(imax) + kNodRing * nod_bytes(nmax) +
+    return rec_bytes(gs) + xyz_bytes(nmax) + out_bytes(pmax) + 2 * stage_bytes(rmax) + kItemBufs * item_bytes(imax) + kNodRing * nod_bytes(nmax) +
            kHdrRing * up16(kHdrBytes);
   }
 };
@@ -208,8 +213,8 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
   constexpr int N = ET<ELEM>::N, NQ = ET<ELEM>::NQ, RD = ET<ELEM>::RD;
   constexpr int kRecBatch = rec_batch<kTileThreads>();
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bar_h[kHdrRing], bar_n[kNodRing], bar_s[2], bar_c;
-  __shared__ uint32_t s_skew[2], s_skew_c[2];
+  __shared__ __align__(8) uint64_t bar_h[kHdrRing], bar_n[kNodRing], bar_s[2], bar_c[2];
+  __shared__ uint32_t s_skew[2], s_skew_c[2][2];
   const int GS = dims.geo_stride;
   [[maybe_unused]] const uint32_t inv_gs = (uint32_t)(((1u << 24) + (uint32_t)GS - 1u) / (uint32_t)GS);  // a = (i * inv_gs) >> 24 for i = a * GS + slot
   // planes: v2[plane * GS + slot] (double2), then v1[plane * GS + slot] (double)
@@ -221,8 +226,10 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
   unsigned char* stage0 = sp;
   const size_t stage_sz = TS::stage_bytes(dims.rec_max);
   sp += 2 * stage_sz;
-  unsigned char* s_meta = sp;                                         sp += TS::meta_bytes(dims.item_max);
-  unsigned char* s_code = sp;                                         sp += TS::code_bytes(dims.item_max);
+  constexpr int kItemBufs = TS::kItemBufs;
+  unsigned char* items0 = sp;                                         sp += kItemBufs * TS::item_bytes(dims.item_max);
+  auto meta_of = [&](int k) { return items0 + (kItemBufs == 2 ? (k & 1) : 0) * TS::item_bytes(dims.item_max); };
+  auto code_of = [&](int k) { return meta_of(k) + TS::meta_bytes(dims.item_max); };
   unsigned char* nod0 = sp;                                           sp += kNodRing * TS::nod_bytes(dims.nod_max);
   unsigned char* hdr0 = sp;
   const bool per_elem = cf.d_E != nullptr || cf.d_scale != nullptr;
@@ -292,10 +299,12 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
     constexpr uint32_t L = (uint32_t)TS::L;
     const uint32_t i0 = (uint32_t)h2.x, ni = (uint32_t)h2.y;
     const uint32_t b_meta = win(i0, ni, 4), b_code = win(i0 * L, ni * L, 4);
-    mbar_arrive_expect_tx(&bar_c, b_meta + b_code);
+    const int ib = kItemBufs == 2 ? (k & 1) : 0;
+    uint64_t* bar = &bar_c[ib];
+    mbar_arrive_expect_tx(bar, b_meta + b_code);
     uint32_t t;
-    s_skew_c[1] = stage_window<4>(s_meta, pair_meta, i0, ni, &bar_c, t);
-    s_skew_c[0] = stage_window<4>(s_code, pair_codes, i0 * L, ni * L, &bar_c, t);
+    s_skew_c[ib][1] = stage_window<4>(meta_of(k), pair_meta, i0, ni, bar, t);
+    s_skew_c[ib][0] = stage_window<4>(code_of(k), pair_codes, i0 * L, ni * L, bar, t);
   };
 
   // coordinates of a tile's distinct nodes: global -> registers (<= 255 nodes: a node or two per
@@ -338,7 +347,8 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
     for (int i = 0; i < kNodRing; ++i) mbar_init(&bar_n[i], 1);
     mbar_init(&bar_s[0], 1);
     mbar_init(&bar_s[1], 1);
-    mbar_init(&bar_c, 1);
+    mbar_init(&bar_c[0], 1);
+    mbar_init(&bar_c[1], 1);
     for (int k = 0; k < 3 && k < n_my; ++k) issue_hdr(k);
     issue_nod(0);
     if (n_my > 1) issue_nod(1);
@@ -371,6 +381,12 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
     if (p_loc && has_next) {
       mbar_wait(&bar_h[(k + 1) & (kHdrRing - 1)], (uint32_t)((k + 1) >> 2) & 1u);  // its header: issued three tiles ago
       issue_loc(k + 1);
+    }
+    if constexpr (kItemBufs == 2) {  // the other buffer was last read in phase 2 of tile k-1
+      if (p_items && has_next) {
+        mbar_wait(&bar_h[(k + 1) & (kHdrRing - 1)], (uint32_t)((k + 1) >> 2) & 1u);
+        issue_items(k + 1);
+      }
     }
     const int4 h0 = hdr_of(k)[0], h2 = hdr_of(k)[2];
     const int32_t ne = h0.y, n_pairs = h0.w, n_items = h2.y;
@@ -466,9 +482,10 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
     }
 
     // ---- phase 2: one thread per work item (explicit shared addresses, bases in registers)
-    mbar_wait(&bar_c, (uint32_t)k & 1u);  // issued before phase 1 of this tile
-    const uint32_t code_b = smem_u32(s_code) + s_skew_c[0];
-    const uint32_t meta_b = smem_u32(s_meta) + s_skew_c[1];
+    const int ib = kItemBufs == 2 ? (k & 1) : 0;
+    mbar_wait(&bar_c[ib], (uint32_t)(kItemBufs == 2 ? (k >> 1) : k) & 1u);  // issued before phase 1 of this tile (a whole tile ago with two buffers)
+    const uint32_t code_b = smem_u32(code_of(k)) + s_skew_c[ib][0];
+    const uint32_t meta_b = smem_u32(meta_of(k)) + s_skew_c[ib][1];
     static_assert(TS::L % 2 == 0, "item codes are fetched two at a time");
     const uint32_t img_b = smem_u32(s_out) + 8u * (uint32_t)skew_d;
     // A chunk of CH contributions: S += g~_a (x) g~_b each.  A code holds the byte offsets of the two
@@ -634,7 +651,7 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
     double* img = s_out + skew_d;
     fence_proxy_async_smem();  // generic-proxy accesses (image writes, item reads) ordered before the async proxy's
     __syncthreads();           // phase 2 is over: the image is complete, the item buffer is free
-    if (p_items && has_next) issue_items(k + 1);
+    if (kItemBufs == 1 && p_items && has_next) issue_items(k + 1);
     if (use_tma_store & 1) {
       if (producer) {
         const int head = skew_d;                           // an odd first slot is 16-byte misaligned on both sides

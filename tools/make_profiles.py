@@ -16,6 +16,7 @@ run = lambda *a: subprocess.run([sys.executable, *a], capture_output=True, text=
 
 for tag, note in (('assemble_c2', 'k_assemble_tiles<P1_TRI,ELASTIC,2,2,128>, config 2 (inside bench.py --no-extra)'),
                   ('assemble_tet', 'k_assemble_tiles<P1_TET,ELASTIC,3,3,128>, 61^3 box (tools/profile_hotpath.py tet)'),
+                  ('assemble_p2', 'k_assemble_tiles<P2_TRI,ELASTIC,2,2,128>, config 3: 708^2 vertices, 999 698 six-node triangles (tools/profile_hotpath.py p2)'),
                   ('pcg_c2', 'k_pcg<2>, config 2, 40 iterations (tools/profile_hotpath.py all)')):
     rep = os.path.join(G, f'{R}_{tag}.ncu-rep')
     if not os.path.exists(rep):

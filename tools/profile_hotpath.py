@@ -1,5 +1,5 @@
 """Small driver for ncu: a few fused assemblies (config 2 triangles, a 61^3 tet box) and a
-short PCG run, so each kernel of interest appears a handful of times."""
+short PCG run, so each kernel of interest appears a handful of times (`p2`: config 3, P2 elasticity)."""
 import os
 import sys
 
@@ -32,6 +32,13 @@ if what == 'trimass':
     V = F.FunctionSpace(mesh, n_components=2)
     for _ in range(4):
         A = V.assemble_device(F.MassForm(2))
+    torch.cuda.synchronize()
+if what == 'p2':
+    mesh = F.create_rect_mesh([[0, 0], [1, 1]], (708, 708))
+    V = F.FunctionSpace(mesh, F.QuadraticTriangleElement, n_components=2)
+    form = F.LinearElasticForm(F.LinearElasticMaterial(200.0, 0.3))
+    for _ in range(4):
+        A = V.assemble_device(form)
     torch.cuda.synchronize()
 if what in ('all', 'tet'):
     mesh = F.create_box_mesh([[0, 0, 0], [1, 1, 1]], (61, 61, 61))

@@ -16,6 +16,9 @@ ncu --set full --clock-control none --import-source on -k regex:k_assemble_tiles
 python tools/profile_hotpath.py tet > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:k_assemble_tiles -s 2 -c 1 -o $O/${R}_assemble_tet \
     python tools/profile_hotpath.py tet > $O/${R}_ncu_tet.log 2>&1
+python tools/profile_hotpath.py p2 > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:k_assemble_tiles -s 2 -c 1 -o $O/${R}_assemble_p2 \
+    python tools/profile_hotpath.py p2 > $O/${R}_ncu_p2.log 2>&1
 python tools/profile_hotpath.py all > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:k_pcg -c 1 -o $O/${R}_pcg_c2 \
     python tools/profile_hotpath.py all > $O/${R}_ncu_pcg.log 2>&1
