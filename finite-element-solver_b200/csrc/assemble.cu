@@ -573,6 +573,51 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
         }
       }
     };
+    // Items with several chunks (tets: 6 contributions in chunks of 2): software pipeline -- the gathers of
+    // chunk c+1 are issued before the FMAs of chunk c, so a warp's own loads overlap its arithmetic (the tet
+    // kernel runs 12 warps per SM; ncu showed it stalled on the LDS -> DFMA dependency, not on bandwidth).
+    constexpr bool kPipelined = FORM != FES_FORM_MASS && !R::kRows && NQ == 1 && (kItemLen / CH) > 1;
+    struct Operands {
+      double2 ta[CH], tb[CH];
+      double za[CH], zb[CH];
+    };
+    [[maybe_unused]] auto load_ops = [&](const uint32_t (&code)[CH], Operands& o) {
+      bool same = true;
+#pragma unroll
+      for (int x = 0; x < CH; ++x) same = same && ((code[x] ^ (code[x] >> 16)) & 0xffffu) == 0u;
+      same = __all_sync(0xffffffffu, same);
+#pragma unroll
+      for (int x = 0; x < CH; ++x) {
+        const uint32_t oa = code[x] & 0xffffu, ob = code[x] >> 16;
+        o.ta[x] = lds_f64x2(v2_b + oa);
+        if constexpr (SD & 1) o.za[x] = lds_f64(v1_b + (oa >> 1));
+        if (!same) {
+          o.tb[x] = lds_f64x2(v2_b + ob);
+          if constexpr (SD & 1) o.zb[x] = lds_f64(v1_b + (ob >> 1));
+        } else {
+          o.tb[x] = o.ta[x];
+          if constexpr (SD & 1) o.zb[x] = o.za[x];
+        }
+      }
+    };
+    [[maybe_unused]] auto fma_ops = [&](const Operands& o, double (&acc)[C][C]) {
+#pragma unroll
+      for (int x = 0; x < CH; ++x) {
+        double A_[SD], B_[SD];
+        A_[0] = o.ta[x].x; A_[1] = o.ta[x].y;
+        B_[0] = o.tb[x].x; B_[1] = o.tb[x].y;
+        if constexpr (SD & 1) { A_[SD - 1] = o.za[x]; B_[SD - 1] = o.zb[x]; }
+        if constexpr (FORM == FES_FORM_LAPLACIAN) {
+#pragma unroll
+          for (int s_ = 0; s_ < SD; ++s_) acc[0][0] = fma(A_[s_], B_[s_], acc[0][0]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < C; ++i)
+#pragma unroll
+            for (int j = 0; j < C; ++j) acc[i][j] = fma(A_[i], B_[j], acc[i][j]);
+        }
+      }
+    };
     for (int t0 = 0; t0 < n_items; t0 += kTileThreads) {  // warp-uniform trip count: the shuffles need every lane
       const int t = t0 + (int)threadIdx.x;
       const bool live = t < n_items;
@@ -589,13 +634,35 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
       for (int i = 0; i < C; ++i)
 #pragma unroll
         for (int j = 0; j < C; ++j) acc[i][j] = 0.0;
-#pragma unroll
-      for (int c0_ = 0; c0_ < kItemLen; c0_ += CH) {
+      if constexpr (kPipelined) {
+        constexpr int NC = kItemLen / CH;
+        Operands cur, nxt;
         uint32_t part[CH];
 #pragma unroll
-        for (int x = 0; x < CH; ++x) part[x] = cd[c0_ + x];
-        // later chunks are padding for every lane of most warps (items are sorted by trips)
-        if (c0_ == 0 || __any_sync(0xffffffffu, part[0] != zero_code)) gather_chunk(part, acc);
+        for (int x = 0; x < CH; ++x) part[x] = cd[x];
+        load_ops(part, cur);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          bool more = false;
+          if (c + 1 < NC) {  // later chunks are padding for every lane of most warps (items are sorted by trips)
+#pragma unroll
+            for (int x = 0; x < CH; ++x) part[x] = cd[(c + 1) * CH + x];
+            more = __any_sync(0xffffffffu, part[0] != zero_code);
+            if (more) load_ops(part, nxt);
+          }
+          fma_ops(cur, acc);
+          if (!more) break;
+          cur = nxt;
+        }
+      } else {
+#pragma unroll
+        for (int c0_ = 0; c0_ < kItemLen; c0_ += CH) {
+          uint32_t part[CH];
+#pragma unroll
+          for (int x = 0; x < CH; ++x) part[x] = cd[c0_ + x];
+          // later chunks are padding for every lane of most warps (items are sorted by trips)
+          if (c0_ == 0 || __any_sync(0xffffffffu, part[0] != zero_code)) gather_chunk(part, acc);
+        }
       }
       // lanes that share a pair: fixed xor tree over the 2^lg adjacent lanes (both partners add, so
       // every lane of the group ends with the same bits)
