@@ -470,7 +470,7 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
         }
       }
     }
-    if (producer && !(use_tma_store & 2)) bulk_wait_read_all();  // the previous tile's store has finished reading the image
+    if (producer) bulk_wait_read_all();  // the previous tile's store has finished reading the image (measured: never the critical path)
     __syncthreads();                     // records visible, image free, coordinates consumed
 
     int nd_next = 0;
@@ -719,7 +719,7 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
     fence_proxy_async_smem();  // generic-proxy accesses (image writes, item reads) ordered before the async proxy's
     __syncthreads();           // phase 2 is over: the image is complete, the item buffer is free
     if (kItemBufs == 1 && p_items && has_next) issue_items(k + 1);
-    if (use_tma_store & 1) {
+    if (use_tma_store) {
       if (producer) {
         const int head = skew_d;                           // an odd first slot is 16-byte misaligned on both sides
         const int body = (n_out - head) & ~1, tail = n_out - head - body;
@@ -817,8 +817,7 @@ int launch_tiles(const Job& j) {
   if (FORM != FES_FORM_MASS && cf.factor < 0.0) { cf.factor = -cf.factor; cf.sign = -1.0; }
   const int64_t grid = std::min<int64_t>(P->n_tiles, (int64_t)sms * per_sm);  // persistent CTAs
   static const bool no_tma = getenv("FES_NO_TMA_STORE") != nullptr;  // tuning knob: plain coalesced stores
-  static const bool exp_nowait = getenv("FES_EXP_NOWAIT") != nullptr;  // timing experiment only: WRONG results
-  const int use_tma = ((!no_tma && (reinterpret_cast<uintptr_t>(j.out) & 15) == 0) ? 1 : 0) | (exp_nowait ? 2 : 0);
+  const int use_tma = (!no_tma && (reinterpret_cast<uintptr_t>(j.out) & 15) == 0) ? 1 : 0;
   static const bool no_pdl = getenv("FES_NO_PDL") != nullptr;  // tuning knob
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)grid);
