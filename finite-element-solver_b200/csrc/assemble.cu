@@ -154,7 +154,7 @@ struct RecLayout {
   static constexpr int DOUBLES = 2 * NV2 + NV1;
 };
 
-// CTA size, measured (tools/tune_tiles.sh): 4 warps per CTA and more CTAs per SM win for the gradient
+// CTA size, measured (tools/exp_sweep.sh): 4 warps per CTA and more CTAs per SM win for the gradient
 // forms; the mass form (hardly any arithmetic) prefers 8 warps.  The environment variable
 // FES_TILE_THREADS (128 / 256) overrides both at run time.
 template <int FORM>
