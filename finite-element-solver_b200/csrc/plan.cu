@@ -5,19 +5,17 @@
 // smaller NODE-level key set and the scalar pattern is expanded afterwards, which
 // yields the identical indptr/indices:
 //   1. key[e,a,b] = node[e,a] * n_nodes + node[e,b],  payload = e*N^2 + a*N + b
-//   2. stable LSD radix sort by key  -> equal keys keep ascending (e,a,b) order, i.e. the
+//   2. stable LSD radix sort by key (sortscan.cuh) -> equal keys keep ascending (e,a,b) order, i.e. the
 //      order np.bincount adds an element's contribution to a slot
 //   3. head flags + inclusive scan    -> pair ids, pair_start offsets, node adjacency
 //   4. per-node degree scan           -> node_ptr;  expansion by n_comp -> indptr / indices
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-
 #include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
 
 #include "plan.cuh"
+#include "sortscan.cuh"
 
 namespace fes {
 namespace {
@@ -457,12 +455,7 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
   k_diag_counts<<<grid_for(np_, kBlock), kBlock, 0, stream>>>(P->pair_row.p, P->node_adj.p, P->pair_start.p, np_, ne_cnt.p);
   FES_LAUNCH_CHECK();
   FES_CUDA(P->ne_ptr.alloc(nn + 1));
-  size_t tb = 0;
-  FES_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, ne_cnt.p, P->ne_ptr.p, nn + 1, stream));
-  DevBuf<uint8_t> tmp;
-  FES_CUDA(tmp.alloc(tb));
-  FES_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, ne_cnt.p, P->ne_ptr.p, nn + 1, stream));
-  count_launch(2);
+  FES_TRY((device_scan<int32_t, false>(ne_cnt.p, P->ne_ptr.p, nn + 1, stream)));
   std::vector<int32_t> h_ne(nn + 1), h_np(nn + 1);
   FES_CUDA(cudaMemcpyAsync(h_ne.data(), P->ne_ptr.p, (nn + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   FES_CUDA(cudaMemcpyAsync(h_np.data(), P->node_ptr.p, (nn + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
@@ -651,21 +644,19 @@ extern "C" int fes_plan_create(const int32_t* d_elem_nodes, int64_t n_el, int N,
 
   // stable LSD radix sort over just the significant key bits
   const int end_bit = bits_for((uint64_t)n_nodes * (uint64_t)n_nodes - 1);
-  size_t tmp_bytes = 0;
-  FES_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a.p, keys_b.p, vals_a.p, P->contrib.p, M, 0, end_bit, stream));
-  size_t scan_tmp = 0;
-  FES_CUDA(cub::DeviceScan::InclusiveSum(nullptr, scan_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, M, stream));
-  DevBuf<uint8_t> tmp;
-  FES_CUDA(tmp.alloc(tmp_bytes > scan_tmp ? tmp_bytes : scan_tmp));
-  FES_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_a.p, keys_b.p, vals_a.p, P->contrib.p, M, 0, end_bit, stream));
-  count_launch(2 * ((end_bit + 7) / 8));
+  bool in_b = false;
+  FES_TRY(radix_sort_pairs<uint64_t>(keys_a.p, keys_b.p, vals_a.p, P->contrib.p, M, end_bit, stream, &in_b));
+  if (!in_b) {  // an even number of passes left the result in the a buffers
+    FES_CUDA(cudaMemcpyAsync(keys_b.p, keys_a.p, keys_a.bytes(), cudaMemcpyDeviceToDevice, stream));
+    FES_CUDA(cudaMemcpyAsync(P->contrib.p, vals_a.p, vals_a.bytes(), cudaMemcpyDeviceToDevice, stream));
+    FES_CUDA(cudaStreamSynchronize(stream));
+  }
   keys_a.release(); vals_a.release();
 
   FES_CUDA(scan.alloc(M));
   k_head_flags<<<grid_for(M, kBlock), kBlock, 0, stream>>>(keys_b.p, M, scan.p);
   FES_LAUNCH_CHECK();
-  FES_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, scan_tmp, scan.p, scan.p, M, stream));
-  count_launch(2);
+  FES_TRY((device_scan<uint32_t, true>(scan.p, scan.p, M, stream)));
   uint32_t n_pairs = 0;
   FES_CUDA(cudaMemcpyAsync(&n_pairs, scan.p + (M - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
   FES_CUDA(cudaStreamSynchronize(stream));
@@ -686,11 +677,7 @@ extern "C" int fes_plan_create(const int32_t* d_elem_nodes, int64_t n_el, int N,
   const uint32_t M32 = (uint32_t)M;
   FES_CUDA(cudaMemcpyAsync(P->pair_start.p + n_pairs, &M32, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
 
-  size_t scan2 = 0;
-  FES_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan2, degree.p, P->node_ptr.p, n_nodes + 1, stream));
-  if (scan2 > tmp.bytes()) FES_CUDA(tmp.alloc(scan2));
-  FES_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, scan2, degree.p, P->node_ptr.p, n_nodes + 1, stream));
-  count_launch(2);
+  FES_TRY((device_scan<int32_t, false>(degree.p, P->node_ptr.p, n_nodes + 1, stream)));
 
   FES_CUDA(P->indices.alloc(P->nnz));
   k_expand_indptr<<<grid_for(n_nodes + 1, kBlock), kBlock, 0, stream>>>(P->node_ptr.p, n_nodes, n_comp, P->indptr.p);

@@ -5,11 +5,10 @@
 // DensityField.gradient (ref fem/sensitivity.py:41-49,305-309,346-348),
 // LinearElasticForm.derived_fields (ref fem/forms.py:335-374) + von_mises
 // (ref fem/invariants.py:48-62) and optimality_criteria_update (ref fem/design.py:39-78).
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 
 #include "elements.cuh"
 #include "gridsum.cuh"
+#include "sortscan.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -370,13 +369,16 @@ extern "C" int fes_filter_create(const int32_t* d_elem_nodes, int64_t n_el, int 
   FES_CUDA(cudaMemsetAsync(counts.p, 0, counts.bytes(), st));
   k_cell_keys<<<grid_for(n_el, kBlock), kBlock, 0, st>>>(g, ctr.p, n_el, keys_a.p, ids_a.p);
   FES_LAUNCH_CHECK();
-  size_t t1 = 0, t2 = 0;
-  FES_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, keys_a.p, keys_b.p, ids_a.p, ids_b.p, n_el, 0, 32, st));
-  FES_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t2, counts.p, counts.p, n_el + 1, st));
-  DevBuf<uint8_t> tmp;
-  FES_CUDA(tmp.alloc(t1 > t2 ? t1 : t2));
-  FES_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, t1, keys_a.p, keys_b.p, ids_a.p, ids_b.p, n_el, 0, 32, st));
-  count_launch(8);
+  {
+    int key_bits = 1;  // cell ids are < n_cells
+    while (key_bits < 32 && ((uint64_t)n_cells >> key_bits) != 0) ++key_bits;
+    bool in_b = false;
+    FES_TRY(radix_sort_pairs<uint32_t>(keys_a.p, keys_b.p, ids_a.p, ids_b.p, n_el, key_bits, st, &in_b));
+    if (!in_b) {
+      FES_CUDA(cudaMemcpyAsync(keys_b.p, keys_a.p, keys_a.bytes(), cudaMemcpyDeviceToDevice, st));
+      FES_CUDA(cudaMemcpyAsync(ids_b.p, ids_a.p, ids_a.bytes(), cudaMemcpyDeviceToDevice, st));
+    }
+  }
   k_cell_starts<<<grid_for(n_cells + 1, kBlock), kBlock, 0, st>>>(keys_b.p, n_el, n_cells, cell_start.p);
   FES_LAUNCH_CHECK();
 
@@ -386,8 +388,7 @@ extern "C" int fes_filter_create(const int32_t* d_elem_nodes, int64_t n_el, int 
                                                                   counts.p, F->indptr.p, F->indices.p, F->data.p)
   if (dim == 2) FES_ROWS(2, 0); else FES_ROWS(3, 0);
   FES_LAUNCH_CHECK();
-  FES_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, t2, counts.p, F->indptr.p, n_el + 1, st));
-  count_launch(2);
+  FES_TRY((device_scan<int32_t, false>(counts.p, F->indptr.p, n_el + 1, st)));
   int32_t nnz = 0;
   FES_CUDA(cudaMemcpyAsync(&nnz, F->indptr.p + n_el, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   FES_CUDA(cudaStreamSynchronize(st));
