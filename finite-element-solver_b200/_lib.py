@@ -41,6 +41,8 @@ SIGNATURES = {
     'fes_plan_indptr': (_p, [_p]),
     'fes_plan_indices': (_p, [_p]),
     'fes_plan_export_csr': (_int, [_p, _p, _p]),
+    'fes_sort_pairs_u64': (_int, [_p, _p, _i64, _int, _p]),
+    'fes_exclusive_scan_i32': (_int, [_p, _p, _i64, _p]),
     'fes_element_matrices': (_int, [_int, _int, _int, _int, _p, _i64, _p, C.POINTER(Coeffs), _p, _p]),
     'fes_element_volumes': (_int, [_int, _int, _p, _i64, _p, _p, _p]),
     'fes_assemble': (_int, [_p, _int, _int, _int, _p, _p, C.POINTER(Coeffs), _p, _p]),

@@ -705,6 +705,32 @@ extern "C" int fes_plan_create(const int32_t* d_elem_nodes, int64_t n_el, int N,
   return FES_OK;
 }
 
+// The builder's two primitives, exposed so the tests can check them against numpy directly
+// (np.argsort(kind='stable') / np.cumsum) at awkward sizes and key distributions.
+extern "C" int fes_sort_pairs_u64(uint64_t* d_keys, uint32_t* d_vals, int64_t n, int end_bit, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (n < 0 || n >= ((int64_t)1 << 32) || end_bit < 1 || end_bit > 64)
+    return set_error(FES_ERR_VALUE, "fes_sort_pairs_u64: bad arguments n=%lld end_bit=%d", (long long)n, end_bit);
+  if (n == 0) return FES_OK;
+  DevBuf<uint64_t> kb;
+  DevBuf<uint32_t> vb;
+  FES_CUDA(kb.alloc(n));
+  FES_CUDA(vb.alloc(n));
+  bool in_b = false;
+  FES_TRY(radix_sort_pairs<uint64_t>(d_keys, kb.p, d_vals, vb.p, n, end_bit, st, &in_b));
+  if (in_b) {
+    FES_CUDA(cudaMemcpyAsync(d_keys, kb.p, kb.bytes(), cudaMemcpyDeviceToDevice, st));
+    FES_CUDA(cudaMemcpyAsync(d_vals, vb.p, vb.bytes(), cudaMemcpyDeviceToDevice, st));
+  }
+  FES_CUDA(cudaStreamSynchronize(st));
+  return FES_OK;
+}
+
+extern "C" int fes_exclusive_scan_i32(const int32_t* d_in, int32_t* d_out, int64_t n, void* stream_) {
+  if (n < 0) return set_error(FES_ERR_VALUE, "fes_exclusive_scan_i32: n < 0");
+  return device_scan<int32_t, false>(d_in, d_out, n, (cudaStream_t)stream_);
+}
+
 extern "C" void fes_plan_destroy(fes_plan* plan) { delete plan; }
 extern "C" int64_t fes_plan_n_dofs(const fes_plan* p) { return p ? p->n_dofs : 0; }
 extern "C" int64_t fes_plan_nnz(const fes_plan* p) { return p ? p->nnz : 0; }

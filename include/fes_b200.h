@@ -90,6 +90,11 @@ const int32_t* fes_plan_indptr(const fes_plan* plan);  /* device, n_dofs+1      
 const int32_t* fes_plan_indices(const fes_plan* plan); /* device, nnz                              */
 /* host export as int64, the dtypes scipy's csr_array holds in the reference */
 int fes_plan_export_csr(const fes_plan* plan, int64_t* h_indptr, int64_t* h_indices);
+/* The builder's primitives (hand-written, csrc/sortscan.cuh), exposed for direct tests: a stable LSD radix
+ * sort of (uint64 key, uint32 value) pairs over the low end_bit key bits, in place -- np.argsort(kind='stable')
+ * of ref fem/space.py:113 -- and an exclusive prefix sum (np.cumsum of ref fem/space.py:126), d_out may alias d_in. */
+int fes_sort_pairs_u64(uint64_t* d_keys, uint32_t* d_vals, int64_t n, int end_bit, void* stream);
+int fes_exclusive_scan_i32(const int32_t* d_in, int32_t* d_out, int64_t n, void* stream);
 
 /* ---- element matrices (unfused) ----------------------------------------------------------
  * Replaces Form.element_matrices(geometry) (ref fem/forms.py:202-209,245-247,254-258,323-333)
