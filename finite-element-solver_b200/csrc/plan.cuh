@@ -92,7 +92,7 @@ inline int tile_inc_budget(int N) {
   switch (N) {
     case 2: return 256;
     case 3: return 336;    // P1 triangle (6 doubles per element record) or P2 line: 5 CTAs per SM (measured; 384 -> 4 CTAs)
-    case 4: return 400;    // P1 tet (12 doubles per element record): 3 CTAs per SM (measured: 512 -> 2 CTAs, 7 % slower)
+    case 4: return 384;    // P1 tet (12 doubles per element record): 16 interior nodes per tile, 3 CTAs per SM (measured: 400 +1 %, 416 -> 2 CTAs +30 %)
     default: return 192;   // P2 triangle (row records: 4 doubles per element); measured 96..256, flat above 128
   }
 }
