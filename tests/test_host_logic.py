@@ -145,6 +145,16 @@ def test_product_path_never_touches_the_oracle():
                 assert 'fes_oracle' not in text and 'ref_shim' not in text, f
 
 
+def test_kernels_are_hand_written_no_library_device_code():
+    """The CUDA sources include no device library (CUB / Thrust / cuBLAS / cuSPARSE / CUTLASS): sort, scans,
+    SpMV and reductions are this repo's own kernels."""
+    csrc = os.path.join(ROOT, 'finite-element-solver_b200', 'csrc')
+    for f in os.listdir(csrc):
+        text = open(os.path.join(csrc, f)).read()
+        for lib in ('cub/', 'cub::', 'thrust', 'cublas', 'cusparse', 'cutlass', 'cusolver'):
+            assert lib not in text, (f, lib)
+
+
 def test_no_cpu_fallback_without_cuda():
     import torch
     if torch.cuda.is_available():
