@@ -127,8 +127,8 @@ __global__ void k_negate(double* __restrict__ v, int64_t n) {
 //   phase 1: one thread per DISTINCT element of the tile evaluates the geometry once -- cofactors,
 //            one rsqrt (no divide, no sqrt), every node's physical gradient at every quadrature
 //            point pre-multiplied by sqrt(w_q mu_e vol_e) -- into shared-memory planes
-//            (element-minor, swizzled slots; the plane stride is 1 mod 8 so different nodes of one
-//            element sit in different banks).
+//            (element-minor, swizzled slots; the plane stride is 0 mod 8, so a gradient's bank depends
+//            on its slot only and the slot sequences of neighbouring lanes decide the conflicts).
 //   phase 2: one thread per work item = a stored pair (v, w), or one of the 2^lg adjacent lanes that
 //            share a pair with many contributions.  A lane walks its contributions in ascending
 //            element id, accumulates the raw outer products S += g~_a (x) g~_b in registers; a fixed

@@ -560,9 +560,20 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
   if (imax > 65535 || rmax > kTileRecCap || items * L >= ((int64_t)1 << 32)) return FES_OK;
   P->rec_max = rmax; P->pair_max = pmax; P->con_max = cmax; P->item_max = imax; P->n_items = items;
   P->nod_max = (nmax + 3) & ~3;
-  // plane stride 1 (mod 8): plane n sits n x 16 B further in bank space, so pairs that read different
-  // nodes of the SAME record do not collide; slots are swizzled inside aligned groups of 8
-  P->geo_stride = ((rmax + 7) & ~7) + 1;
+  // slots are swizzled inside aligned groups of 8 (mode 0)
+  {
+    // Smallest stride above every (swizzled) slot with the wanted residue; the last slot holds the zero record.
+    // Stride = 0 (mod 8): the bank of a gathered gradient depends on its slot only, not on the local node
+    // index, and the slot sequences of neighbouring lanes are what the item order and the slot modes make
+    // conflict-free (bank model: gathers 1.34x -> 1.19x of conflict-free on config 2; measured 0.165 -> 0.162 ms).
+    // The earlier 1 (mod 8) stride protected lanes reading different nodes of ONE record, which the
+    // (class, degree, slot, node) item order no longer produces.
+    static const int gs_align = getenv("FES_GS_ALIGN") ? atoi(getenv("FES_GS_ALIGN")) : 8;   // tuning knobs
+    static const int gs_res = getenv("FES_GS_RES") ? atoi(getenv("FES_GS_RES")) : 0;
+    int gs = ((rmax + 7) & ~7) + 1;
+    while (gs % gs_align != gs_res % gs_align) ++gs;
+    P->geo_stride = gs;
+  }
   if ((int64_t)N * P->geo_stride * 16 > 65535) return FES_OK;  // 16-bit byte offsets in the codes
   P->tile_read_bytes = rd;
   if (getenv("FES_PLAN_DEBUG"))

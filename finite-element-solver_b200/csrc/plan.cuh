@@ -25,7 +25,7 @@ struct fes_plan {
   bool tiled = false;
   int64_t n_tiles = 0, n_geo = 0, tile_read_bytes = 0;
   int inc_max = 0;                     // (node, incident element) records per tile: the tiling budget
-  int geo_stride = 0;                  // shared-memory plane stride of the records: 1 (mod 8), > rec_max
+  int geo_stride = 0;                  // shared-memory plane stride of the records: 0 (mod 8), > every slot
   int slot_mode = 0;                   // rec_slot mode the codes were emitted with
   int rec_max = 0, pair_max = 0, con_max = 0, item_max = 0, nod_max = 0;  // distinct elements / pairs / contributions / work items / distinct nodes per tile, upper bounds
   int64_t n_items = 0;
