@@ -249,6 +249,7 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
     if (pl < R::NV2) v2[(size_t)pl * GS + GS - 1] = make_double2(0.0, 0.0);
     else v1[(size_t)(pl - R::NV2) * GS + GS - 1] = 0.0;
   }
+  asm volatile("griddepcontrol.launch_dependents;");  // the next grid of the stream may be scheduled as CTAs of this one retire
   const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
   if (n_my <= 0) return;
   auto tile_of = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
@@ -361,7 +362,6 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
   // retire (its prologue -- barrier init and the first plan-stream copies above, which read only the
   // immutable plan -- then overlaps this grid's tail); nothing a previous kernel may have written
   // (coordinates, per-element coefficients, the CSR values) is touched before the wait below.
-  asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
   mbar_wait(&bar_h[0], 0);
