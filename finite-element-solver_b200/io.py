@@ -73,7 +73,9 @@ def load_solution(path='solution.npz'):
         if cls is None or not (isinstance(cls, type) and issubclass(cls, solution_module.Solution)):
             raise ValueError(f'Unknown solution class in saved solution: {name}')
         type_name = str(data[_ELEMENT_TYPE]) if _ELEMENT_TYPE in data else ''
-        element_type = getattr(elements_module, type_name) if type_name else None
+        element_type = getattr(elements_module, type_name, None) if type_name else None
+        if type_name and not (isinstance(element_type, type) and issubclass(element_type, elements_module.Element)):
+            raise ValueError(f'Unknown element type in saved solution: {type_name}')
         fields = {f.name: data[_VALUE_PREFIX + f.name] for f in dataclasses.fields(cls)
                   if f.name not in _SOLUTION_HEADER}
         return cls(mesh, n_components, element_type=element_type, **fields)

@@ -62,6 +62,11 @@ def test_elastic_solution_measures_and_refusals(tmp_path):
     np.savez(open(bad, 'wb'), **arrays)
     with pytest.raises(ValueError, match='Unknown solution class'):
         F.load_solution(str(bad))
+    arrays['__solution_class__'] = np.array('WaveSolution')
+    arrays['__element_type__'] = np.array('_lib')
+    np.savez(open(bad, 'wb'), **arrays)
+    with pytest.raises(ValueError, match='Unknown element type'):
+        F.load_solution(str(bad))
 
 
 @pytest.mark.gpu
