@@ -18,7 +18,8 @@ from .materials import LinearElasticMaterial  # noqa: F401
 from .mesh import Mesh, create_box_mesh, create_rect_mesh  # noqa: F401
 from .integrators import NewmarkMethod, ThetaMethod, wave_energy  # noqa: F401
 from .io import load_mesh, load_solution, save_mesh, save_solution  # noqa: F401
-from .solution import ElasticSolution, FieldSolution, Solution, TransientSolution, WaveSolution  # noqa: F401
+from .solution import (BucklingSolution, ElasticSolution, FieldSolution, ModalSolution,  # noqa: F401
+                       ScalarFieldSolution, Solution, TransientSolution, WaveSolution)
 from .problem import LinearProblem, heat, linear_elastic, poisson, projection, wave  # noqa: F401
 from .sensitivity import (Compliance, DensityField, MeanStress, ModulusField, PointValue,  # noqa: F401
                           SensitivityAnalysis, SoftMaxStress)

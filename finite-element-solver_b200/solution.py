@@ -35,9 +35,30 @@ class Solution:
         return load_solution(path)
 
 
+def _moved(mesh, displacement, n_components, scale=1.0):
+    """The mesh displaced by the leading vertex DOFs of a (P1 or P2) displacement vector."""
+    from .mesh import Mesh
+    n_vertices = len(mesh.vertices)
+    d = np.asarray(displacement, dtype=float).reshape(-1, n_components)[:n_vertices]
+    return Mesh(mesh.vertices + scale * d, mesh.elements, mesh.boundary)
+
+
 @dataclass(frozen=True, eq=False)
 class FieldSolution(Solution):
+    """A single steady field u (ref fem/solution.py:65-80)."""
     u: object = None
+
+    def deformed_mesh(self):
+        return _moved(self.mesh, self.u, self.n_components)
+
+
+@dataclass(frozen=True, eq=False)
+class ScalarFieldSolution(FieldSolution):
+    """A scalar field plus its per-element flux grad u (ref fem/solution.py:83-104)."""
+    flux: object = None        # (n_elements, spatial_dim)
+
+    def nodal_flux(self, method='average'):
+        return self.space.recover_nodal(self.flux, method=method)
 
 
 def trace(t):
@@ -112,6 +133,40 @@ class ElasticSolution(FieldSolution):
     @property
     def max_shear(self):
         return max_shear(self.stress)
+
+
+@dataclass(frozen=True, eq=False)
+class BucklingSolution(Solution):
+    """Linearised-buckling eigenpairs (ref fem/solution.py:189-222); carried for file interoperability --
+    the eigen solve itself is outside this library's path."""
+    load_factors: object = None   # (n_modes,) ascending
+    modes: object = None          # (n_modes, n_dofs)
+
+    @property
+    def critical_load_factor(self):
+        return float(self.load_factors[0])
+
+    def mode_mesh(self, i, scale=1.0):
+        return _moved(self.mesh, self.modes[i], self.n_components, scale)
+
+
+@dataclass(frozen=True, eq=False)
+class ModalSolution(Solution):
+    """Free-vibration eigenpairs (ref fem/solution.py:225-262); carried for file interoperability."""
+    angular_frequencies: object = None   # (n_modes,) ascending, rad/s
+    modes: object = None                 # (n_modes, n_dofs)
+
+    @property
+    def frequencies(self):
+        return np.asarray(self.angular_frequencies) / (2 * np.pi)
+
+    @property
+    def periods(self):
+        with np.errstate(divide='ignore'):
+            return 1.0 / self.frequencies
+
+    def mode_mesh(self, i, scale=1.0):
+        return _moved(self.mesh, self.modes[i], self.n_components, scale)
 
 
 @dataclass(frozen=True, eq=False)

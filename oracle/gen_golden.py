@@ -310,6 +310,13 @@ def io_cases():
     x = prob.space.node_coords
     hist = NewmarkMethod(dt=0.05, steps=3).run(prob, np.sin(np.pi * x[:, 0]) * x[:, 1], np.zeros(len(x)))
     save_solution(hist, os.path.join(OUT, 'io_wave.npz'))
+    from fem.solution import ModalSolution, ScalarFieldSolution
+    V1 = FunctionSpace(mesh, n_components=1)
+    u1 = np.sin(mesh.vertices[:, 0]) * mesh.vertices[:, 1]
+    save_solution(ScalarFieldSolution.from_solve(V1, u1), os.path.join(OUT, 'io_scalar.npz'))
+    rng = np.random.default_rng(4)
+    save_solution(ModalSolution(mesh, 2, np.array([1.5, 2.5, 7.0]), rng.normal(size=(3, 2 * len(mesh.vertices)))),
+                  os.path.join(OUT, 'io_modal.npz'))
     print('io cases written')
 
 

@@ -23,7 +23,9 @@ def test_mesh_json_round_trip(tmp_path):
 
 
 @pytest.mark.parametrize('name,cls,etype', [('io_wave', 'WaveSolution', None),
-                                             ('io_elastic_p2', 'ElasticSolution', 'QuadraticTriangleElement')])
+                                             ('io_elastic_p2', 'ElasticSolution', 'QuadraticTriangleElement'),
+                                             ('io_scalar', 'ScalarFieldSolution', 'LinearTriangleElement'),
+                                             ('io_modal', 'ModalSolution', None)])
 def test_solution_archives_interoperate(tmp_path, name, cls, etype):
     import fes_b200 as F
     path = os.path.join(GOLD, name + '.npz')
@@ -81,3 +83,13 @@ def test_elastic_solution_from_solve_matches_the_reference_archive():
     np.testing.assert_allclose(sol.compliance, ref.compliance, rtol=1e-12, atol=1e-16)
     nodal = sol.nodal_von_mises()
     assert nodal.shape == (V.n_nodes,) and np.all(nodal >= 0)
+
+
+def test_modal_solution_units_and_mode_mesh():
+    import fes_b200 as F
+    sol = F.load_solution(os.path.join(GOLD, 'io_modal.npz'))
+    np.testing.assert_allclose(sol.frequencies, sol.angular_frequencies / (2 * np.pi))
+    np.testing.assert_allclose(sol.periods * sol.frequencies, 1.0)
+    moved = sol.mode_mesh(1, scale=0.5)
+    np.testing.assert_allclose(moved.vertices, sol.mesh.vertices + 0.5 * sol.modes[1].reshape(-1, 2))
+    assert np.array_equal(moved.elements, sol.mesh.elements)
