@@ -335,6 +335,39 @@ k_elastic_fields(const int32_t* __restrict__ en, int64_t n_el, const double* __r
   if (compliance) compliance[e] = comp * vol;
 }
 
+// ---- gradient of a scalar nodal field at the first quadrature point (ref fem/space.py:511-517) ------------
+template <int ELEM, int SD>
+__global__ void __launch_bounds__(kBlock)
+k_scalar_gradient(const int32_t* __restrict__ en, int64_t n_el, const double* __restrict__ coords,
+                  const double* __restrict__ u, Rule rule, double* __restrict__ grad) {
+  constexpr int RD = ET<ELEM>::RD, N = ET<ELEM>::N;
+  static_assert(RD == SD, "gradients need a volume element");
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_el) return;
+  double X[RD + 1][SD];
+  load_corners<ELEM, SD>(en + e * N, coords, X);
+  Geom<RD, SD> g;
+  make_geom<RD, SD>(X, g);
+  double d[N][RD];
+  dshape_at<ELEM>(rule.pts[0], d);
+  double out[SD];
+#pragma unroll
+  for (int x = 0; x < SD; ++x) out[x] = 0.0;
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    const double un = __ldg(u + en[e * N + n]);
+#pragma unroll
+    for (int x = 0; x < SD; ++x) {
+      double gx = 0.0;
+#pragma unroll
+      for (int r = 0; r < RD; ++r) gx += d[n][r] * g.Jinv[r][x];
+      out[x] += un * gx;
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < SD; ++x) grad[e * SD + x] = out[x];
+}
+
 int rule_for(int elem_kind, int min_degree, Rule& r) {
   if (!quad_rule(elem_ref_dim(elem_kind), min_degree, r))
     return set_error(FES_ERR_UNSUPPORTED, "no quadrature rule of degree >= %d for reference_dim=%d", min_degree,
@@ -509,6 +542,20 @@ extern "C" int fes_von_mises_gradient(int elem_kind, const int32_t* en, int64_t 
     k_von_mises_gradient<FES_P2_TRI><<<g, kBlock, 0, st>>>(en, n_el, coords, d_u, d_E, E, nu, r, d_vm, d_dvm_du);
   else
     return set_error(FES_ERR_UNSUPPORTED, "stress quantities of interest are plane-strain 2D only (element kind %d)", elem_kind);
+  FES_LAUNCH_CHECK();
+  return FES_OK;
+}
+
+extern "C" int fes_scalar_gradient(int elem_kind, int sd, int min_degree, const int32_t* en, int64_t n_el,
+                                   const double* coords, const double* d_u, double* d_grad, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  Rule r;
+  FES_TRY(rule_for(elem_kind, min_degree, r));
+  if (n_el == 0) return FES_OK;
+  const int g = grid_for(n_el, kBlock);
+#define FES_CALL(EL, SD_) k_scalar_gradient<EL, SD_><<<g, kBlock, 0, st>>>(en, n_el, coords, d_u, r, d_grad)
+  FES_VOLUME_DISPATCH(FES_CALL);
+#undef FES_CALL
   FES_LAUNCH_CHECK();
   return FES_OK;
 }

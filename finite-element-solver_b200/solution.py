@@ -57,6 +57,11 @@ class ScalarFieldSolution(FieldSolution):
     """A scalar field plus its per-element flux grad u (ref fem/solution.py:83-104)."""
     flux: object = None        # (n_elements, spatial_dim)
 
+    @classmethod
+    def from_solve(cls, space, u):
+        """Package a scalar solve with its per-element flux grad u (device kernel `fes_scalar_gradient`)."""
+        return cls(space.mesh, space.n_components, _host(u), flux=_host(space.gradient(u)), element_type=space.element_type)
+
     def nodal_flux(self, method='average'):
         return self.space.recover_nodal(self.flux, method=method)
 

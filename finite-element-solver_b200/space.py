@@ -264,6 +264,21 @@ class FunctionSpace:
             cache[nq] = (pts, wdet)
         return cache[nq]
 
+    def gradient(self, u):
+        """(n_elements, spatial_dim) gradient of a scalar nodal field, one value per element, taken at the first
+        quadrature point (ref fem/space.py:511-517).  numpy in -> numpy out, device tensor in -> device tensor out."""
+        host = not isinstance(u, torch.Tensor)
+        ud = torch.as_tensor(np.ascontiguousarray(u, dtype=np.float64)) if host else u
+        ud = ud.to(device=self.device, dtype=torch.float64).contiguous().reshape(-1)
+        if ud.numel() != self.n_nodes:
+            raise ValueError(f'expected one value per node ({self.n_nodes}), got {ud.numel()}')
+        n_el = len(self.element_nodes)
+        out = torch.empty((n_el, self.spatial_dim), dtype=torch.float64, device=self.device)
+        _lib.check(_lib.lib().fes_scalar_gradient(self.element_type.KIND, self.spatial_dim,
+                                                  self.element_type.default_quadrature_degree(), _lib.ptr(self._en_d), n_el,
+                                                  _lib.ptr(self._coords_d), _lib.ptr(ud), _lib.ptr(out), _lib.stream()))
+        return out.cpu().numpy() if host else out
+
     def node_scatter(self, element_values, m):
         """Sum (n_el, N, m) per-(element, local node) values into (n_nodes, m), each node in ascending
         element id: bit-identical to the reference's bincount / np.add.at scatters

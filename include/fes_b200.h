@@ -245,6 +245,10 @@ int fes_weighted_gradient_matrices(int elem_kind, int spatial_dim, int n_comp, i
 int fes_elastic_fields(int elem_kind, const int32_t* d_elem_nodes, int64_t n_el, const double* d_coords,
                        const double* d_u, const double* d_E, double E, double nu, int min_degree,
                        double* d_strain, double* d_stress, double* d_compliance, void* stream);
+/* FunctionSpace.gradient (ref fem/space.py:511-517): (n_el, spatial_dim) gradient of a scalar nodal field at the
+ * first point of the rule (constant per element for P1). */
+int fes_scalar_gradient(int elem_kind, int spatial_dim, int min_degree, const int32_t* d_elem_nodes, int64_t n_el,
+                        const double* d_coords, const double* d_u, double* d_grad, void* stream);
 /* _VonMisesStress (ref fem/sensitivity.py:137-199): per-element plane-strain von Mises stress at the first
  * point of the rule and d(von Mises)/d(u_e), (n_el, nodes_per_elem, 2); either output may be NULL.
  * Scatter the weighted derivative with fes_node_scatter to get the adjoint load of MeanStress /

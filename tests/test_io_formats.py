@@ -93,3 +93,20 @@ def test_modal_solution_units_and_mode_mesh():
     moved = sol.mode_mesh(1, scale=0.5)
     np.testing.assert_allclose(moved.vertices, sol.mesh.vertices + 0.5 * sol.modes[1].reshape(-1, 2))
     assert np.array_equal(moved.elements, sol.mesh.elements)
+
+
+@pytest.mark.gpu
+def test_scalar_solution_from_solve_matches_the_reference_archive():
+    import fes_b200 as F
+    ref = F.load_solution(os.path.join(GOLD, 'io_scalar.npz'))
+    V = F.FunctionSpace(ref.mesh, n_components=1)
+    sol = F.ScalarFieldSolution.from_solve(V, ref.u)
+    assert sol.element_type is F.LinearTriangleElement
+    np.testing.assert_allclose(sol.flux, ref.flux, rtol=1e-12, atol=1e-14)
+    assert sol.nodal_flux().shape == (V.n_nodes, 2)
+    Vq = F.FunctionSpace(ref.mesh, F.QuadraticTriangleElement, n_components=1)
+    x = Vq.node_coords
+    g = Vq.gradient(2.0 * x[:, 0] - 3.0 * x[:, 1] + 1.0)          # a linear field: exact gradient on P2 too
+    np.testing.assert_allclose(g, np.tile([2.0, -3.0], (len(g), 1)), rtol=0, atol=1e-12)
+    with pytest.raises(ValueError):
+        V.gradient(np.zeros(V.n_nodes + 1))
