@@ -22,7 +22,7 @@ BASE = ['metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', '
         'vs_baseline', 'dtype', 'data', 'config']
 
 
-@pytest.mark.parametrize('name', ['r01_bench_n1.json', 'r01_bench_n2.json', 'r01_bench_n8.json'])
+@pytest.mark.parametrize('name', ['r01_bench_n1.json', 'r01_bench_n2.json', 'r01_bench_n4.json', 'r01_bench_n8.json'])
 def test_own_arm_line(name):
     d = _line(name)
     for k in BASE + ['roofline', 'e2e', 'gpu_launches', 'clocks']:
