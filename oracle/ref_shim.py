@@ -3,16 +3,25 @@
 `import fem` fails here because `fem/__init__.py` pulls in matplotlib and
 `fem/backends.py` imports pyamg, neither installed.  Registering an empty
 `fem` package pointing at the reference tree skips `__init__`, and a stub `pyamg` lets
-`fem.backends` import.  The reference location is FES_REFERENCE, else /root/reference.
-Nothing on the GPU box may call this: /root/reference does not exist there.
+`fem.backends` import.  The reference location is FES_REFERENCE, else /root/reference (build
+container), else `baseline/_ref` -- the git-ignored `pip install --target` of the unmodified
+reference that `__graft_entry__.build()` makes and that travels to the GPU box with the snapshot.
+Only tests/, smoke() and bench.py's CPU legs may use it.
 """
 import os
 import sys
 import types
 
 
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
 def reference_root():
-    return os.environ.get('FES_REFERENCE', '/root/reference')
+    cands = [os.environ.get('FES_REFERENCE'), '/root/reference', os.path.join(_REPO, 'baseline', '_ref')]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, 'fem')):
+            return c
+    return cands[1]
 
 
 def available():
