@@ -63,7 +63,7 @@ SIGNATURES = {
     'fes_comm_handle': (_int, [_p, _p]),
     'fes_comm_connect': (_int, [_p, _p]),
     'fes_comm_destroy': (None, [_p]),
-    'fes_solver_set_dist': (_int, [_p, _p, _i64, _i64, _p, _p, _p]),
+    'fes_solver_set_dist': (_int, [_p, _p, _i64, _i64, _p, _p, _p, _i64]),
     'fes_filter_create': (_int, [_p, _i64, _int, _p, _int, _dbl, _p, C.POINTER(_p)]),
     'fes_filter_destroy': (None, [_p]),
     'fes_filter_nnz': (_i64, [_p]),

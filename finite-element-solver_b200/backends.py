@@ -49,6 +49,15 @@ class PCGSolver:
         if x is None:
             x = torch.zeros(self.n, dtype=torch.float64, device=b.device)
             warm_start = False
+        for name, t in (('b', b), ('x', x)):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.numel() == self.n):
+                raise ValueError(f'{name} must be a CUDA float64 tensor of {self.n} entries')
+        if not x.is_contiguous() or x.data_ptr() % 16:
+            # the block kernels read the vector with 16-byte loads: solve on an aligned copy, write back
+            xa = x.contiguous().clone()
+            self.solve_device(b, xa, warm_start)
+            x.copy_(xa)
+            return x
         iters, relres = C.c_int64(0), C.c_double(0.0)
         status = _lib.lib().fes_solver_solve(self._h, _lib.ptr(b.contiguous()), _lib.ptr(x), self.rtol,
                                              int(self.maxiter or 0), 1 if warm_start else 0, C.byref(iters),
@@ -88,6 +97,10 @@ class JacobiPCGBackend:
         if isinstance(A, DeviceCSR):
             if A.shape[0] != A.shape[1]:
                 raise ValueError(f'operator must be square, got {A.shape}')
+            if free_mask is not None and not (isinstance(free_mask, torch.Tensor) and free_mask.dtype == torch.uint8
+                                              and free_mask.device == A.device and free_mask.is_contiguous()
+                                              and free_mask.numel() == A.shape[0]):
+                raise ValueError(f'free_mask must be a contiguous uint8 tensor of {A.shape[0]} entries on {A.device}')
             _lib.check(L.fes_solver_create(A.shape[0], _lib.ptr(A.indptr_d), _lib.ptr(A.indices_d),
                                            _lib.ptr(A.data_d), _lib.ptr(free_mask), _lib.stream(), C.byref(handle)))
             plan = getattr(A, '_plan', None)

@@ -37,17 +37,17 @@ struct PcgState {
   int status;  // 0 converged, 1 not converged in maxiter, 2 breakdown (p.Ap <= 0 or NaN)
   double relres;
   double bnorm;
-  long long cycles[6];  // CTA 0 / thread 0: p update, halo, product, product reduce, x/r update, update reduce
+  long long cycles[6];  // thread 0 with FES_PCG_TIMERS: p update / barrier, halo, product, product reduce, x/r update, update reduce (+ loop top)
 };
 
 // Peer-memory communicator: one cudaMalloc'd region per rank, exported over CUDA IPC.
 //   [0,128)      u64 halo_flag[16]   peer r stores its halo epoch here after writing my ghosts
 //   [128,256)    u64 red_flag[16]    peer r stores the reduction step here after filling its box
-//   [256,2304)   double red_box[4][16][4]   ring of reduction mailboxes, [step & 3][src rank][value]
-//   [2304,2320)  u64 counters[2]     this rank's halo epoch / reduction step (persist across solves)
-//   [4096,...)   double p[max_dofs]  the CG direction vector; peers write its ghost entries
-constexpr int kCommMaxWorld = 16;
-constexpr size_t kCommHaloFlag = 0, kCommRedFlag = 128, kCommRedBox = 256, kCommCounters = 2304, kCommVec = 4096;
+//   [256,4352)   double red_box[4][16][8]   ring of reduction mailboxes, [step & 3][src rank][value]
+//   [4352,4368)  u64 counters[2]     this rank's halo epoch / reduction step (persist across solves)
+//   [8192,...)   double p[max_dofs]  the CG direction vector; peers write its ghost entries
+constexpr int kCommMaxWorld = 16, kBoxVals = 8;
+constexpr size_t kCommHaloFlag = 0, kCommRedFlag = 128, kCommRedBox = 256, kCommCounters = 4352, kCommVec = 8192;
 
 struct fes_comm {
   int rank = 0, world = 1;
@@ -84,6 +84,9 @@ struct fes_solver {
   int64_t row_begin = 0, row_end = 0;
   fes::DevBuf<int32_t> send_ptr, send_src, send_dst;
   unsigned recv_mask = 0, send_mask = 0;
+  int64_t n_free_global = 0;          // free dofs over all ranks: the default iteration cap must not depend on the rank
+  int64_t n_slots_interior = 0;       // SELL slots [0, n_slots_interior) multiply rows that touch no ghost column
+  fes::DevBuf<unsigned long long> halo_done;  // CTAs that finished their halo stores (monotonic; a multiple of the grid between exchanges)
 };
 
 namespace fes {
@@ -120,7 +123,10 @@ struct PcgArgs {
   const int32_t* send_src;           // local dof to read
   const int32_t* send_dst;           // dof index in the receiver's local numbering
   unsigned recv_mask, send_mask;     // bit r: this rank receives from / sends to rank r
-  int fused;                         // single-GPU: one reduction + two grid barriers per iteration (see k_pcg)
+  int fused;                         // one reduction + two grid barriers per iteration (see k_pcg)
+  int timers;                        // FES_PCG_TIMERS: per-phase cycle counters in state->cycles
+  int64_t n_slots_interior;          // slots below this bound read no ghost entry (distributed overlap)
+  unsigned long long* halo_done;     // device counter of the barrier-free halo post
 };
 
 constexpr long long kSpinLimit = 40000000000LL;  // ~20 s of SM clocks: a lost peer traps instead of hanging
@@ -162,13 +168,51 @@ __device__ __forceinline__ void halo_exchange(const PcgArgs& A, cg::grid_group& 
   __threadfence_system();  // drop stale L1 lines of the ghost entries before the gathers
 }
 
+// The same exchange without a grid barrier, for the overlapped loop: every CTA stores its share of the
+// boundary values into the neighbours' ghost entries, fences, and counts itself done; the CTA that
+// completes the count publishes the epoch to the neighbours.  Nobody waits here -- rows that read ghost
+// entries call halo_wait just before they are multiplied, so the NVLink latency hides under the interior rows.
+__device__ __forceinline__ void halo_post(const PcgArgs& A, const double* vec, unsigned long long epoch, int64_t tid,
+                                          int64_t nth) {
+  const int32_t total = A.send_ptr[A.world];
+  for (int64_t k = tid; k < total; k += nth) {
+    int r = 0;
+    while (k >= A.send_ptr[r + 1]) ++r;
+    double* peer_vec = reinterpret_cast<double*>(A.comm_peer[r] + kCommVec);
+    peer_vec[A.send_dst[k]] = vec[A.send_src[k]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long seen = atomicAdd(A.halo_done, 1ULL) + 1ULL;
+    if (seen % gridDim.x == 0) {  // last CTA of this exchange: every store of every CTA is fenced and counted
+      __threadfence_system();
+      for (int r = 0; r < A.world; ++r)
+        if ((A.send_mask >> r) & 1u)
+          *(reinterpret_cast<volatile unsigned long long*>(A.comm_peer[r] + kCommHaloFlag) + A.rank) = epoch;
+    }
+  }
+}
+
+__device__ __forceinline__ void halo_wait(const PcgArgs& A, unsigned long long epoch) {
+  if (threadIdx.x == 0) {
+    for (int r = 0; r < A.world; ++r)
+      if ((A.recv_mask >> r) & 1u)
+        spin_until(reinterpret_cast<volatile unsigned long long*>(A.comm + kCommHaloFlag) + r, epoch);
+    __threadfence_system();
+  }
+  __syncthreads();
+  __threadfence_system();  // drop L1 lines that may hold ghost entries fetched before they arrived
+}
+
 // Sum NV values over all ranks through the peers' mailboxes; fixed rank order, so every rank and
 // every CTA computes the same bits.  v holds this rank's totals on entry (valid in every thread).
 template <int NV>
 __device__ __forceinline__ void rank_sum(const PcgArgs& A, double (&v)[NV], unsigned long long step) {
+  static_assert(NV <= kBoxVals, "reduction mailbox too small");
   if (blockIdx.x == 0 && (int)threadIdx.x < A.world) {
     unsigned char* peer = A.comm_peer[threadIdx.x];
-    volatile double* box = reinterpret_cast<volatile double*>(peer + kCommRedBox) + ((step & 3) * kCommMaxWorld + A.rank) * 4;
+    volatile double* box = reinterpret_cast<volatile double*>(peer + kCommRedBox) + ((step & 3) * kCommMaxWorld + A.rank) * kBoxVals;
 #pragma unroll
     for (int k = 0; k < NV; ++k) box[k] = v[k];
     __threadfence_system();
@@ -179,11 +223,11 @@ __device__ __forceinline__ void rank_sum(const PcgArgs& A, double (&v)[NV], unsi
       spin_until(reinterpret_cast<volatile unsigned long long*>(A.comm + kCommRedFlag) + r, step);
   }
   __syncthreads();
-  const volatile double* mine = reinterpret_cast<const volatile double*>(A.comm + kCommRedBox) + (step & 3) * kCommMaxWorld * 4;
+  const volatile double* mine = reinterpret_cast<const volatile double*>(A.comm + kCommRedBox) + (step & 3) * kCommMaxWorld * kBoxVals;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     double t = 0.0;
-    for (int r = 0; r < A.world; ++r) t += mine[r * 4 + k];
+    for (int r = 0; r < A.world; ++r) t += mine[r * kBoxVals + k];
     v[k] = t;
   }
 }
@@ -192,12 +236,16 @@ __device__ __forceinline__ bool is_free(const uint8_t* mask, int64_t i) { return
 
 // y = A vec on the free rows (0 on fixed rows); returns this thread's share of vec . y.
 // RESIDUAL writes b - A vec instead.  MASKED_X treats vec as zero on fixed dofs (warm start).
+// Slots [slot0, slot1) only; with DOTS the six extra sums are ADDED to dots[0..5] (the overlapped loop
+// calls this twice per iteration: interior rows, then the rows that read ghost entries).
 template <int C, bool MASKED_X, bool RESIDUAL, bool DOTS = false>
 __device__ __forceinline__ double sparse_product(const PcgArgs& A, int64_t tid, int64_t nth, const double* vec,
-                                                 double* y, double* dots = nullptr) {
+                                                 double* y, double* dots = nullptr, int64_t slot0 = 0,
+                                                 int64_t slot1 = -1) {
   double partial = 0.0;
   [[maybe_unused]] double d_rho = 0.0, d_s1 = 0.0, d_s2 = 0.0, d_rr = 0.0, d_t1 = 0.0, d_t2 = 0.0;
-  for (int64_t slot = tid; slot < A.n_slots; slot += nth) {
+  if (slot1 < 0) slot1 = A.n_slots;
+  for (int64_t slot = slot0 + tid; slot < slot1; slot += nth) {
     const int lane = (int)(slot & 31);
     const int64_t slice = slot >> 5;
     const int32_t brow = __ldcs(A.sell_row + slot);
@@ -251,7 +299,7 @@ __device__ __forceinline__ double sparse_product(const PcgArgs& A, int64_t tid, 
     }
   }
   if constexpr (DOTS) {
-    dots[0] = d_rho; dots[1] = d_s1; dots[2] = d_s2; dots[3] = d_rr; dots[4] = d_t1; dots[5] = d_t2;
+    dots[0] += d_rho; dots[1] += d_s1; dots[2] += d_s2; dots[3] += d_rr; dots[4] += d_t1; dots[5] += d_t2;
   }
   return partial;
 }
@@ -265,9 +313,16 @@ __device__ __forceinline__ double sparse_product(const PcgArgs& A, int64_t tid, 
 // SIMP 1.49 against 1.68 design iterations / s, config 5 tets 1237 against 1031 us -- the six extra dot
 // products and the two extra vector reads inside the product phase cost the HBM-bound SpMV more than the
 // barrier and the reduction they remove, so the textbook loop stays the default.
+//
+// Distributed default = FUSED with overlap: one rank reduction instead of two per iteration (a whole NVLink
+// round trip less), and the halo of p is posted without a grid barrier at the top of the iteration and
+// awaited only by the rows that read ghost entries, after the interior rows have been multiplied.
+#ifndef FES_PCG_DIST_BLOCKS
+#define FES_PCG_DIST_BLOCKS 1  // CTAs per SM of the overlapped distributed loop: 1 = 128 registers, no spills (2 spills ~300 B)
+#endif
 template <int C, bool DIST, bool FUSED>
-__global__ void __launch_bounds__(kPcgBlock, (C == 3 || DIST) ? 2 : (FUSED ? FES_PCG_FUSED_BLOCKS : 3)) k_pcg(PcgArgs A) {
-  static_assert(!(DIST && FUSED), "the fused loop is the single-GPU variant");
+__global__ void __launch_bounds__(kPcgBlock, (DIST && FUSED) ? FES_PCG_DIST_BLOCKS
+                                             : (C == 3 || DIST) ? 2 : (FUSED ? FES_PCG_FUSED_BLOCKS : 3)) k_pcg(PcgArgs A) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double sm[7 * 33];
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,7 +370,17 @@ __global__ void __launch_bounds__(kPcgBlock, (C == 3 || DIST) ? 2 : (FUSED ? FES
   double rr = v3[1], rho = v3[2], rho_prev = 1.0;
   long long it = 0;
   int status = 0;
-  long long cyc[6] = {0, 0, 0, 0, 0, 0};
+  // phase timers (FES_PCG_TIMERS): thread 0 adds the SM cycles since the previous tick to phase k, in global memory
+  long long t_last = clock64();
+  if (A.timers && tid == 0)
+    for (int k = 0; k < 6; ++k) A.state->cycles[k] = 0;
+  auto tick = [&](int k) {
+    if (A.timers) {
+      const long long t = clock64();
+      if (tid == 0) A.state->cycles[k] += t - t_last;
+      t_last = t;
+    }
+  };
   if (bb == 0.0) {  // scipy returns x = 0 for a zero right-hand side
     for (int64_t i = lo + tid; i < hi; i += nth)
       if (is_free(A.mask, i)) A.x[i] = 0.0;
@@ -331,12 +396,27 @@ __global__ void __launch_bounds__(kPcgBlock, (C == 3 || DIST) ? 2 : (FUSED ? FES
     for (;;) {
       if (sqrt(rr) < A.rtol * sqrt(bb)) break;
       if (it >= A.maxiter) { status = 1; break; }
-      long long c0 = clock64();
-      double v7[7];
-      v7[0] = sparse_product<C, false, false, true>(A, tid, nth, A.p, A.q, v7 + 1);
-      long long c1 = clock64(); cyc[2] += c1 - c0;
+      tick(5);
+      double v7[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      if (dist) {
+        // p is complete on the owned rows (grid barrier at the end of the previous iteration / of the set-up)
+        ++halo_epoch;
+        halo_post(A, A.p, halo_epoch, tid, nth);
+        tick(1);
+        v7[0] = sparse_product<C, false, false, true>(A, tid, nth, A.p, A.q, v7 + 1, 0, A.n_slots_interior);
+        if (A.n_slots_interior + (int64_t)blockIdx.x * blockDim.x < A.n_slots) {  // CTA-uniform: this CTA multiplies interface rows
+          tick(2);
+          halo_wait(A, halo_epoch);
+          tick(1);
+          v7[0] += sparse_product<C, false, false, true>(A, tid, nth, A.p, A.q, v7 + 1, A.n_slots_interior, A.n_slots);
+        }
+      } else {
+        v7[0] = sparse_product<C, false, false, true>(A, tid, nth, A.p, A.q, v7 + 1);
+      }
+      tick(2);
       grid_sum<7>(grid, v7, A.partials, 0, sm);
-      c0 = clock64(); cyc[3] += c0 - c1;
+      if (dist) rank_sum<7>(A, v7, ++red_step);
+      tick(3);
       const double pq = v7[0], rho_k = v7[1];
       if (!(pq > 0.0)) { status = 2; break; }
       const double alpha = rho_k / pq;
@@ -350,9 +430,9 @@ __global__ void __launch_bounds__(kPcgBlock, (C == 3 || DIST) ? 2 : (FUSED ? FES
         A.r[i] = ri;
         A.p[i] = fma(beta, pi, A.dinv[i] * ri);
       }
-      c1 = clock64(); cyc[4] += c1 - c0;
+      tick(4);
       grid.sync();
-      cyc[0] += clock64() - c1;
+      tick(0);
       rr = rr_next;
       ++it;
     }
@@ -361,18 +441,18 @@ __global__ void __launch_bounds__(kPcgBlock, (C == 3 || DIST) ? 2 : (FUSED ? FES
       if (sqrt(rr) < A.rtol * sqrt(bb)) break;
       if (it >= A.maxiter) { status = 1; break; }
       const double beta = (it == 0) ? 0.0 : rho / rho_prev;
-      long long c0 = clock64();
+      tick(5);
       for (int64_t i = lo + tid; i < hi; i += nth) A.p[i] = fma(beta, A.p[i], A.dinv[i] * A.r[i]);
       grid.sync();
-      long long c1 = clock64(); cyc[0] += c1 - c0;
+      tick(0);
       if (dist) halo_exchange(A, grid, A.p, ++halo_epoch, tid, nth);
-      c0 = clock64(); cyc[1] += c0 - c1;
+      tick(1);
 
       double v1[1] = {sparse_product<C, false, false>(A, tid, nth, A.p, A.q)};
-      c1 = clock64(); cyc[2] += c1 - c0;
+      tick(2);
       grid_sum<1>(grid, v1, A.partials, 3, sm);
       if (dist) rank_sum<1>(A, v1, ++red_step);
-      c0 = clock64(); cyc[3] += c0 - c1;
+      tick(3);
       const double pq = v1[0];
       if (!(pq > 0.0)) { status = 2; break; }
       const double alpha = rho / pq;
@@ -386,10 +466,10 @@ __global__ void __launch_bounds__(kPcgBlock, (C == 3 || DIST) ? 2 : (FUSED ? FES
         v2[0] += ri * ri;
         v2[1] += ri * ri * A.dinv[i];
       }
-      c1 = clock64(); cyc[4] += c1 - c0;
+      tick(4);
       grid_sum<2>(grid, v2, A.partials, 1, sm);
       if (dist) rank_sum<2>(A, v2, ++red_step);
-      cyc[5] += clock64() - c1;
+      tick(5);
       rr = v2[0];
       rho_prev = rho;
       rho = v2[1];
@@ -401,7 +481,6 @@ __global__ void __launch_bounds__(kPcgBlock, (C == 3 || DIST) ? 2 : (FUSED ? FES
     A.state->status = status;
     A.state->bnorm = sqrt(bb);
     A.state->relres = bb > 0.0 ? sqrt(rr) / sqrt(bb) : 0.0;
-    for (int k = 0; k < 6; ++k) A.state->cycles[k] = cyc[k];
     if (dist) {
       volatile unsigned long long* ctr = reinterpret_cast<volatile unsigned long long*>(A.comm + kCommCounters);
       ctr[0] = halo_epoch;
@@ -517,10 +596,21 @@ int launch_pcg_variant(fes_solver* s, PcgArgs& args, cudaStream_t st) {
 
 template <int C, bool DIST>
 int launch_pcg(fes_solver* s, PcgArgs& args, cudaStream_t st) {
-  if constexpr (!DIST) {
-    if (args.fused) return launch_pcg_variant<C, false, true>(s, args, st);
-  }
+  if (args.fused) return launch_pcg_variant<C, DIST, true>(s, args, st);
   return launch_pcg_variant<C, DIST, false>(s, args, st);
+}
+
+// 1 = the block row reads a column outside the owned block range [b0, b1) (a ghost node)
+__global__ void k_interface_rows(int64_t b0, int64_t b1, const int32_t* __restrict__ row_ptr,
+                                 const int32_t* __restrict__ row_col, uint8_t* __restrict__ flag) {
+  const int64_t r = b0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= b1) return;
+  uint8_t f = 0;
+  for (int32_t k = row_ptr[r]; k < row_ptr[r + 1]; ++k) {
+    const int32_t c = row_col[k];
+    f |= (c < b0 || c >= b1) ? 1 : 0;
+  }
+  flag[r - b0] = f;
 }
 
 // SELL-32-sigma structure over block rows: the row order and slice offsets are computed on the
@@ -533,17 +623,43 @@ int build_sell(fes_solver* s, cudaStream_t st) {
   FES_CUDA(cudaStreamSynchronize(st));
   // only the owned block rows are multiplied (all of them on one GPU)
   const int64_t b0 = s->row_begin / s->c, b1 = s->row_end / s->c, nb = b1 - b0;
-  const int64_t n_slices = (nb + 31) / 32;
+  // Distributed: rows that read no ghost column come first (their slices are multiplied while the halo
+  // is in flight), the interface rows follow from the next slice boundary.
+  std::vector<int32_t> seq;   // block rows in multiplication order, -1 = padding
+  seq.reserve(nb + 32);
+  int64_t n_interior_slots = 0;
+  if (s->comm != nullptr && s->comm->world > 1 && nb > 0) {
+    DevBuf<uint8_t> d_flag;
+    FES_CUDA(d_flag.alloc(nb));
+    k_interface_rows<<<grid_for(nb, 256), 256, 0, st>>>(b0, b1, s->row_ptr, s->row_col, d_flag.p);
+    FES_LAUNCH_CHECK();
+    std::vector<uint8_t> flag(nb);
+    FES_CUDA(cudaMemcpyAsync(flag.data(), d_flag.p, nb, cudaMemcpyDeviceToHost, st));
+    FES_CUDA(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < nb; ++i) if (!flag[i]) seq.push_back((int32_t)(b0 + i));
+    while (seq.size() % 32) seq.push_back(-1);
+    n_interior_slots = (int64_t)seq.size();
+    for (int64_t i = 0; i < nb; ++i) if (flag[i]) seq.push_back((int32_t)(b0 + i));
+  } else {
+    for (int64_t i = 0; i < nb; ++i) seq.push_back((int32_t)(b0 + i));
+    n_interior_slots = 0;  // unused on one GPU
+  }
+  const int64_t n_seq = (int64_t)seq.size();
+  const int64_t n_slices = (n_seq + 31) / 32;
+  s->n_slots_interior = n_interior_slots;
+  auto len_of = [&](int32_t r) { return r < 0 ? -1 : ptr[r + 1] - ptr[r]; };
   std::vector<int32_t> row(n_slices * 32, -1), slice_ptr(n_slices + 1, 0);
   std::vector<int32_t> order;
-  for (int64_t w0 = 0; w0 < nb; w0 += kSigma) {
-    const int64_t w1 = std::min<int64_t>(nb, w0 + kSigma);
-    order.resize(w1 - w0);
-    for (int64_t i = w0; i < w1; ++i) order[i - w0] = (int32_t)(b0 + i);
-    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-      return ptr[a + 1] - ptr[a] > ptr[b + 1] - ptr[b];
-    });
-    for (int64_t i = w0; i < w1; ++i) row[i] = order[i - w0];
+  // sigma windows never straddle the interior / interface boundary (a multiple of 32, not of sigma)
+  for (int part = 0; part < 2; ++part) {
+    const int64_t p0 = part == 0 ? 0 : n_interior_slots, p1 = part == 0 ? (n_interior_slots ? n_interior_slots : n_seq) : n_seq;
+    if (part == 1 && n_interior_slots == 0) break;
+    for (int64_t w0 = p0; w0 < p1; w0 += kSigma) {
+      const int64_t w1 = std::min<int64_t>(p1, w0 + kSigma);
+      order.assign(seq.begin() + w0, seq.begin() + w1);
+      std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return len_of(a) > len_of(b); });
+      for (int64_t i = w0; i < w1; ++i) row[i] = order[i - w0];
+    }
   }
   int64_t total = 0;
   for (int64_t sl = 0; sl < n_slices; ++sl) {
@@ -770,8 +886,10 @@ extern "C" void fes_comm_destroy(fes_comm* c) {
 }
 
 extern "C" int fes_solver_set_dist(fes_solver* s, fes_comm* comm, int64_t row_begin, int64_t row_end,
-                                   const int32_t* h_send_ptr, const int32_t* h_send_src, const int32_t* h_send_dst) {
+                                   const int32_t* h_send_ptr, const int32_t* h_send_src, const int32_t* h_send_dst,
+                                   int64_t n_free_global) {
   if (!s || !comm || !h_send_ptr) return set_error(FES_ERR_VALUE, "fes_solver_set_dist: NULL argument");
+  if (n_free_global < 0) return set_error(FES_ERR_VALUE, "fes_solver_set_dist: n_free_global < 0");
   if (row_begin < 0 || row_end > s->n || row_begin > row_end || row_begin % s->c || row_end % s->c)
     return set_error(FES_ERR_VALUE, "fes_solver_set_dist: bad owned row range [%lld, %lld)", (long long)row_begin,
                      (long long)row_end);
@@ -779,6 +897,9 @@ extern "C" int fes_solver_set_dist(fes_solver* s, fes_comm* comm, int64_t row_be
   if (s->sell_row.p != nullptr) return set_error(FES_ERR_VALUE, "fes_solver_set_dist: call before the first solve");
   s->comm = comm;
   s->row_begin = row_begin; s->row_end = row_end;
+  s->n_free_global = n_free_global;
+  FES_CUDA(s->halo_done.alloc(1));
+  FES_CUDA(cudaMemset(s->halo_done.p, 0, sizeof(unsigned long long)));
   const int world = comm->world;
   const int32_t total = h_send_ptr[world];
   FES_CUDA(s->send_ptr.alloc(world + 1));
@@ -803,10 +924,16 @@ extern "C" int fes_solver_solve(fes_solver* s, const double* d_b, double* d_x, d
   if (!s) return set_error(FES_ERR_VALUE, "fes_solver_solve: NULL solver");
   if (iters_out) *iters_out = 0;
   if (relres_out) *relres_out = 0.0;
-  if (s->n == 0 || s->n_free == 0) return FES_OK;
-  if (maxiter <= 0) maxiter = 10 * s->n_free;
-  FES_TRY(ensure_sell(s, st));
   const bool dist = s->comm != nullptr && s->comm->world > 1;
+  // Every exit condition of a distributed solve is global: a rank whose local dofs are all fixed still
+  // joins the collective kernel, and the default iteration cap comes from the global free-dof count
+  // (scipy: maxiter = 10 n), so all ranks stop at the same iteration.
+  const int64_t n_free = dist ? s->n_free_global : s->n_free;
+  if (s->n == 0 || n_free == 0) return FES_OK;
+  if (maxiter <= 0) maxiter = 10 * n_free;
+  if (warm_start && s->c == 2 && !dist && (reinterpret_cast<uintptr_t>(d_x) & 15))
+    return set_error(FES_ERR_VALUE, "fes_solver_solve: a warm-start vector of a 2-component operator must be 16-byte aligned");
+  FES_TRY(ensure_sell(s, st));
   if (dist && !s->comm->connected) return set_error(FES_ERR_VALUE, "fes_solver_solve: communicator is not connected");
   double* pvec = dist ? reinterpret_cast<double*>(s->comm->base + kCommVec) : s->p.p;
   PcgArgs a{s->n, s->mask, s->dinv.p, d_b, d_x, s->r.p, pvec, s->q.p, s->partials.p, s->state.p, rtol,
@@ -814,7 +941,10 @@ extern "C" int fes_solver_solve(fes_solver* s, const double* d_b, double* d_x, d
             s->sell_cols.p, s->sell_vals.p, s->row_begin, s->row_end, dist ? s->comm->world : 1,
             dist ? s->comm->rank : 0, dist ? s->comm->base : nullptr, dist ? s->comm->d_peer.p : nullptr,
             s->send_ptr.p, s->send_src.p, s->send_dst.p, s->recv_mask, s->send_mask,
-            getenv("FES_PCG_FUSED") ? 1 : 0};  // env: the single-reduction loop (A-B knob; measured slower, see k_pcg)
+            // one GPU: the textbook three-barrier loop unless FES_PCG_FUSED is set (A-B knob; measured slower, see
+            // k_pcg).  Distributed: the single-reduction overlapped loop unless FES_PCG_DIST_CLASSIC is set.
+            dist ? (getenv("FES_PCG_DIST_CLASSIC") ? 0 : 1) : (getenv("FES_PCG_FUSED") ? 1 : 0),
+            getenv("FES_PCG_TIMERS") ? 1 : 0, s->n_slots_interior, s->halo_done.p};
   if (dist) {
     if (s->c == 2) FES_TRY((launch_pcg<2, true>(s, a, st)));
     else if (s->c == 3) FES_TRY((launch_pcg<3, true>(s, a, st)));

@@ -164,7 +164,7 @@ class DistributedSystem:
     """DiscreteSystem over a node partition: owned rows assembled locally, Jacobi-PCG with the
     halo exchange and the dot-product reductions inside the persistent kernel."""
 
-    def __init__(self, part, A_local, n_comp, free_mask_local, comm, schedule, backend):
+    def __init__(self, part, A_local, n_comp, free_mask_local, comm, schedule, backend, group=None):
         """A_local: DeviceCSR on the local numbering (from FunctionSpace.assemble_device on
         part.local_mesh); free_mask_local: uint8 (n_local_dofs) 1 = free; schedule: halo_schedule()."""
         self.part, self.n_comp, self.comm = part, n_comp, comm
@@ -175,9 +175,18 @@ class DistributedSystem:
         rep = lambda a: (c * a.astype(np.int64)[:, None] + np.arange(c)).ravel().astype(np.int32)
         dptr = (ptr.astype(np.int64) * c).astype(np.int32)
         self._lists = (np.ascontiguousarray(dptr), np.ascontiguousarray(rep(src)), np.ascontiguousarray(rep(dst)))
+        # free dofs of the whole system = sum over ranks of the free dofs they OWN (every exit condition of
+        # the collective kernel must be the same on all ranks)
+        import torch.distributed as dist
+        owned_free = free_mask_local[c * part.owned_begin:c * part.owned_end].sum(dtype=torch.int64).reshape(1)
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            if dist.get_backend(group) == 'gloo':
+                owned_free = owned_free.cpu()
+            dist.all_reduce(owned_free, group=group)
+        self.n_free_global = int(owned_free.item())
         _lib.check(_lib.lib().fes_solver_set_dist(
             self._solver._h, comm.handle, c * part.owned_begin, c * part.owned_end,
-            _lib.ptr(self._lists[0]), _lib.ptr(self._lists[1]), _lib.ptr(self._lists[2])))
+            _lib.ptr(self._lists[0]), _lib.ptr(self._lists[1]), _lib.ptr(self._lists[2]), self.n_free_global))
 
     @property
     def solver(self):

@@ -162,7 +162,14 @@ class _ElementModulusParameterization:
         if lam is u:
             return self._energy(ud)
         ld = _dev(lam, dev)
-        return (self._energy(ud + ld) - self._energy(ud - ld)) * 0.25
+        # polarization of the element strain energy, on vectors NORMALISED to unit size: with |u| and |lam| many
+        # orders apart (a stress adjoint at E ~ 1e11 scales like E/h against 1/E) the plain difference
+        # Q(u+lam) - Q(u-lam) cancels catastrophically; a b (Q(u/a + lam/b) - Q(u/a - lam/b)) / 4 does not.
+        a, b = float(ud.abs().max()), float(ld.abs().max())
+        if a == 0.0 or b == 0.0:
+            return torch.zeros(len(self.space.element_nodes), dtype=torch.float64, device=dev)
+        un, ln = ud / a, ld / b
+        return (self._energy(un + ln) - self._energy(un - ln)) * (0.25 * a * b)
 
 
 class DensityField(_ElementModulusParameterization):

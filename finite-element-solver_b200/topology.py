@@ -129,7 +129,7 @@ class TopologyOptimizer:
         self.base_E, self.nu, self.source = equation.E, equation.nu, equation.source
         self.iters, self.volume_frac, self.penalty = iters, volume_frac, float(penalty)
         self.objective = objective if objective is not None else MinCompliance()
-        self.strategy = strategy
+        self.strategy = strategy   # stored and never used, exactly as the reference does (fem/topology.py:181)
         self.backend = backend if backend is not None else JacobiPCGBackend()
         self.warm_start, self.history_mode = warm_start, history
         self.space = FunctionSpace(mesh, n_components=mesh.spatial_dim)
@@ -170,6 +170,10 @@ class TopologyOptimizer:
     def rho(self):
         return self._rho.cpu().numpy()
 
+    @rho.setter
+    def rho(self, value):   # a plain attribute in the reference (fem/topology.py:203)
+        self.set_rho(value)
+
     @property
     def rho_d(self):
         return self._rho
@@ -205,6 +209,13 @@ class TopologyOptimizer:
         _lib.check(L.fes_assemble(sp.plan().handle, sp.element_type.KIND, low.form, sp.spatial_dim,
                                   _lib.ptr(sp._en_d), _lib.ptr(sp._coords_d), C.byref(cf), _lib.ptr(self._values),
                                   _lib.stream()))
+        robin = self._problem._robin_operator
+        if robin is not None:
+            # the tangent of problem.with_operator(stiffness) includes the Robin term (ref fem/problem.py:138-140,
+            # fem/topology.py:252): add kappa * M_boundary on its sub-pattern, in place
+            _lib.check(L.fes_csr_add_subpattern(self.space.n_dofs, _lib.ptr(self._A.indptr_d), _lib.ptr(self._A.indices_d),
+                                                _lib.ptr(self._values), _lib.ptr(robin.indptr_d), _lib.ptr(robin.indices_d),
+                                                _lib.ptr(robin.data_d), 1.0, _lib.stream()))
         if self._solver is None:
             self._solver = self.backend.prepare(self._A, self._mask)
         else:

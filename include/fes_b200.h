@@ -183,9 +183,17 @@ int fes_comm_handle(const fes_comm* comm, void* out64);         /* cudaIpcMemHan
 int fes_comm_connect(fes_comm* comm, const void* handles);      /* world x 64 bytes, rank order      */
 void fes_comm_destroy(fes_comm* comm);
 /* Rows [row_begin,row_end) of the local numbering are owned; h_send_* (dof level) list, per peer
- * rank, the owned dofs it needs and their index in ITS numbering.  Call before the first solve. */
+ * rank, the owned dofs it needs and their index in ITS numbering.  n_free_global = free dofs summed
+ * over the ranks' OWNED rows (identical on every rank): the default iteration cap 10 n of scipy's cg
+ * (ref fem/backends.py:201-213) and the "nothing to solve" test use it, so every rank leaves the
+ * collective kernel at the same iteration.  Call before the first solve.
+ * Per iteration the distributed kernel posts the halo of p without a grid barrier, multiplies the
+ * rows that read no ghost entry while it is in flight, and sums all dot products of the iteration in
+ * ONE cross-rank reduction (single-reduction CG); FES_PCG_DIST_CLASSIC=1 selects the textbook loop
+ * (halo barrier + two reductions) for A-B timing. */
 int fes_solver_set_dist(fes_solver* s, fes_comm* comm, int64_t row_begin, int64_t row_end,
-                        const int32_t* h_send_ptr, const int32_t* h_send_src, const int32_t* h_send_dst);
+                        const int32_t* h_send_ptr, const int32_t* h_send_src, const int32_t* h_send_dst,
+                        int64_t n_free_global);
 
 /* ---- SIMP inner loop ----------------------------------------------------------------------
  * Replaces calculate_smoothing_matrix (ref fem/topology.py:39-77), DensityField.gradient /

@@ -7,6 +7,7 @@ import pytest
 import torch
 
 import fes_oracle as fo
+import window as ow
 from conftest import load_golden
 
 pytestmark = pytest.mark.gpu
@@ -241,6 +242,13 @@ def test_full_size_cantilever_properties():
     Ke_o = fo.ke_elastic(fo.geometry(fo.P1_TRI, sub_v[sub_e[win]]), 200.0, 0.3)
     Ke_g = F.LinearElasticForm(F.LinearElasticMaterial(200.0, 0.3)).element_matrices(V)[win].cpu().numpy()
     close(Ke_g, Ke_o)
+    # the FUSED kernel's rows against the oracle at this size: every row of three node windows (the first
+    # mesh rows with the y = 0 boundary, the middle, the last rows) -- row lengths and column ids
+    # array_equal, values 1e-12 with the floor 1e-12 max|A| (ref tests/test_assembly.py:196-218)
+    nx, n_nodes = 2829, 2829 * 708
+    ke = lambda geo, ids: fo.ke_elastic(geo, 200.0, 0.3)
+    for v0 in (0, (n_nodes // 2 // nx) * nx - 17, n_nodes - 3 * nx):
+        ow.compare_window(A, fo.P1_TRI, 2, sub_v, sub_e, v0, min(v0 + 3 * nx, n_nodes), ke, scale=scale)
 
 
 def test_full_size_p2_properties():
@@ -274,22 +282,38 @@ def test_full_size_p2_properties():
     win = np.arange(500000, 502000)
     geo = fo.geometry(fo.P2_TRI, V.node_coords[V.element_nodes[win]])
     close(Ke[win].cpu().numpy(), fo.ke_elastic(geo, 200.0, 0.3))
+    # the fused kernel's rows (stiffness and mass) against the oracle: windows of vertex nodes (first rows,
+    # middle) and of edge nodes (numbered after the 708^2 vertices)
+    nv = 708 * 708
+    Mm = V.mass_matrix_d
+    for v0, v1 in ((0, 3 * 708), (nv // 2, nv // 2 + 2000), (nv + 700000, nv + 703000), (V.n_nodes - 2500, V.n_nodes)):
+        ow.compare_window(A, fo.P2_TRI, 2, V.node_coords, V.element_nodes, v0, v1,
+                          lambda g, ids: fo.ke_elastic(g, 200.0, 0.3), scale=scale)
+        ow.compare_window(Mm, fo.P2_TRI, 2, V.node_coords, V.element_nodes, v0, v1, lambda g, ids: fo.ke_mass(g, 2))
 
 
 def test_full_size_tet_pattern_properties():
-    """Config 5 scale check on one GPU at 101^3 nodes (6 M tets): pattern counts follow the closed
-    form for a Kuhn mesh and the operator annihilates rigid translations."""
+    """Config 5 on one GPU at its full size, 151^3 nodes = 20 250 000 tets: pattern counts follow the closed
+    form for a Kuhn mesh, the operator annihilates rigid translations, and the fused kernel's rows agree with
+    the oracle on node windows (one node plane at x = 0 with its boundary stencils, half a plane in the
+    middle of the box, the last lines of the box)."""
     F = fes()
-    n = 101
-    mesh = F.create_box_mesh([[0, 0, 0], [1, 1, 1]], (n, n, n))
+    from fes_b200.mesh import box_arrays
+    n = 151
+    verts, elems = box_arrays([[0, 0, 0], [1, 1, 1]], (n, n, n))
+    mesh = F.Mesh(verts, elems, np.zeros((0, 3), dtype=np.int64))   # boundary facets are not needed here
     V = F.FunctionSpace(mesh, n_components=3)
     A = V.assemble_device(F.LinearElasticForm(F.LinearElasticMaterial(200.0, 0.3)))
+    ke = lambda geo, ids: fo.ke_elastic(geo, 200.0, 0.3)
+    smax = float(A.data_d.abs().max())
+    for v0, v1 in ((0, n * n), (n ** 3 // 2, n ** 3 // 2 + n * n // 2), (n ** 3 - 20 * n, n ** 3)):
+        ow.compare_window(A, fo.P1_TET, 3, verts, elems, v0, v1, ke, scale=smax)
     # Kuhn mesh: node pairs = nodes + 2*edges; edges = 3 axis + 3 face-diagonal + 1 body-diagonal families
     m = n - 1
     edges = 3 * n * n * m + 3 * n * m * m + m ** 3
     assert V.plan().n_pairs == n ** 3 + 2 * edges
     assert A.nnz == 9 * V.plan().n_pairs
-    scale = float(A.data_d.abs().max())
+    scale = smax
     for comp in range(3):
         t = torch.zeros(V.n_dofs, dtype=torch.float64, device=A.device); t[comp::3] = 1.0
         assert float(A.matvec(t).abs().max()) < 1e-9 * scale
@@ -319,3 +343,32 @@ def test_partitioned_row_blocks_concatenate_to_the_single_gpu_operator(kind, wor
     np.testing.assert_array_equal(indptr, whole.indptr)
     np.testing.assert_array_equal(np.concatenate(ixs), whole.indices)
     np.testing.assert_array_equal(np.concatenate(datas), whole.data)
+
+
+@pytest.mark.parametrize('case', ['tri_1001x251', 'p2_355', 'tet_41'])
+def test_whole_operator_against_the_oracle_at_survey_sizes(case):
+    """The largest meshes the oracle assembles whole in seconds (BASELINE.md 2.1 sizes): the complete
+    CSR of the fused kernel -- indptr / indices array_equal, every value 1e-12 + floor."""
+    F = fes()
+    mat = F.LinearElasticMaterial(200.0, 0.3)
+    if case == 'tri_1001x251':
+        v, e = fo.rect_mesh([[0, 0], [4, 1]], (1001, 251))
+        V = F.FunctionSpace(F.Mesh(v, e, np.zeros((0, 2), dtype=np.int64)), n_components=2)
+        en, X, okind, c = e, v, fo.P1_TRI, 2
+    elif case == 'p2_355':
+        mesh = F.create_rect_mesh([[0, 0], [1, 1]], (355, 355))
+        V = F.FunctionSpace(mesh, F.QuadraticTriangleElement, n_components=2)
+        en, X, okind, c = V.element_nodes, V.node_coords, fo.P2_TRI, 2
+    else:
+        v, e = fo.box_mesh([[0, 0, 0], [1, 1, 1]], (41, 41, 41))
+        V = F.FunctionSpace(F.Mesh(v, e, np.zeros((0, 3), dtype=np.int64)), n_components=3)
+        en, X, okind, c = e, v, fo.P1_TET, 3
+    geo = fo.geometry(okind, X[en])
+    ref = fo.assemble(en, c, len(X), fo.ke_elastic(geo, 200.0, 0.3))
+    A = V.assemble(F.LinearElasticForm(mat))
+    np.testing.assert_array_equal(A.indptr, ref.indptr)
+    np.testing.assert_array_equal(A.indices, ref.indices)
+    close(A.data, ref.data)
+    if case != 'tet_41':
+        refm = fo.assemble(en, c, len(X), fo.ke_mass(geo, c))
+        close(V.mass_matrix.data, refm.data)
