@@ -137,6 +137,129 @@ def bind_to_gpu_numa_node(index):
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (numpy/scipy restatement of the reference's warm assemble)
 # ---------------------------------------------------------------------------------------------
+def reference_or_port_assembly(kind, res, repeats=2):
+    """Warm assembly rate of the CPU arm on one of BASELINE.json's cases (bounded sizes, stated):
+    the UNMODIFIED reference's FunctionSpace.assemble when its tree is reachable, else the oracle port.
+    kind: 'p1_laplacian' | 'p2_elastic' | 'p2_mass' | 'tet_elastic'."""
+    import fes_oracle as fo
+    import ref_shim
+    t_cold = time.perf_counter()
+    if ref_shim.available():
+        ref_shim.install()
+        from fem.elements import QuadraticTriangleElement
+        from fem.forms import LaplacianForm, LinearElasticForm, MassForm
+        from fem.materials import LinearElasticMaterial
+        from fem.mesh.mesh import Mesh
+        from fem.space import FunctionSpace
+        if kind == 'tet_elastic':
+            v, e = fo.box_mesh([[0, 0, 0], [1, 1, 1]], res)
+            V = FunctionSpace(Mesh(v, e, np.zeros((0, 3), dtype=np.int64)), n_components=3)
+            form = LinearElasticForm(LinearElasticMaterial(E, NU))
+        else:
+            v, e = fo.rect_mesh([[0, 0], [1, 1]], res)
+            mesh = Mesh(v, e, np.zeros((0, 2), dtype=np.int64))
+            if kind == 'p1_laplacian':
+                V, form = FunctionSpace(mesh), LaplacianForm()
+            else:
+                V = FunctionSpace(mesh, QuadraticTriangleElement, n_components=2)
+                form = LinearElasticForm(LinearElasticMaterial(E, NU)) if kind == 'p2_elastic' else MassForm(2)
+        V.assemble(form)
+        cold = time.perf_counter() - t_cold
+        best = min(_timed(lambda: V.assemble(form)) for _ in range(repeats))
+        n_el, impl = len(V.mesh.elements), 'reference'
+    else:
+        if kind == 'tet_elastic':
+            v, e = fo.box_mesh([[0, 0, 0], [1, 1, 1]], res)
+            okind, c = fo.P1_TET, 3
+        else:
+            v, e = fo.rect_mesh([[0, 0], [1, 1]], res)
+            okind, c = fo.P1_TRI, (1 if kind == 'p1_laplacian' else 2)
+            if kind != 'p1_laplacian':
+                e, v, _ = fo.p2_nodes(v, e, fo.boundary_facets(e))
+                okind = fo.P2_TRI
+        geo = fo.geometry(okind, v[e])
+        plan = fo.scatter_plan(e, c, len(v))
+        ke = {'p1_laplacian': lambda: fo.ke_laplacian(geo), 'p2_mass': lambda: fo.ke_mass(geo, 2)}.get(
+            kind, lambda: fo.ke_elastic(geo, E, NU))
+        cold = time.perf_counter() - t_cold
+        best = min(_timed(lambda: plan.scatter(ke())) for _ in range(repeats))
+        n_el, impl = len(e), 'port'
+    return {'elements_per_s': n_el / best, 'elements': int(n_el), 'warm_s': best, 'cold_s': cold, 'kind': impl,
+            'sample': f'{kind} on {"x".join(str(r) for r in res)} nodes, best of {repeats} warm assemblies'}
+
+
+def _timed(fn):
+    t0 = time.perf_counter()
+    fn()
+    return time.perf_counter() - t0
+
+
+def cpu_pcg_twin():
+    """scipy cg(A_ff, b, rtol=1e-10, atol=0, M=diag^-1) -- the algorithmic twin of the GPU Jacobi-PCG and
+    of the reference's _CGSolver call (ref fem/backends.py:201-213) -- on the 504x126-node 4:1 cantilever
+    of BASELINE.md 2.3 (127 008 dofs), operator from the oracle."""
+    import fes_oracle as fo
+    from scipy.sparse.linalg import LinearOperator, cg
+    v, e = fo.rect_mesh(CORNERS, (504, 126))
+    A = fo.assemble(e, 2, len(v), fo.ke_elastic(fo.geometry(fo.P1_TRI, v[e]), E, NU))
+    fixed_nodes = np.flatnonzero(v[:, 0] == 0.0)
+    fixed = (2 * fixed_nodes[:, None] + np.arange(2)).ravel()
+    free = np.setdiff1d(np.arange(2 * len(v)), fixed)
+    b = np.zeros(2 * len(v))
+    tip = np.flatnonzero(v[:, 0] == CORNERS[1][0])
+    b[2 * tip + 1] = -1.0 / (len(tip) - 1)                      # a tip traction; the exact load does not matter here
+    Aff, bf = A[np.ix_(free, free)].tocsr(), b[free]
+    dinv = 1.0 / Aff.diagonal()
+    its = [0]
+    t0 = time.perf_counter()
+    x, info = cg(Aff, bf, rtol=1e-10, atol=0.0, M=LinearOperator(Aff.shape, matvec=lambda r: dinv * r),
+                 callback=lambda xk: its.__setitem__(0, its[0] + 1))
+    dt = time.perf_counter() - t0
+    return {'dofs': int(Aff.shape[0]), 'iterations': its[0], 'seconds': dt, 'us_per_iteration': 1e6 * dt / max(its[0], 1),
+            'info': int(info), 'impl': 'scipy.sparse.linalg.cg with M = diag(A)^-1, one thread',
+            'sample': '504x126-node cantilever (BASELINE.md 2.3), 127 008 dofs'}
+
+
+def cpu_simp_iterations(n_iters, budget_s):
+    """Design iterations of the UNMODIFIED reference's TopologyOptimizer (ref fem/topology.py:291-317) at
+    config 4 (1201x401 nodes, 960 000 triangles) on the host cores: constructor once, then up to n_iters
+    iterations within budget_s.  None when the reference tree is absent."""
+    import ref_shim
+    if not ref_shim.available():
+        return None
+    ref_shim.install()
+    import fes_oracle as fo
+    from fem.boundary import BCType, BoundaryConditions
+    from fem.equations import LinearElastic
+    from fem.mesh.mesh import Mesh
+    from fem.regions import in_box, intersect, on_plane
+    from fem.topology import TopologyOptimizer
+    import fes_b200.mesh as fm
+    w, h = 3.0, 1.0
+    v, e = fo.rect_mesh([[0, 0], [w, h]], (1201, 401))
+    mesh = Mesh(v, e, fm.rect_boundary((1201, 401)))
+    bc = BoundaryConditions()
+    bottom, top = on_plane(1, 0.0), on_plane(1, h)
+    bc.add(BCType.DIRICHLET, intersect(bottom, in_box([None, None], [0.04 * w, None])), [0, 0])
+    bc.add(BCType.DIRICHLET, intersect(bottom, in_box([0.96 * w, None], [None, None])), [None, 0])
+    bc.add(BCType.NEUMANN, intersect(top, in_box([0.4 * w, None], [0.6 * w, None])), [0, -0.5])
+    t0 = time.perf_counter()
+    topo = TopologyOptimizer(mesh, LinearElastic(200.0, 0.4), bc, iters=1, volume_frac=0.5,
+                             smoothing_radius=0.00625, penalty=3.0)
+    ctor = time.perf_counter() - t0
+    times, comps = [], []
+    for _ in range(n_iters):
+        t0 = time.perf_counter()
+        hist = topo.solve()
+        times.append(time.perf_counter() - t0)
+        comps.append(float(np.sum(hist.compliance[-1])))
+        if sum(times) + ctor + times[-1] > budget_s:
+            break
+    return {'iterations_per_s': len(times) / sum(times), 'iterations_timed': len(times), 'seconds_per_iteration': times,
+            'constructor_s': ctor, 'total_compliance': comps, 'kind': 'reference',
+            'impl': 'TopologyOptimizer.solve of the unmodified reference (DirectBackend = SuperLU), one design iteration per call'}
+
+
 def cpu_assemble_rate(sample_res=(1001, 251), repeats=3):
     """Warm `assemble` of the oracle on a bounded sample of the same workload: the scatter plan
     and geometry are built once (as the reference caches them), then element matrices + bincount
@@ -179,6 +302,25 @@ def reference_space(res=RES):
     v, e = fo.rect_mesh(CORNERS, res)
     mesh = Mesh(v, e, np.zeros((0, 2), dtype=np.int64))
     return FunctionSpace(mesh, n_components=2), LinearElasticForm(LinearElasticMaterial(E, NU)), len(e)
+
+
+def cpu_baseline_sample(sample_res=(1001, 251)):
+    """`cpu_baseline` of the GPU arm: a bounded sample of config 2 (500 000 triangles of the same cantilever),
+    the unmodified reference's warm FunctionSpace.assemble when its tree is reachable (kind "reference"),
+    else the oracle port (kind "port").  The full-size figure is `bench.py --impl reference`."""
+    import ref_shim
+    if ref_shim.available():
+        V, form, n_el = reference_space(sample_res)
+        c0, t0 = time.process_time(), time.perf_counter()
+        V.assemble(form)
+        best = min(_timed(lambda: V.assemble(form)) for _ in range(3))
+        wall = time.perf_counter() - t0
+        return {'value': n_el / best, 'unit': UNIT, 'cores': max(1, int(round((time.process_time() - c0) / wall))),
+                'kind': 'reference', 'host_cpus': os.cpu_count(), 'blas_threads': blas_threads(),
+                'sample': f'{n_el} triangles ({sample_res[0]}x{sample_res[1]} nodes of the same cantilever): warm '
+                          'FunctionSpace.assemble(LinearElasticForm) of the unmodified reference, best of 3'}
+    rate, sample = cpu_assemble_rate(sample_res)
+    return {'value': rate, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': sample, 'host_cpus': os.cpu_count()}
 
 
 def run_reference(args):
@@ -255,6 +397,54 @@ def slab_mesh(rank, world):
     return F.create_rect_mesh(corners, (nx, RES[1]))
 
 
+def parity_gate(V, plan, values, mesh):
+    """The parity gate of SURVEY 8(d), inside the bench job: the CSR the timed kernel just wrote is compared
+    with the CPU oracle on three node windows of THIS mesh (first mesh rows with the boundary stencils, the
+    middle, the last rows): row lengths and column indices array_equal, values rtol 1e-12 with the absolute
+    floor 1e-12 max|A| (ref tests/test_assembly.py:196-218).  Any mismatch raises."""
+    import types
+    import fes_oracle as fo
+    import window as ow
+    A = types.SimpleNamespace(indptr_d=plan.indptr_d, indices_d=plan.indices_d, data_d=values)
+    nx, n_nodes = RES[0] if len(mesh.vertices) == RES[0] * RES[1] else len(mesh.vertices) // RES[1], len(mesh.vertices)
+    scale = float(values.abs().max())
+    ke = lambda geo, ids: fo.ke_elastic(geo, E, NU)
+    t0 = time.perf_counter()
+    windows = [ow.compare_window(A, fo.P1_TRI, 2, mesh.vertices, mesh.elements, v0, min(v0 + 3 * nx, n_nodes), ke,
+                                 scale=scale)
+               for v0 in (0, (n_nodes // 2 // nx) * nx - 17, n_nodes - 3 * nx)]
+    return {'status': 'ok', 'against': 'CPU oracle (oracle/window.py), rows of 3 node windows of the timed mesh',
+            'pattern': 'indptr differences and indices array_equal', 'values': 'rtol 1e-12 + 1e-12 max|A|',
+            'rows_compared': int(sum(w['rows'] for w in windows)), 'nnz_compared': int(sum(w['nnz'] for w in windows)),
+            'max_abs_diff': max(w['max_abs_diff'] for w in windows), 'max_abs_value': scale,
+            'seconds': time.perf_counter() - t0}
+
+
+def pinned_copy_probe(n_bytes, dev, world, reps=3):
+    """Plain pinned host<->device copies of the e2e leg's sizes, all ranks at once: what the host fabric gives
+    each GPU when N of them copy concurrently (the e2e leg is bounded by exactly this)."""
+    import torch
+    import torch.distributed as dist
+    h = torch.empty(n_bytes // 8, dtype=torch.float64).pin_memory()
+    d = torch.empty(n_bytes // 8, dtype=torch.float64, device=dev)
+    out = {}
+    for name, (dst, src) in (('d2h', (h, d)), ('h2d', (d, h))):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[f'pinned_{name}_gbs_per_gpu_slowest_rank'] = n_bytes / float(t.item()) / 1e9
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -295,6 +485,8 @@ def run_gpu(args):
 
     for _ in range(args.warmup):
         step()
+    barrier()
+    parity = parity_gate(V, plan, values, mesh) if rank == 0 else None   # raises on any mismatch: no number without parity
     barrier()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -353,6 +545,14 @@ def run_gpu(args):
            'd2h_bytes_per_step': int(plan.nnz * 8), 'ms_per_step': e2e_s * 1e3,
            'api': 'fes_assemble_host (pinned host coordinates in, pinned host CSR values out)',
            'host_cpus_bound_to_gpu_numa_node': local_cpus}
+    del h_values
+    probe = pinned_copy_probe(int(plan.nnz * 8), dev, world)
+    e2e.update(probe)
+    e2e['copy_bound_ms_per_step'] = 1e3 * (plan.nnz * 8 / (probe['pinned_d2h_gbs_per_gpu_slowest_rank'] * 1e9)
+                                           + h_coords.numel() * 8 / (probe['pinned_h2d_gbs_per_gpu_slowest_rank'] * 1e9))
+    e2e['limiter'] = ('host<->device copies: the step is the D2H of the CSR values plus the H2D of the coordinates at the '
+                      'bandwidth the probe measures with all ranks copying at once; the kernel is %.1f %% of the step'
+                      % (100.0 * ms_step / (e2e_s * 1e3)))
 
     out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
            'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
@@ -362,15 +562,14 @@ def run_gpu(args):
                                   + (f'; {world} slabs side by side, one per GPU, ghost-element owner-computes' if world > 1 else ''),
                       'n_elements_per_gpu': n_el, 'nnz_per_gpu': plan.nnz,
                       'l2': 'inputs+outputs per step (0.5 GB) exceed the 126 MB L2; no flush needed'},
-           'roofline': roofline, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks.summary()}
+           'roofline': roofline, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks.summary(),
+           'parity': parity}
 
     extra = {'plan_build_s': plan_s, 'plan_device_bytes': plan.bytes}
     if rank == 0 and world == 1:
-        rate, sample = cpu_assemble_rate()
-        out['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': sample,
-                               'host_cpus': os.cpu_count()}
+        out['cpu_baseline'] = cpu_baseline_sample()
         if not args.no_extra:
-            extra.update(extra_metrics(F, V, mesh, dev))
+            extra.update(extra_metrics(F, V, mesh, dev, args.cpu_budget))
     if not args.no_extra:
         del values
         torch.cuda.empty_cache()
@@ -408,6 +607,7 @@ def config5_metrics(F, world, rank, dev, n=151, pcg_iters=300):
     mesh_l = part.local_mesh(verts, np.concatenate(faces))
     host_s = time.perf_counter() - t0
     n_el_global, n_el_local = len(elems), len(part.local_elements)
+    elems_keep = elems if world == 1 else None       # the one-GPU parity gate needs the connectivity
     del elems
     Vl = F.FunctionSpace(mesh_l, n_components=3)
     form = F.LinearElasticForm(F.LinearElasticMaterial(200.0, 0.3))
@@ -468,11 +668,40 @@ def config5_metrics(F, world, rank, dev, n=151, pcg_iters=300):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     us_iter = 1e6 * float(t.item()) / pcg_iters
+    # parity, where the driver sees it.  N = 1: the rows the timed kernel wrote against the CPU oracle on node
+    # windows of THIS mesh.  N > 1: a reduced box (41^3) solved to rtol 1e-10 on the N ranks and on rank 0
+    # alone -- row blocks array_equal to the one-GPU pattern, solutions within 1e-9 -- see tools/dist_check.py.
+    if world == 1:
+        import types
+        import fes_oracle as fo
+        import window as ow
+        smax = float(A.data_d.abs().max())
+        ke = lambda geo, ids: fo.ke_elastic(geo, 200.0, 0.3)
+        nn = len(verts)
+        wins = [ow.compare_window(A, fo.P1_TET, 3, verts, elems_keep, v0, v1, ke, scale=smax)
+                for v0, v1 in ((0, n * n // 2), (nn // 2, nn // 2 + n * n // 2), (nn - 10 * n, nn))]
+        parity = {'status': 'ok', 'against': 'CPU oracle on 3 node windows of the timed mesh (pattern array_equal, values 1e-12 + floor)',
+                  'rows_compared': int(sum(w['rows'] for w in wins)), 'nnz_compared': int(sum(w['nnz'] for w in wins)),
+                  'max_abs_diff': max(w['max_abs_diff'] for w in wins), 'max_abs_value': smax}
+    else:
+        sys.path.insert(0, os.path.join(ROOT, 'tools'))
+        import dist_check
+        del A, x
+        torch.cuda.empty_cache()
+        rec, ok = dist_check.run_case('tet', 41, rank, world, dev)
+        parity = rec
+        flag = torch.tensor([int(ok)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not bool(flag.item()):
+            raise RuntimeError(f'distributed PCG parity failed: {rec}')
+        if rank == 0:
+            parity = dict(rec, status='ok')
     return {'n_nodes_per_side': n, 'elements': n_el_global, 'elements_per_gpu': n_el_local, 'dofs': 3 * n ** 3,
             'nnz_per_gpu': plan.nnz, 'assembly_ms': asm_ms, 'elements_per_s': n_el_global / (asm_ms * 1e-3),
             'assembly_hbm_frac_of_measured': alg / (asm_ms * 1e-3) / 1e9 / measured_peak()[0],
             'plan_build_s': plan_s, 'host_mesh_partition_s': host_s, 'pcg_us_per_iteration': us_iter,
-            'pcg_iterations_timed': pcg_iters, 'scaling': 'strong'}
+            'pcg_iterations_timed': pcg_iters, 'scaling': 'strong', 'parity': parity,
+            'pcg_loop': 'classic (3 barriers)' if world == 1 else 'overlapped single-reduction (distributed default)'}
 
 
 def assembly_case(F, V, form, reps=20):
@@ -497,20 +726,82 @@ def assembly_case(F, V, form, reps=20):
             'algorithmic_bytes': alg, 'hbm_frac_of_measured': alg / (ms * 1e-3) / 1e9 / measured_peak()[0]}
 
 
-def extra_metrics(F, V, mesh, dev):
+def graph_replay_case(F, V, form, launches=200, replays=5):
+    """Config 1 is 0.7 us of HBM traffic -- below a launch latency -- so its roofline fraction is quoted from a
+    CUDA-graph replay of many reassemblies: `launches` fused assemblies captured once, replayed."""
+    import torch
+    from fes_b200 import _lib
+    plan = V.plan()
+    A = V.assemble_device(form)
+    low = form.lower(V, False)
+    cf = low.coeffs()
+    L = _lib.lib()
+    side = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            V.assemble_device(form, out=A.data_d)
+        side.synchronize()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(launches):
+                _lib.check(L.fes_assemble(plan.handle, V.element_type.KIND, low.form, V.spatial_dim, _lib.ptr(V._en_d),
+                                          _lib.ptr(V._coords_d), C.byref(cf), _lib.ptr(A.data_d), _lib.stream()))
+        g.replay()
+        side.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(side)
+        for _ in range(replays):
+            g.replay()
+        ev1.record(side)
+        side.synchronize()
+    torch.cuda.current_stream().wait_stream(side)
+    ms = ev0.elapsed_time(ev1) / (replays * launches)
+    n_el, N = len(V.element_nodes), V.element_nodes.shape[1]
+    alg = 4 * N * n_el + 8 * V.spatial_dim * V.n_nodes + 8 * plan.nnz
+    return {'ms_per_assembly_graph_replay': ms, 'launches_per_graph': launches, 'replays': replays,
+            'elements_per_s_graph_replay': n_el / (ms * 1e-3),
+            'hbm_frac_of_measured_graph_replay': alg / (ms * 1e-3) / 1e9 / measured_peak()[0],
+            'note': 'the working set (4.8 MB) stays in L2 between replays: a launch-/latency-bound figure, not an HBM one'}
+
+
+def extra_metrics(F, V, mesh, dev, cpu_budget_s=240.0):
     """Secondary numbers of BASELINE.json: configs 1 and 3 (assembly only), the PCG solve of
-    config 2 and SIMP iterations/sec on config 4 (1201x401 nodes, 960 000 triangles, MBB beam)."""
+    config 2 and SIMP iterations/sec on config 4 (1201x401 nodes, 960 000 triangles, MBB beam, all 100
+    design iterations), each with the CPU arm timed beside it in this run (SURVEY 8d i-v; bounded samples,
+    stated) as long as the CPU budget lasts."""
     import torch
     from fes_b200.regions import in_box, intersect, on_plane
     out = {}
+    t_cpu = [0.0]
+
+    def cpu(fn, *a):
+        if t_cpu[0] > cpu_budget_s:
+            return {'skipped': f'CPU budget of {cpu_budget_s:.0f} s spent'}
+        t0 = time.perf_counter()
+        try:
+            r = fn(*a)
+        except Exception as exc:      # reported, never silently dropped
+            r = {'error': f'{type(exc).__name__}: {exc}'[:300]}
+        t_cpu[0] += time.perf_counter() - t0
+        return r
+
     V1 = F.FunctionSpace(F.create_rect_mesh([[0, 0], [1, 1]], (225, 225)))
-    out['config1_p1_laplacian_225x225'] = assembly_case(F, V1, F.LaplacianForm())
+    c1 = assembly_case(F, V1, F.LaplacianForm())
+    try:
+        c1.update(graph_replay_case(F, V1, F.LaplacianForm()))
+    except Exception as exc:
+        c1['graph_replay_error'] = f'{type(exc).__name__}: {exc}'[:300]
+    c1['cpu'] = cpu(reference_or_port_assembly, 'p1_laplacian', (225, 225), 3)
+    out['config1_p1_laplacian_225x225'] = c1
     del V1
     V3 = F.FunctionSpace(F.create_rect_mesh([[0, 0], [1, 1]], (708, 708)), F.QuadraticTriangleElement, n_components=2)
     out['config3_p2_elastic_708x708'] = assembly_case(F, V3, F.LinearElasticForm(F.LinearElasticMaterial(E, NU)))
     out['config3_p2_mass_708x708'] = assembly_case(F, V3, F.MassForm(2))
     del V3
     torch.cuda.empty_cache()
+    out['config3_p2_elastic_708x708']['cpu'] = cpu(reference_or_port_assembly, 'p2_elastic', (355, 355), 1)
+    out['config3_p2_mass_708x708']['cpu'] = cpu(reference_or_port_assembly, 'p2_mass', (355, 355), 1)
     bc = F.BoundaryConditions()
     bc.add(F.BCType.DIRICHLET, on_plane(0, 0.0), [0, 0])
     bc.add(F.BCType.NEUMANN, on_plane(0, 4.0), [0, -1])
@@ -523,11 +814,18 @@ def extra_metrics(F, V, mesh, dev):
     dt = time.perf_counter() - t0
     its = system.solver.last_iterations
     nnz, n = prob.tangent(None).nnz, V.n_dofs
-    out['pcg_config2'] = {'dofs': n, 'iterations': its, 'seconds': dt, 'us_per_iteration': 1e6 * dt / max(its, 1),
+    s_it = dt / max(its, 1)
+    csr_bytes = 12 * nnz + 4 * (n + 1) + 80 * n                       # scalar CSR + 10 vector passes
+    sell_bytes = system.solver.operator_bytes + 14 * 8 * n             # what the kernel reads: block-SELL copy + 14 vector passes
+    out['pcg_config2'] = {'dofs': n, 'iterations': its, 'seconds': dt, 'us_per_iteration': 1e6 * s_it,
                           'relres': system.solver.last_relres,
-                          'hbm_frac_of_measured': ((12 * nnz + 4 * (n + 1) + 80 * n) / (dt / max(its, 1)) / 1e9)
-                          / measured_peak()[0]}
+                          'hbm_frac_of_measured': (csr_bytes / s_it / 1e9) / measured_peak()[0],
+                          'hbm_frac_of_measured_block_sell_bytes': (sell_bytes / s_it / 1e9) / measured_peak()[0],
+                          'bytes_per_iteration_csr_formula': csr_bytes, 'bytes_per_iteration_block_sell': sell_bytes,
+                          'note': 'first figure: SURVEY 8(d) scalar-CSR byte formula; second: the bytes the kernel streams '
+                                  '(9 B per stored value in block-SELL, vectors partly L2-resident)'}
     del system, prob
+    out['pcg_config2']['cpu'] = cpu(cpu_pcg_twin)
     w, h = 3.0, 1.0
     m4 = F.create_rect_mesh([[0, 0], [w, h]], (1201, 401))
     bc = F.BoundaryConditions()
@@ -535,18 +833,31 @@ def extra_metrics(F, V, mesh, dev):
     bc.add(F.BCType.DIRICHLET, intersect(bottom, in_box([None, None], [0.04 * w, None])), [0, 0])
     bc.add(F.BCType.DIRICHLET, intersect(bottom, in_box([0.96 * w, None], [None, None])), [None, 0])
     bc.add(F.BCType.NEUMANN, intersect(top, in_box([0.4 * w, None], [0.6 * w, None])), [0, -0.5])
-    topo = F.TopologyOptimizer(m4, F.LinearElastic(200.0, 0.4), bc, iters=5, volume_frac=0.5,
+    n_it = 100                                                          # config 4 as BASELINE.json states it
+    topo = F.TopologyOptimizer(m4, F.LinearElastic(200.0, 0.4), bc, iters=n_it, volume_frac=0.5,
                                smoothing_radius=0.00625, penalty=3.0, history=None)
-    topo.step()
+    maxiter = 10 * int(topo._mask.sum().item())
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    n_it = 4
-    comps = [topo.step().total_compliance for _ in range(n_it)]
+    comps, lap = [], []
+    for _ in range(n_it):
+        comps.append(topo.step().total_compliance)                      # raises RuntimeError('CG failed ...') at maxiter
+        lap.append(time.perf_counter() - t0)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    cg = topo.cg_iterations
     out['simp_config4'] = {'elements': len(m4.elements), 'iterations_per_s': n_it / dt, 'design_iterations_timed': n_it,
-                           'cg_iterations': topo.cg_iterations, 'total_compliance': comps,
-                           'reference_iterations_per_s_survey': 0.0117}
+                           'seconds_total': dt, 'iterations_per_s_first_10': 10 / lap[9],
+                           'iterations_per_s_last_10': 10 / (lap[-1] - lap[-11]),
+                           'cg_iterations': cg, 'cg_iterations_total': int(sum(cg)), 'cg_iterations_max': int(max(cg)),
+                           'cg_maxiter': maxiter, 'any_solve_hit_maxiter': bool(max(cg) >= maxiter),
+                           'total_compliance_first_last': [comps[0], comps[-1]], 'total_compliance': comps,
+                           'volume_fraction_final': topo._volume_fraction(topo.rho),
+                           'warm_start': True}
+    del topo
+    torch.cuda.empty_cache()
+    out['simp_config4']['cpu'] = cpu(cpu_simp_iterations, 2, max(60.0, cpu_budget_s - t_cpu[0]))
+    out['cpu_seconds_spent_on_baselines'] = t_cpu[0]
     return out
 
 
@@ -558,6 +869,7 @@ if __name__ == '__main__':
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-extra', action='store_true')
     ap.add_argument('--tet-n', type=int, default=151, help='nodes per side of the config-5 tet box')
+    ap.add_argument('--cpu-budget', type=float, default=240.0, help='seconds of host time for the CPU arms in extra')
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != 'reference' else a.warmup
     if a.impl == 'reference':

@@ -54,6 +54,7 @@ SIGNATURES = {
     'fes_solver_create': (_int, [_i64, _p, _p, _p, _p, _p, C.POINTER(_p)]),
     'fes_solver_create_host': (_int, [_i64, _p, _p, _p, C.POINTER(_p)]),
     'fes_solver_destroy': (None, [_p]),
+    'fes_solver_operator_bytes': (_i64, [_p]),
     'fes_solver_use_plan': (_int, [_p, _p]),
     'fes_solver_refresh': (_int, [_p, _p]),
     'fes_solver_solve': (_int, [_p, _p, _p, _dbl, _i64, _int, C.POINTER(_i64), C.POINTER(_dbl), _p]),

@@ -65,6 +65,11 @@ class PCGSolver:
         self._finish(status, iters, relres)
         return x
 
+    @property
+    def operator_bytes(self):
+        """Bytes of the block-SELL operator copy one product reads (0 before the first solve)."""
+        return int(_lib.lib().fes_solver_operator_bytes(self._h))
+
     def refresh(self):
         """The operator's values changed in place (same pattern): rebuild the Jacobi diagonal."""
         _lib.check(_lib.lib().fes_solver_refresh(self._h, _lib.stream()))

@@ -86,7 +86,9 @@ struct fes_solver {
   unsigned recv_mask = 0, send_mask = 0;
   int64_t n_free_global = 0;          // free dofs over all ranks: the default iteration cap must not depend on the rank
   int64_t n_slots_interior = 0;       // SELL slots [0, n_slots_interior) multiply rows that touch no ghost column
-  fes::DevBuf<unsigned long long> halo_done;  // CTAs that finished their halo stores (monotonic; a multiple of the grid between exchanges)
+  int n_ship = 0;
+  fes::DevBuf<int32_t> ship_dof, ship_ptr, ship_rank, ship_dst;
+  fes::DevBuf<uint8_t> shipped;
 };
 
 namespace fes {
@@ -126,7 +128,14 @@ struct PcgArgs {
   int fused;                         // one reduction + two grid barriers per iteration (see k_pcg)
   int timers;                        // FES_PCG_TIMERS: per-phase cycle counters in state->cycles
   int64_t n_slots_interior;          // slots below this bound read no ghost entry (distributed overlap)
-  unsigned long long* halo_done;     // device counter of the barrier-free halo post
+  // overlapped loop: the owned dofs some peer needs, each ONCE, with its (rank, ghost index) targets; the thread
+  // that updates such a dof in the vector phase also stores it into the peers' vectors
+  int n_ship;
+  const int32_t* ship_dof;           // [n_ship] local dof
+  const int32_t* ship_ptr;           // [n_ship + 1] into ship_rank / ship_dst
+  const int32_t* ship_rank;
+  const int32_t* ship_dst;
+  const uint8_t* shipped;            // [n] 1 = the dof is in ship_dof (the plain vector loop skips it)
 };
 
 constexpr long long kSpinLimit = 40000000000LL;  // ~20 s of SM clocks: a lost peer traps instead of hanging
@@ -168,30 +177,20 @@ __device__ __forceinline__ void halo_exchange(const PcgArgs& A, cg::grid_group& 
   __threadfence_system();  // drop stale L1 lines of the ghost entries before the gathers
 }
 
-// The same exchange without a grid barrier, for the overlapped loop: every CTA stores its share of the
-// boundary values into the neighbours' ghost entries, fences, and counts itself done; the CTA that
-// completes the count publishes the epoch to the neighbours.  Nobody waits here -- rows that read ghost
-// entries call halo_wait just before they are multiplied, so the NVLink latency hides under the interior rows.
-__device__ __forceinline__ void halo_post(const PcgArgs& A, const double* vec, unsigned long long epoch, int64_t tid,
-                                          int64_t nth) {
-  const int32_t total = A.send_ptr[A.world];
-  for (int64_t k = tid; k < total; k += nth) {
-    int r = 0;
-    while (k >= A.send_ptr[r + 1]) ++r;
-    double* peer_vec = reinterpret_cast<double*>(A.comm_peer[r] + kCommVec);
-    peer_vec[A.send_dst[k]] = vec[A.send_src[k]];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned long long seen = atomicAdd(A.halo_done, 1ULL) + 1ULL;
-    if (seen % gridDim.x == 0) {  // last CTA of this exchange: every store of every CTA is fenced and counted
-      __threadfence_system();
-      for (int r = 0; r < A.world; ++r)
-        if ((A.send_mask >> r) & 1u)
-          *(reinterpret_cast<volatile unsigned long long*>(A.comm_peer[r] + kCommHaloFlag) + A.rank) = epoch;
-    }
-  }
+// Overlapped loop.  The boundary values of p travel INSIDE the vector phase: the thread that computes the new
+// p of a dof some peer needs stores it straight into the peers' vectors (ship), fences, and runs into the grid
+// barrier that ends the iteration; one thread then publishes the epoch (halo_publish) and nobody waits --
+// the rows that read ghost entries call halo_wait just before they are multiplied, after the interior rows,
+// so the NVLink latency hides under the interior product.  Ghost entries are read through L2 (ld.cg) in
+// those rows: no L1 invalidation is needed on the receiving side.
+__device__ __forceinline__ void ship(const PcgArgs& A, int k, double value) {
+  for (int32_t t = A.ship_ptr[k]; t < A.ship_ptr[k + 1]; ++t)
+    reinterpret_cast<double*>(A.comm_peer[A.ship_rank[t]] + kCommVec)[A.ship_dst[t]] = value;
+}
+
+__device__ __forceinline__ void halo_publish(const PcgArgs& A, unsigned long long epoch) {
+  if (blockIdx.x == 0 && (int)threadIdx.x < A.world && ((A.send_mask >> threadIdx.x) & 1u))
+    *(reinterpret_cast<volatile unsigned long long*>(A.comm_peer[threadIdx.x] + kCommHaloFlag) + A.rank) = epoch;
 }
 
 __device__ __forceinline__ void halo_wait(const PcgArgs& A, unsigned long long epoch) {
@@ -202,7 +201,6 @@ __device__ __forceinline__ void halo_wait(const PcgArgs& A, unsigned long long e
     __threadfence_system();
   }
   __syncthreads();
-  __threadfence_system();  // drop L1 lines that may hold ghost entries fetched before they arrived
 }
 
 // Sum NV values over all ranks through the peers' mailboxes; fixed rank order, so every rank and
@@ -238,7 +236,7 @@ __device__ __forceinline__ bool is_free(const uint8_t* mask, int64_t i) { return
 // RESIDUAL writes b - A vec instead.  MASKED_X treats vec as zero on fixed dofs (warm start).
 // Slots [slot0, slot1) only; with DOTS the six extra sums are ADDED to dots[0..5] (the overlapped loop
 // calls this twice per iteration: interior rows, then the rows that read ghost entries).
-template <int C, bool MASKED_X, bool RESIDUAL, bool DOTS = false>
+template <int C, bool MASKED_X, bool RESIDUAL, bool DOTS = false, bool VEC_L2 = false>
 __device__ __forceinline__ double sparse_product(const PcgArgs& A, int64_t tid, int64_t nth, const double* vec,
                                                  double* y, double* dots = nullptr, int64_t slot0 = 0,
                                                  int64_t slot1 = -1) {
@@ -264,11 +262,12 @@ __device__ __forceinline__ double sparse_product(const PcgArgs& A, int64_t tid, 
       const int32_t col = __ldcs(cp + s * 32);  // the operator streams through L2 (evict-first): the vectors stay resident
       double pw[C];
       if constexpr (C == 2) {
-        const double2 t = *reinterpret_cast<const double2*>(vec + 2 * (int64_t)col);
+        const double2* src = reinterpret_cast<const double2*>(vec + 2 * (int64_t)col);
+        const double2 t = VEC_L2 ? __ldcg(src) : *src;   // VEC_L2: ghost entries were written by a peer, read them at L2
         pw[0] = t.x; pw[1] = t.y;
       } else {
 #pragma unroll
-        for (int j = 0; j < C; ++j) pw[j] = vec[(int64_t)C * col + j];
+        for (int j = 0; j < C; ++j) pw[j] = VEC_L2 ? __ldcg(vec + (int64_t)C * col + j) : vec[(int64_t)C * col + j];
       }
       if (MASKED_X) {
 #pragma unroll
@@ -366,6 +365,14 @@ __global__ void __launch_bounds__(kPcgBlock, (DIST && FUSED) ? FES_PCG_DIST_BLOC
   }
   grid_sum<3>(grid, v3, A.partials, 0, sm);
   if (dist) rank_sum<3>(A, v3, ++red_step);
+  if constexpr (dist && FUSED) {
+    // p0 of the dofs the peers need.  Only now: rank_sum was a barrier across the ranks, so no peer is still
+    // multiplying the warm-start x out of the ghost entries these stores overwrite.  The grid barrier orders
+    // the stores before the first halo_publish.
+    for (int k = (int)tid; k < A.n_ship; k += (int)nth) ship(A, k, A.p[A.ship_dof[k]]);
+    __threadfence_system();
+    grid.sync();
+  }
   const double bb = v3[0];
   double rr = v3[1], rho = v3[2], rho_prev = 1.0;
   long long it = 0;
@@ -399,16 +406,15 @@ __global__ void __launch_bounds__(kPcgBlock, (DIST && FUSED) ? FES_PCG_DIST_BLOC
       tick(5);
       double v7[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       if (dist) {
-        // p is complete on the owned rows (grid barrier at the end of the previous iteration / of the set-up)
+        // the boundary values of p were shipped and fenced before the last grid barrier: publish, do not wait
         ++halo_epoch;
-        halo_post(A, A.p, halo_epoch, tid, nth);
-        tick(1);
+        halo_publish(A, halo_epoch);
         v7[0] = sparse_product<C, false, false, true>(A, tid, nth, A.p, A.q, v7 + 1, 0, A.n_slots_interior);
         if (A.n_slots_interior + (int64_t)blockIdx.x * blockDim.x < A.n_slots) {  // CTA-uniform: this CTA multiplies interface rows
           tick(2);
           halo_wait(A, halo_epoch);
           tick(1);
-          v7[0] += sparse_product<C, false, false, true>(A, tid, nth, A.p, A.q, v7 + 1, A.n_slots_interior, A.n_slots);
+          v7[0] += sparse_product<C, false, false, true, true>(A, tid, nth, A.p, A.q, v7 + 1, A.n_slots_interior, A.n_slots);
         }
       } else {
         v7[0] = sparse_product<C, false, false, true>(A, tid, nth, A.p, A.q, v7 + 1);
@@ -423,7 +429,23 @@ __global__ void __launch_bounds__(kPcgBlock, (DIST && FUSED) ? FES_PCG_DIST_BLOC
       const double rho_next = fmax(fma(alpha, fma(alpha, v7[3], -2.0 * v7[2]), rho_k), 0.0);
       const double rr_next = fmax(fma(alpha, fma(alpha, v7[6], -2.0 * v7[5]), v7[4]), 0.0);
       const double beta = rho_next / rho_k;
+      if (dist) {  // dofs some peer needs: updated once, by the thread that also ships the new p
+        bool sent = false;
+        for (int k = (int)tid; k < A.n_ship; k += (int)nth) {
+          const int32_t i = A.ship_dof[k];
+          const double pi = A.p[i];
+          if (pi != 0.0) A.x[i] = fma(alpha, pi, A.x[i]);
+          const double ri = A.r[i] - alpha * A.q[i];
+          A.r[i] = ri;
+          const double pn = fma(beta, pi, A.dinv[i] * ri);
+          A.p[i] = pn;
+          ship(A, k, pn);
+          sent = true;
+        }
+        if (sent) __threadfence_system();  // peer stores performed before this thread reaches the grid barrier
+      }
       for (int64_t i = lo + tid; i < hi; i += nth) {
+        if (dist && A.shipped[i]) continue;
         const double pi = A.p[i];
         if (pi != 0.0) A.x[i] = fma(alpha, pi, A.x[i]);  // fixed rows (p = 0) keep their prescribed value
         const double ri = A.r[i] - alpha * A.q[i];
@@ -821,6 +843,13 @@ extern "C" int fes_solver_create_host(int64_t n, const int64_t* h_indptr, const 
 
 extern "C" void fes_solver_destroy(fes_solver* s) { delete s; }
 
+// Bytes of the operator copy one product streams (block-SELL values + one column index per block + the
+// row-slot table + slice offsets); 0 before the first solve built it.
+extern "C" int64_t fes_solver_operator_bytes(const fes_solver* s) {
+  if (!s || s->sell_row.p == nullptr) return 0;
+  return s->sell_entries * ((int64_t)8 * s->c * s->c + 4) + s->n_slices * 32 * 4 + (s->n_slices + 1) * 4;
+}
+
 extern "C" int fes_solver_use_plan(fes_solver* s, const fes_plan* plan) {
   if (!s || !plan) return set_error(FES_ERR_VALUE, "fes_solver_use_plan: NULL argument");
   if (plan->n_dofs != s->n || s->indptr != plan->indptr.p)
@@ -898,9 +927,38 @@ extern "C" int fes_solver_set_dist(fes_solver* s, fes_comm* comm, int64_t row_be
   s->comm = comm;
   s->row_begin = row_begin; s->row_end = row_end;
   s->n_free_global = n_free_global;
-  FES_CUDA(s->halo_done.alloc(1));
-  FES_CUDA(cudaMemset(s->halo_done.p, 0, sizeof(unsigned long long)));
   const int world = comm->world;
+  {  // every sent dof once, with all its (rank, ghost index) targets
+    const int32_t total = h_send_ptr[world];
+    std::vector<int32_t> order(total), rank_of(total);
+    for (int r = 0; r < world; ++r)
+      for (int32_t k = h_send_ptr[r]; k < h_send_ptr[r + 1]; ++k) rank_of[k] = r;
+    for (int32_t k = 0; k < total; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return h_send_src[a] < h_send_src[b]; });
+    std::vector<int32_t> dof, ptr, rk(total), dst(total);
+    std::vector<uint8_t> flag(s->n > 0 ? s->n : 1, 0);
+    for (int32_t j = 0; j < total; ++j) {
+      const int32_t k = order[j], i = h_send_src[k];
+      if (i < row_begin || i >= row_end) return set_error(FES_ERR_VALUE, "fes_solver_set_dist: send list names a dof this rank does not own");
+      if (dof.empty() || dof.back() != i) { dof.push_back(i); ptr.push_back(j); flag[i] = 1; }
+      rk[j] = rank_of[k];
+      dst[j] = h_send_dst[k];
+    }
+    ptr.push_back(total);
+    s->n_ship = (int)dof.size();
+    FES_CUDA(s->ship_dof.alloc(dof.size() ? dof.size() : 1));
+    FES_CUDA(s->ship_ptr.alloc(ptr.size()));
+    FES_CUDA(s->ship_rank.alloc(total > 0 ? total : 1));
+    FES_CUDA(s->ship_dst.alloc(total > 0 ? total : 1));
+    FES_CUDA(s->shipped.alloc(flag.size()));
+    if (!dof.empty()) FES_CUDA(cudaMemcpy(s->ship_dof.p, dof.data(), dof.size() * 4, cudaMemcpyHostToDevice));
+    FES_CUDA(cudaMemcpy(s->ship_ptr.p, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice));
+    if (total > 0) {
+      FES_CUDA(cudaMemcpy(s->ship_rank.p, rk.data(), (size_t)total * 4, cudaMemcpyHostToDevice));
+      FES_CUDA(cudaMemcpy(s->ship_dst.p, dst.data(), (size_t)total * 4, cudaMemcpyHostToDevice));
+    }
+    FES_CUDA(cudaMemcpy(s->shipped.p, flag.data(), flag.size(), cudaMemcpyHostToDevice));
+  }
   const int32_t total = h_send_ptr[world];
   FES_CUDA(s->send_ptr.alloc(world + 1));
   FES_CUDA(s->send_src.alloc(total > 0 ? total : 1));
@@ -944,7 +1002,8 @@ extern "C" int fes_solver_solve(fes_solver* s, const double* d_b, double* d_x, d
             // one GPU: the textbook three-barrier loop unless FES_PCG_FUSED is set (A-B knob; measured slower, see
             // k_pcg).  Distributed: the single-reduction overlapped loop unless FES_PCG_DIST_CLASSIC is set.
             dist ? (getenv("FES_PCG_DIST_CLASSIC") ? 0 : 1) : (getenv("FES_PCG_FUSED") ? 1 : 0),
-            getenv("FES_PCG_TIMERS") ? 1 : 0, s->n_slots_interior, s->halo_done.p};
+            getenv("FES_PCG_TIMERS") ? 1 : 0, s->n_slots_interior, s->n_ship, s->ship_dof.p, s->ship_ptr.p,
+            s->ship_rank.p, s->ship_dst.p, s->shipped.p};
   if (dist) {
     if (s->c == 2) FES_TRY((launch_pcg<2, true>(s, a, st)));
     else if (s->c == 3) FES_TRY((launch_pcg<3, true>(s, a, st)));

@@ -155,6 +155,9 @@ int fes_solver_create(int64_t n, const int32_t* d_indptr, const int32_t* d_indic
 int fes_solver_create_host(int64_t n, const int64_t* h_indptr, const int64_t* h_indices,
                            const double* h_data, fes_solver** out);
 void fes_solver_destroy(fes_solver* s);
+/* bytes of the operator copy ONE product streams (block-SELL values, one column index per block,
+ * row-slot table): the measured side of the PCG roofline next to SURVEY 8(d)'s scalar-CSR formula */
+int64_t fes_solver_operator_bytes(const fes_solver* s);
 /* The operator's indptr/indices/data are the plan's CSR (values from fes_assemble): let the
  * SpMV walk node blocks (one column index and one c-wide gather per c x c block). */
 int fes_solver_use_plan(fes_solver* s, const fes_plan* plan);

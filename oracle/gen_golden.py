@@ -183,6 +183,34 @@ def simp_case():
     print('filter/oc written')
 
 
+def simp100_case():
+    """Config 4 as BASELINE.json states it -- 100 design iterations -- on a reduced MBB mesh (61x21 nodes,
+    2400 triangles, r = 2.5 cells): the reference's TopologyOptimizer.solve() trajectory (DirectBackend)."""
+    w, h = 3.0, 1.0
+    res = (61, 21)
+    mesh = create_rect_mesh([[0, 0], [w, h]], res)
+    bc = BoundaryConditions()
+    bottom, top = on_plane(1, 0.0), on_plane(1, h)
+    bc.add(BCType.DIRICHLET, intersect(bottom, in_box([None, None], [0.04 * w, None])), [0, 0])
+    bc.add(BCType.DIRICHLET, intersect(bottom, in_box([0.96 * w, None], [None, None])), [None, 0])
+    bc.add(BCType.NEUMANN, intersect(top, in_box([0.4 * w, None], [0.6 * w, None])), [0, -0.5])
+    r = 2.5 * (w / (res[0] - 1))
+    topo = TopologyOptimizer(mesh, LinearElastic(200.0, 0.4), bc, iters=100, volume_frac=0.5,
+                             smoothing_radius=r, penalty=3.0)
+    hist = topo.solve()
+    rho = np.array(hist.rho + [topo.rho])                 # rho[k] = density going INTO iteration k; rho[100] = final
+    comp = np.array([float(np.sum(c)) for c in hist.compliance])
+    keep = np.array([0, 1, 2, 5, 10, 25, 50, 75, 98, 99])
+    vol = topo.space.element_volumes
+    free, fixed, vals = topo._problem.constraints
+    out = {'free': free, 'fixed': fixed, 'load': topo._problem.load, 'resolution': np.array(res), 'width_height': np.array([w, h]), 'radius': r, 'E0': 200.0, 'nu': 0.4,
+           'penalty': 3.0, 'volume_frac': 0.5, 'total_compliance': comp, 'kept_iterations': keep,
+           'rho_kept': rho[keep], 'rho_next_kept': rho[keep + 1], 'compliance_kept': np.array(hist.compliance)[keep],
+           'volume_fraction': np.array([float((vol * r_).sum() / vol.sum()) for r_ in rho])}
+    np.savez_compressed(os.path.join(OUT, 'simp100.npz'), **out)
+    print('simp100 written; compliance', comp[0], '->', comp[-1])
+
+
 def transient_cases():
     """ThetaMethod on a heat problem (source + nonzero Dirichlet data + Neumann flux) and NewmarkMethod on
     a wave problem, both with the reference's DirectBackend (ref fem/integrators.py)."""
@@ -391,6 +419,7 @@ if __name__ == '__main__':
     assembly_case('p2tri', create_rect_mesh([[0, 0], [1.5, 1]], (5, 4)), QuadraticTriangleElement)
     solve_cases()
     simp_case()
+    simp100_case()
     transient_cases()
     adjoint_cases()
     fields_cases()

@@ -123,3 +123,44 @@ def test_simp_dilution_and_scaled_modulus():
     solid = F.LinearElasticForm(F.LinearElasticMaterial(200.0, 0.3)).element_matrices(V).cpu().numpy()
     diluted = F.LinearElasticForm(F.LinearElasticMaterial(rho ** 3 * 200.0, 0.3)).element_matrices(V).cpu().numpy()
     np.testing.assert_allclose(rho[:, None, None] ** 3 * solid, diluted, rtol=1e-12, atol=1e-12 * np.abs(solid).max())
+
+
+def _mbb100(F, g, **kw):
+    from fes_b200.regions import in_box, intersect, on_plane
+    w, h = (float(x) for x in g['width_height'])
+    mesh = F.create_rect_mesh([[0, 0], [w, h]], tuple(int(r) for r in g['resolution']))
+    bc = F.BoundaryConditions()
+    bottom, top = on_plane(1, 0.0), on_plane(1, h)
+    bc.add(F.BCType.DIRICHLET, intersect(bottom, in_box([None, None], [0.04 * w, None])), [0, 0])
+    bc.add(F.BCType.DIRICHLET, intersect(bottom, in_box([0.96 * w, None], [None, None])), [None, 0])
+    bc.add(F.BCType.NEUMANN, intersect(top, in_box([0.4 * w, None], [0.6 * w, None])), [0, -0.5])
+    return F.TopologyOptimizer(mesh, F.LinearElastic(float(g['E0']), float(g['nu'])), bc, iters=100,
+                               volume_frac=float(g['volume_frac']), smoothing_radius=float(g['radius']),
+                               penalty=float(g['penalty']), **kw)
+
+
+def test_simp_100_iterations_against_the_reference_run():
+    """Config 4 as BASELINE.json states it (100 design iterations, ref fem/topology.py:291-317) on the reduced MBB
+    mesh of tests/golden/simp100.npz, against the reference's own run with its direct solver:
+      (i)  FREE-RUNNING: total compliance of every one of the 100 iterations within 1e-8 relative, the volume
+           fraction held, no solve at the iteration cap;
+      (ii) TEACHER-FORCED at iterations 0 ... 99 (void elements at rho = 1e-6 from ~10 on): rho_{k+1} within 1e-9,
+           per-element compliance within 1e-8 of its maximum (checks i-iv)."""
+    F = fes()
+    g = load_golden('simp100')
+    topo = _mbb100(F, g, backend=F.JacobiPCGBackend(rtol=1e-12), history=None)
+    free, fixed, vals = topo._problem.constraints                      # the same problem the reference resolved
+    np.testing.assert_array_equal(free, g['free'])
+    np.testing.assert_array_equal(fixed, g['fixed'])
+    np.testing.assert_allclose(topo._problem.load, g['load'], rtol=1e-13, atol=1e-16)
+    comps = [topo.step().total_compliance for _ in range(100)]
+    np.testing.assert_allclose(comps, g['total_compliance'], rtol=1e-8)
+    assert abs(topo._volume_fraction(topo.rho) - 0.5) < 1e-6
+    assert max(topo.cg_iterations) < 10 * int(topo._mask.sum().item())
+    forced = _mbb100(F, g, backend=F.JacobiPCGBackend(rtol=1e-12), warm_start=False, history=None)
+    for j, k in enumerate(g['kept_iterations']):
+        forced.set_rho(g['rho_kept'][j])
+        sol = forced.step()
+        assert sol.total_compliance == pytest.approx(g['total_compliance'][k], rel=1e-8)
+        np.testing.assert_allclose(sol.compliance, g['compliance_kept'][j], atol=1e-8 * g['compliance_kept'][j].max())
+        np.testing.assert_allclose(forced.rho, g['rho_next_kept'][j], rtol=1e-9, atol=1e-9)
