@@ -80,6 +80,7 @@ SIGNATURES = {
     'fes_element_loads': (_int, [_int, _int, _int, _p, _i64, _p, _p, _int, _p, _p]),
     'fes_weighted_gradient_matrices': (_int, [_int, _int, _int, _int, _p, _i64, _p, _p, _p, _p, _p]),
     'fes_elastic_fields': (_int, [_int, _p, _i64, _p, _p, _p, _dbl, _dbl, _int, _p, _p, _p, _p]),
+    'fes_elastic_stress_field': (_int, [_int, _p, _i64, _p, _p, _p, _dbl, _dbl, _int, _p, _p]),
     'fes_scalar_gradient': (_int, [_int, _int, _int, _p, _i64, _p, _p, _p, _p]),
     'fes_von_mises_gradient': (_int, [_int, _p, _i64, _p, _p, _p, _dbl, _dbl, _int, _p, _p, _p]),
 }

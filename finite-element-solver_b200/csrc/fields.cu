@@ -335,6 +335,60 @@ k_elastic_fields(const int32_t* __restrict__ en, int64_t n_el, const double* __r
   if (compliance) compliance[e] = comp * vol;
 }
 
+// ---- Cauchy stress at EVERY quadrature point (ref fem/forms.py:376-398, LinearElasticForm.stress_field) ------
+// (n_el, n_qp, SD, SD), in-plane only (no plane-strain lift): the spatially resolved counterpart of the
+// per-element tensors above; a P2 displacement has a strain that varies linearly within the element.
+template <int ELEM, int SD>
+__global__ void __launch_bounds__(kBlock)
+k_stress_field(const int32_t* __restrict__ en, int64_t n_el, const double* __restrict__ coords,
+               const double* __restrict__ u, const double* __restrict__ d_E, double E, double nu, Rule rule,
+               double* __restrict__ stress) {
+  constexpr int RD = ET<ELEM>::RD, N = ET<ELEM>::N;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_el) return;
+  double X[RD + 1][SD];
+  load_corners<ELEM, SD>(en + e * N, coords, X);
+  Geom<RD, SD> g;
+  make_geom<RD, SD>(X, g);
+  const Material m = lame(d_E ? __ldg(d_E + e) : E, nu);
+  double ue[N][SD];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    const int64_t v = en[e * N + n];
+#pragma unroll
+    for (int i = 0; i < SD; ++i) ue[n][i] = __ldg(u + v * SD + i);
+  }
+  for (int q = 0; q < rule.nq; ++q) {
+    double d[N][RD];
+    dshape_at<ELEM>(rule.pts[q], d);
+    double H[SD][SD];  // H[i][x] = d u_i / d x_x at this point
+#pragma unroll
+    for (int i = 0; i < SD; ++i)
+#pragma unroll
+      for (int x = 0; x < SD; ++x) H[i][x] = 0.0;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+#pragma unroll
+      for (int x = 0; x < SD; ++x) {
+        double gx = 0.0;
+#pragma unroll
+        for (int r = 0; r < RD; ++r) gx += d[n][r] * g.Jinv[r][x];
+#pragma unroll
+        for (int i = 0; i < SD; ++i) H[i][x] += ue[n][i] * gx;
+      }
+    }
+    double tr = 0.0;
+#pragma unroll
+    for (int i = 0; i < SD; ++i) tr += H[i][i];
+    double* out = stress + (e * rule.nq + q) * (SD * SD);
+#pragma unroll
+    for (int i = 0; i < SD; ++i)
+#pragma unroll
+      for (int j = 0; j < SD; ++j)
+        out[i * SD + j] = (i == j) ? (m.lam * tr + 2.0 * m.mu * H[i][i]) : m.mu * (H[i][j] + H[j][i]);
+  }
+}
+
 // ---- gradient of a scalar nodal field at the first quadrature point (ref fem/space.py:511-517) ------------
 template <int ELEM, int SD>
 __global__ void __launch_bounds__(kBlock)
@@ -466,6 +520,26 @@ extern "C" int fes_elastic_fields(int elem_kind, const int32_t* en, int64_t n_el
     k_elastic_fields<FES_P1_TET, 3><<<g, kBlock, 0, st>>>(en, n_el, coords, d_u, d_E, E, nu, r, d_strain, d_stress, d_compliance);
   else if (elem_kind == FES_P2_TRI)
     k_elastic_fields<FES_P2_TRI, 2><<<g, kBlock, 0, st>>>(en, n_el, coords, d_u, d_E, E, nu, r, d_strain, d_stress, d_compliance);
+  else
+    return set_error(FES_ERR_UNSUPPORTED, "no elastic constitutive matrix for element kind %d", elem_kind);
+  FES_LAUNCH_CHECK();
+  return FES_OK;
+}
+
+extern "C" int fes_elastic_stress_field(int elem_kind, const int32_t* en, int64_t n_el, const double* coords,
+                                        const double* d_u, const double* d_E, double E, double nu, int min_degree,
+                                        double* d_stress, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  Rule r;
+  FES_TRY(rule_for(elem_kind, min_degree, r));
+  if (n_el == 0) return FES_OK;
+  const int g = grid_for(n_el, kBlock);
+  if (elem_kind == FES_P1_TRI)
+    k_stress_field<FES_P1_TRI, 2><<<g, kBlock, 0, st>>>(en, n_el, coords, d_u, d_E, E, nu, r, d_stress);
+  else if (elem_kind == FES_P1_TET)
+    k_stress_field<FES_P1_TET, 3><<<g, kBlock, 0, st>>>(en, n_el, coords, d_u, d_E, E, nu, r, d_stress);
+  else if (elem_kind == FES_P2_TRI)
+    k_stress_field<FES_P2_TRI, 2><<<g, kBlock, 0, st>>>(en, n_el, coords, d_u, d_E, E, nu, r, d_stress);
   else
     return set_error(FES_ERR_UNSUPPORTED, "no elastic constitutive matrix for element kind %d", elem_kind);
   FES_LAUNCH_CHECK();

@@ -103,6 +103,26 @@ class LinearElasticForm(_Form):
             space.element_type.default_quadrature_degree(), _lib.ptr(eps), _lib.ptr(sig), _lib.ptr(comp), _lib.stream()))
         return ElasticFields(eps, sig, comp)
 
+    def stress_field(self, space, u, degree=None):
+        """(n_elements, n_qp, d, d) in-plane Cauchy stress at every quadrature point of the space's rule
+        (ref fem/forms.py:376-398; `degree` picks another tabulated rule, as geometry_at does).  Device tensor."""
+        m = self.material
+        n_el, sd = len(space.element_nodes), space.spatial_dim
+        ud = u if isinstance(u, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(u, dtype=np.float64))
+        ud = ud.to(device=space.device, dtype=torch.float64).contiguous().reshape(-1)
+        if ud.numel() != space.n_nodes * sd:
+            raise ValueError(f'expected {space.n_nodes * sd} displacement DOFs, got {ud.numel()}')
+        degree = space.element_type.default_quadrature_degree() if degree is None else int(degree)
+        n_qp = int(_lib.lib().fes_quadrature_size(space.element_type.KIND, degree))
+        if n_qp == 0:
+            raise NotImplementedError(f'no tabulated rule of degree >= {degree} for {space.element_type.__name__}')
+        E_elem = _per_element(m.E, n_el, space.device, 'per-element modulus') if m.per_element() else None
+        sig = torch.empty((n_el, n_qp, sd, sd), dtype=torch.float64, device=space.device)
+        _lib.check(_lib.lib().fes_elastic_stress_field(
+            space.element_type.KIND, _lib.ptr(space._en_d), n_el, _lib.ptr(space._coords_d), _lib.ptr(ud),
+            _lib.ptr(E_elem), 0.0 if m.per_element() else float(m.E), float(m.nu), degree, _lib.ptr(sig), _lib.stream()))
+        return sig
+
 
 @dataclass(frozen=True, eq=False)
 class ScaledForm(_Form):

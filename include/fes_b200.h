@@ -256,6 +256,12 @@ int fes_weighted_gradient_matrices(int elem_kind, int spatial_dim, int n_comp, i
 int fes_elastic_fields(int elem_kind, const int32_t* d_elem_nodes, int64_t n_el, const double* d_coords,
                        const double* d_u, const double* d_E, double E, double nu, int min_degree,
                        double* d_strain, double* d_stress, double* d_compliance, void* stream);
+/* LinearElasticForm.stress_field (ref fem/forms.py:376-398): the in-plane Cauchy stress at EVERY point of the
+ * cheapest rule of degree >= min_degree, d_stress (n_el, n_qp, sd, sd) row-major, n_qp = fes_quadrature_size;
+ * no plane-strain lift.  d_E NULL -> the scalar modulus E. */
+int fes_elastic_stress_field(int elem_kind, const int32_t* d_elem_nodes, int64_t n_el, const double* d_coords,
+                             const double* d_u, const double* d_E, double E, double nu, int min_degree,
+                             double* d_stress, void* stream);
 /* FunctionSpace.gradient (ref fem/space.py:511-517): (n_el, spatial_dim) gradient of a scalar nodal field at the
  * first point of the rule (constant per element for P1). */
 int fes_scalar_gradient(int elem_kind, int spatial_dim, int min_degree, const int32_t* d_elem_nodes, int64_t n_el,

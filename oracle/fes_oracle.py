@@ -526,6 +526,26 @@ def elastic_fields(geo, u, elem_nodes, E, nu):
     return eps, sig, comp
 
 
+def stress_field(geo, u, elem_nodes, E, nu):
+    """(n_el, n_qp, d, d) in-plane Cauchy stress at every quadrature point of `geo`'s rule, no plane-strain
+    lift (ref: fem/forms.py:376-398)."""
+    dim = _REF_DIM[geo.kind]
+    n_el = len(elem_nodes)
+    ue = element_vectors(u, elem_nodes, dim)
+    mu, lam = lame(np.broadcast_to(np.asarray(E, float), (n_el,)), nu)
+    D = mu[:, None, None] * hooke(dim, 1.0, 0.0) + lam[:, None, None] * hooke(dim, 0.0, 1.0)
+    n_qp = geo.grad.shape[1]
+    out = np.zeros((n_el, n_qp, dim, dim))
+    shear = [(0, 1)] if dim == 2 else [(0, 1), (1, 2), (0, 2)]
+    for q in range(n_qp):
+        sv = np.einsum('est,et->es', D, np.einsum('esk,ek->es', voigt_B(geo.grad[:, q]), ue))
+        for i in range(dim):
+            out[:, q, i, i] = sv[:, i]
+        for o, (i, j) in enumerate(shear):
+            out[:, q, i, j] = out[:, q, j, i] = sv[:, dim + o]
+    return out
+
+
 def von_mises(sig):
     dev = sig - (np.trace(sig, axis1=1, axis2=2) / 3.0)[:, None, None] * np.eye(3)
     return np.sqrt(1.5 * np.einsum('eij,eij->e', dev, dev))

@@ -409,6 +409,10 @@ def fields_cases():
             fields = LinearElasticForm(LinearElasticMaterial(E, 0.3)).derived_fields(Vd.geometry, ue)
             out[f'{name}_strain_{tag}'], out[f'{name}_stress_{tag}'] = fields.strain, fields.stress
             out[f'{name}_compliance_{tag}'] = fields.compliance
+            # stress at every quadrature point (ref fem/forms.py:376-398): the space's own rule, and a richer one
+            form = LinearElasticForm(LinearElasticMaterial(E, 0.3))
+            out[f'{name}_stressfield_{tag}'] = form.stress_field(Vd.geometry, ue)
+            out[f'{name}_stressfield2_{tag}'] = form.stress_field(Vd.geometry_at(2), ue)
     np.savez_compressed(os.path.join(OUT, 'fields.npz'), **out)
     print('fields cases written')
 

@@ -93,6 +93,23 @@ def test_derived_fields(name, tag):
     np.testing.assert_allclose(fields.compliance.cpu().numpy(), G[f'{name}_compliance_{tag}'], rtol=1e-12, atol=1e-16)
 
 
+@pytest.mark.parametrize('name', ['tri', 'p2tri', 'tet'])
+@pytest.mark.parametrize('tag', ['uni', 'var'])
+def test_stress_field_per_quadrature_point(name, tag):
+    """LinearElasticForm.stress_field (ref fem/forms.py:376-398): (n_el, n_qp, d, d) at the space's rule and at
+    the degree-2 rule, against the reference's outputs; the first point of the default rule is the in-plane
+    block of derived_fields' stress."""
+    F, d, V1, Vd = spaces(name)
+    E = 200.0 if tag == 'uni' else G[f'{name}_E_var']
+    form = F.LinearElasticForm(F.LinearElasticMaterial(E, 0.3))
+    s0 = form.stress_field(Vd, G[f'{name}_u']).cpu().numpy()
+    assert s0.shape == G[f'{name}_stressfield_{tag}'].shape
+    np.testing.assert_allclose(s0, G[f'{name}_stressfield_{tag}'], rtol=1e-12, atol=1e-12)
+    s2 = form.stress_field(Vd, G[f'{name}_u'], degree=2).cpu().numpy()
+    np.testing.assert_allclose(s2, G[f'{name}_stressfield2_{tag}'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(s0[:, 0], G[f'{name}_stress_{tag}'][:, :d, :d], rtol=1e-12, atol=1e-12)
+
+
 def test_node_scatter_is_bincount_bit_for_bit():
     """A million random element values on a shuffled mesh: the device gather equals np.bincount exactly."""
     import torch

@@ -79,3 +79,16 @@ def test_derived_fields_match_reference(name, tag):
     np.testing.assert_allclose(eps, G[f'{name}_strain_{tag}'], rtol=1e-12, atol=1e-15)
     np.testing.assert_allclose(sig, G[f'{name}_stress_{tag}'], rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(comp, G[f'{name}_compliance_{tag}'], rtol=1e-12, atol=1e-16)
+
+
+@pytest.mark.parametrize('name', ['tri', 'p2tri', 'tet'])
+@pytest.mark.parametrize('tag', ['uni', 'var'])
+def test_stress_field_per_quadrature_point_matches_reference(name, tag):
+    """LinearElasticForm.stress_field (ref fem/forms.py:376-398) at the space's rule and at degree 2."""
+    en, X = G[f'{name}_element_nodes'], G[f'{name}_node_coords']
+    E = 200.0 if tag == 'uni' else G[f'{name}_E_var']
+    for key, geo in ((f'{name}_stressfield_{tag}', fo.geometry(KIND[name], X[en])),
+                     (f'{name}_stressfield2_{tag}', fo.geometry(KIND[name], X[en], 2))):
+        got = fo.stress_field(geo, G[f'{name}_u'], en, E, 0.3)
+        assert got.shape == G[key].shape
+        np.testing.assert_allclose(got, G[key], rtol=1e-12, atol=1e-12)
