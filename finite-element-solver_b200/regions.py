@@ -9,24 +9,32 @@ fall back to the reference's per-point loop if that does not produce the right s
 import numpy as np
 
 
+# the reference's coordinate tolerance (ref fem/regions.py:26): it only absorbs round-off of linspace / midpoint
+# arithmetic -- 0.4 * 3.0 is not the coordinate 1.2 of a mesh vertex without it
+DEFAULT_ATOL = 1e-9
+
+
 def everywhere():
     return lambda X: np.ones(len(X), dtype=bool)
 
 
-def on_plane(axis, value, tol=1e-9):
-    return lambda X: np.abs(np.asarray(X)[:, axis] - value) < tol
+def on_plane(axis, value, atol=DEFAULT_ATOL):
+    """Points whose `axis` coordinate equals `value` within atol, inclusive (ref fem/regions.py:35-38)."""
+    return lambda X: np.abs(np.asarray(X)[:, axis] - value) <= atol
 
 
-def in_box(lower, upper):
+def in_box(lower, upper, atol=DEFAULT_ATOL):
+    """Points inside an axis-aligned box, inclusive within atol; None leaves a side unbounded
+    (ref fem/regions.py:41-58)."""
     def region(X):
         X = np.asarray(X)
         m = np.ones(len(X), dtype=bool)
         for k, lo in enumerate(lower):
             if lo is not None:
-                m &= X[:, k] >= lo
+                m &= X[:, k] >= lo - atol
         for k, hi in enumerate(upper):
             if hi is not None:
-                m &= X[:, k] <= hi
+                m &= X[:, k] <= hi + atol
         return m
     return region
 

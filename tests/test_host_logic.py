@@ -91,6 +91,26 @@ def test_boundary_resolution_matches_reference():
     np.testing.assert_array_equal(r.fixed_values, s['vals'])
 
 
+def test_region_tolerance_matches_reference():
+    """The reference's regions absorb round-off with atol = 1e-9, inclusive (ref fem/regions.py:26-58):
+    0.4 * 3.0 = 1.2000000000000002 must still select the mesh vertex at x = 1.2.  The 61x21 MBB problem of
+    tests/golden/simp100.npz (constraints and load written by the reference) has such edges."""
+    g = load_golden('simp100')
+    w, h = (float(x) for x in g['width_height'])
+    mesh = create_rect_mesh([[0, 0], [w, h]], tuple(int(r) for r in g['resolution']))
+    bc = BoundaryConditions()
+    bottom, top = on_plane(1, 0.0), on_plane(1, h)
+    bc.add(BCType.DIRICHLET, intersect(bottom, in_box([None, None], [0.04 * w, None])), [0, 0])
+    bc.add(BCType.DIRICHLET, intersect(bottom, in_box([0.96 * w, None], [None, None])), [None, 0])
+    bc.add(BCType.NEUMANN, intersect(top, in_box([0.4 * w, None], [0.6 * w, None])), [0, -0.5])
+    r = bc.resolve(mesh, 2)
+    np.testing.assert_array_equal(r.free_idxs, g['free'])
+    np.testing.assert_array_equal(r.fixed_idxs, g['fixed'])
+    loaded_nodes = np.flatnonzero(g['load'].reshape(-1, 2)[:, 1])
+    assert r.neumann[0].facet_mask.sum() == len(loaded_nodes) - 1     # a contiguous strip of facets
+    assert in_box([1.2000000000000002], [None])(np.array([[1.2]]))[0] and on_plane(0, 1.0)(np.array([[1.0 + 5e-10]]))[0]
+
+
 def test_boundary_condition_guardrails():
     mesh = create_rect_mesh([[0, 0], [1, 1]], (4, 4))
     bc = BoundaryConditions()
