@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libfes_b200.so')
+LIB_PATH = os.environ.get('FES_B200_LIB') or os.path.join(_HERE, 'libfes_b200.so')   # env: A-B builds of the same library (tuning)
 
 OK, ERR_VALUE, ERR_CUDA, ERR_UNSUPPORTED, ERR_CG, ERR_NCCL = 0, -1, -2, -3, -4, -5
 P1_LINE, P1_TRI, P1_TET, P2_LINE, P2_TRI = 0, 1, 2, 3, 4

@@ -42,12 +42,13 @@ struct PcgState {
 
 // Peer-memory communicator: one cudaMalloc'd region per rank, exported over CUDA IPC.
 //   [0,128)      u64 halo_flag[16]   peer r stores its halo epoch here after writing my ghosts
-//   [128,256)    u64 red_flag[16]    peer r stores the reduction step here after filling its box
-//   [256,4352)   double red_box[4][16][8]   ring of reduction mailboxes, [step & 3][src rank][value]
-//   [4352,4368)  u64 counters[2]     this rank's halo epoch / reduction step (persist across solves)
-//   [8192,...)   double p[max_dofs]  the CG direction vector; peers write its ghost entries
+//   [256,8448)   {double value; u64 step} red_box[4][16][8]   ring of reduction mailboxes, [step & 3][src rank][value]:
+//                every value travels with the step it belongs to in ONE 16-byte store, so a reader needs no
+//                flag and the writer no fence -- a reduction costs one NVLink one-way latency, not 1.5 round trips
+//   [8448,8464)  u64 counters[2]     this rank's halo epoch / reduction step (persist across solves)
+//   [16384,...)  double p[max_dofs]  the CG direction vector; peers write its ghost entries
 constexpr int kCommMaxWorld = 16, kBoxVals = 8;
-constexpr size_t kCommHaloFlag = 0, kCommRedFlag = 128, kCommRedBox = 256, kCommCounters = 4352, kCommVec = 8192;
+constexpr size_t kCommHaloFlag = 0, kCommRedBox = 256, kCommCounters = 8448, kCommVec = 16384;
 
 struct fes_comm {
   int rank = 0, world = 1;
@@ -126,6 +127,7 @@ struct PcgArgs {
   const int32_t* send_dst;           // dof index in the receiver's local numbering
   unsigned recv_mask, send_mask;     // bit r: this rank receives from / sends to rank r
   int fused;                         // one reduction + two grid barriers per iteration (see k_pcg)
+  int overlap;                       // distributed three-phase loop: halo shipped inside the p update, interior rows first
   int timers;                        // FES_PCG_TIMERS: per-phase cycle counters in state->cycles
   int64_t n_slots_interior;          // slots below this bound read no ghost entry (distributed overlap)
   // overlapped loop: the owned dofs some peer needs, each ONCE, with its (rank, ghost index) targets; the thread
@@ -189,8 +191,12 @@ __device__ __forceinline__ void ship(const PcgArgs& A, int k, double value) {
 }
 
 __device__ __forceinline__ void halo_publish(const PcgArgs& A, unsigned long long epoch) {
-  if (blockIdx.x == 0 && (int)threadIdx.x < A.world && ((A.send_mask >> threadIdx.x) & 1u))
-    *(reinterpret_cast<volatile unsigned long long*>(A.comm_peer[threadIdx.x] + kCommHaloFlag) + A.rank) = epoch;
+  // lanes of the LAST warp of CTA 0 publish (thread 0 of every CTA is the one that waits)
+  const int r = (int)threadIdx.x - ((int)blockDim.x - 32);
+  if (blockIdx.x == 0 && r >= 0 && r < A.world && ((A.send_mask >> r) & 1u)) {
+    *(reinterpret_cast<volatile unsigned long long*>(A.comm_peer[r] + kCommHaloFlag) + A.rank) = epoch;
+    __threadfence_system();  // push the flag out now instead of whenever the write buffer drains
+  }
 }
 
 __device__ __forceinline__ void halo_wait(const PcgArgs& A, unsigned long long epoch) {
@@ -205,29 +211,46 @@ __device__ __forceinline__ void halo_wait(const PcgArgs& A, unsigned long long e
 
 // Sum NV values over all ranks through the peers' mailboxes; fixed rank order, so every rank and
 // every CTA computes the same bits.  v holds this rank's totals on entry (valid in every thread).
-template <int NV>
-__device__ __forceinline__ void rank_sum(const PcgArgs& A, double (&v)[NV], unsigned long long step) {
-  static_assert(NV <= kBoxVals, "reduction mailbox too small");
-  if (blockIdx.x == 0 && (int)threadIdx.x < A.world) {
-    unsigned char* peer = A.comm_peer[threadIdx.x];
-    volatile double* box = reinterpret_cast<volatile double*>(peer + kCommRedBox) + ((step & 3) * kCommMaxWorld + A.rank) * kBoxVals;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) box[k] = v[k];
-    __threadfence_system();
-    *(reinterpret_cast<volatile unsigned long long*>(peer + kCommRedFlag) + A.rank) = step;
+__device__ __forceinline__ void st_tagged(unsigned char* slot, double value, unsigned long long step) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"((unsigned long long)__double_as_longlong(value)),
+               "l"(step)
+               : "memory");
+}
+__device__ __forceinline__ double ld_tagged(const unsigned char* slot, unsigned long long step) {
+  unsigned long long bits, tag;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(bits), "=l"(tag) : "l"(slot) : "memory");
+    if (tag == step) break;
+    if (clock64() - t0 > kSpinLimit) {
+      printf("fes_b200: peer reduction timed out (tag %llu, want %llu)\n", tag, step);
+      __trap();
+    }
   }
-  if (threadIdx.x == 0) {
+  return __longlong_as_double((long long)bits);
+}
+
+template <int NV>
+__device__ __forceinline__ void rank_sum(const PcgArgs& A, double (&v)[NV], unsigned long long step, double* sm) {
+  static_assert(NV <= kBoxVals, "reduction mailbox too small");
+  const size_t ring = ((step & 3) * kCommMaxWorld) * kBoxVals * 16;
+  if (blockIdx.x == 0 && (int)threadIdx.x < A.world * NV) {  // thread (r, k): value k into rank r's mailbox for this rank
+    const int r = (int)threadIdx.x / NV, k = (int)threadIdx.x - r * NV;
+    double mine = v[0];
+#pragma unroll
+    for (int j = 1; j < NV; ++j) mine = (k == j) ? v[j] : mine;
+    st_tagged(A.comm_peer[r] + kCommRedBox + ring + ((size_t)A.rank * kBoxVals + k) * 16, mine, step);
+  }
+  __syncthreads();  // sm may still be read by the block reduction that produced v
+  if ((int)threadIdx.x < NV) {  // thread k sums value k over the ranks in rank order: the same bits everywhere
+    double t = 0.0;
     for (int r = 0; r < A.world; ++r)
-      spin_until(reinterpret_cast<volatile unsigned long long*>(A.comm + kCommRedFlag) + r, step);
+      t += ld_tagged(A.comm + kCommRedBox + ring + ((size_t)r * kBoxVals + threadIdx.x) * 16, step);
+    sm[threadIdx.x] = t;
   }
   __syncthreads();
-  const volatile double* mine = reinterpret_cast<const volatile double*>(A.comm + kCommRedBox) + (step & 3) * kCommMaxWorld * kBoxVals;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    double t = 0.0;
-    for (int r = 0; r < A.world; ++r) t += mine[r * kBoxVals + k];
-    v[k] = t;
-  }
+  for (int k = 0; k < NV; ++k) v[k] = sm[k];
 }
 
 __device__ __forceinline__ bool is_free(const uint8_t* mask, int64_t i) { return mask == nullptr || mask[i] != 0; }
@@ -364,7 +387,7 @@ __global__ void __launch_bounds__(kPcgBlock, (DIST && FUSED) ? FES_PCG_DIST_BLOC
     v3[2] += ri * ri * A.dinv[i];
   }
   grid_sum<3>(grid, v3, A.partials, 0, sm);
-  if (dist) rank_sum<3>(A, v3, ++red_step);
+  if (dist) rank_sum<3>(A, v3, ++red_step, sm);
   if constexpr (dist && FUSED) {
     // p0 of the dofs the peers need.  Only now: rank_sum was a barrier across the ranks, so no peer is still
     // multiplying the warm-start x out of the ghost entries these stores overwrite.  The grid barrier orders
@@ -421,7 +444,7 @@ __global__ void __launch_bounds__(kPcgBlock, (DIST && FUSED) ? FES_PCG_DIST_BLOC
       }
       tick(2);
       grid_sum<7>(grid, v7, A.partials, 0, sm);
-      if (dist) rank_sum<7>(A, v7, ++red_step);
+      if (dist) rank_sum<7>(A, v7, ++red_step, sm);
       tick(3);
       const double pq = v7[0], rho_k = v7[1];
       if (!(pq > 0.0)) { status = 2; break; }
@@ -464,16 +487,50 @@ __global__ void __launch_bounds__(kPcgBlock, (DIST && FUSED) ? FES_PCG_DIST_BLOC
       if (it >= A.maxiter) { status = 1; break; }
       const double beta = (it == 0) ? 0.0 : rho / rho_prev;
       tick(5);
-      for (int64_t i = lo + tid; i < hi; i += nth) A.p[i] = fma(beta, A.p[i], A.dinv[i] * A.r[i]);
-      grid.sync();
-      tick(0);
-      if (dist) halo_exchange(A, grid, A.p, ++halo_epoch, tid, nth);
-      tick(1);
-
-      double v1[1] = {sparse_product<C, false, false>(A, tid, nth, A.p, A.q)};
+      double v1[1];
+      if (dist && A.overlap) {
+        // The textbook recurrences with the exchange hidden: the thread that computes the new p of a dof some peer
+        // needs ships it (NVLink store) inside the p update; after the grid barrier one thread publishes the epoch,
+        // the interior rows are multiplied, and only the rows that read ghost entries wait for the neighbours.
+        bool sent = false;
+        for (int k = (int)tid; k < A.n_ship; k += (int)nth) {
+          const int32_t i = A.ship_dof[k];
+          const double pn = fma(beta, A.p[i], A.dinv[i] * A.r[i]);
+          A.p[i] = pn;
+          ship(A, k, pn);
+          sent = true;
+        }
+        for (int64_t i = lo + tid; i < hi; i += nth)
+          if (!A.shipped[i]) A.p[i] = fma(beta, A.p[i], A.dinv[i] * A.r[i]);
+        if (sent) __threadfence_system();  // after the plain update: the NVLink stores have been in flight meanwhile
+        grid.sync();
+        tick(0);
+        ++halo_epoch;
+        halo_publish(A, halo_epoch);
+        if (A.overlap >= 2) { halo_wait(A, halo_epoch); tick(1); }   // wait first
+        if (A.overlap == 3) {
+          // one pass, plain loads: L1 was invalidated by the grid barrier above and no ghost line has been read since
+          v1[0] = sparse_product<C, false, false>(A, tid, nth, A.p, A.q);
+        } else {
+          v1[0] = sparse_product<C, false, false>(A, tid, nth, A.p, A.q, nullptr, 0, A.n_slots_interior);
+          if (A.n_slots_interior + (int64_t)blockIdx.x * blockDim.x < A.n_slots) {  // CTA-uniform
+            tick(2);
+            if (A.overlap == 1) halo_wait(A, halo_epoch);
+            tick(1);
+            v1[0] += sparse_product<C, false, false, false, true>(A, tid, nth, A.p, A.q, nullptr, A.n_slots_interior, A.n_slots);
+          }
+        }
+      } else {
+        for (int64_t i = lo + tid; i < hi; i += nth) A.p[i] = fma(beta, A.p[i], A.dinv[i] * A.r[i]);
+        grid.sync();
+        tick(0);
+        if (dist) halo_exchange(A, grid, A.p, ++halo_epoch, tid, nth);
+        tick(1);
+        v1[0] = sparse_product<C, false, false>(A, tid, nth, A.p, A.q);
+      }
       tick(2);
       grid_sum<1>(grid, v1, A.partials, 3, sm);
-      if (dist) rank_sum<1>(A, v1, ++red_step);
+      if (dist) rank_sum<1>(A, v1, ++red_step, sm);
       tick(3);
       const double pq = v1[0];
       if (!(pq > 0.0)) { status = 2; break; }
@@ -490,7 +547,7 @@ __global__ void __launch_bounds__(kPcgBlock, (DIST && FUSED) ? FES_PCG_DIST_BLOC
       }
       tick(4);
       grid_sum<2>(grid, v2, A.partials, 1, sm);
-      if (dist) rank_sum<2>(A, v2, ++red_step);
+      if (dist) rank_sum<2>(A, v2, ++red_step, sm);
       tick(5);
       rr = v2[0];
       rho_prev = rho;
@@ -1000,8 +1057,10 @@ extern "C" int fes_solver_solve(fes_solver* s, const double* d_b, double* d_x, d
             dist ? s->comm->rank : 0, dist ? s->comm->base : nullptr, dist ? s->comm->d_peer.p : nullptr,
             s->send_ptr.p, s->send_src.p, s->send_dst.p, s->recv_mask, s->send_mask,
             // one GPU: the textbook three-barrier loop unless FES_PCG_FUSED is set (A-B knob; measured slower, see
-            // k_pcg).  Distributed: the single-reduction overlapped loop unless FES_PCG_DIST_CLASSIC is set.
-            dist ? (getenv("FES_PCG_DIST_CLASSIC") ? 0 : 1) : (getenv("FES_PCG_FUSED") ? 1 : 0),
+            // k_pcg).  Distributed: the textbook loop with the exchange overlapped (default); FES_PCG_DIST_FUSED
+            // selects the single-reduction overlapped loop, FES_PCG_DIST_CLASSIC the loop with the halo barrier.
+            dist ? (getenv("FES_PCG_DIST_FUSED") ? 1 : 0) : (getenv("FES_PCG_FUSED") ? 1 : 0),
+            dist ? (getenv("FES_PCG_DIST_CLASSIC") ? 0 : (getenv("FES_PCG_DIST_MODE") ? atoi(getenv("FES_PCG_DIST_MODE")) : 3)) : 0,
             getenv("FES_PCG_TIMERS") ? 1 : 0, s->n_slots_interior, s->n_ship, s->ship_dof.p, s->ship_ptr.p,
             s->ship_rank.p, s->ship_dst.p, s->shipped.p};
   if (dist) {
