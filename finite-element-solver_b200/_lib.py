@@ -36,6 +36,8 @@ SIGNATURES = {
     'fes_plan_nnz': (_i64, [_p]),
     'fes_plan_n_pairs': (_i64, [_p]),
     'fes_plan_n_tiles': (_i64, [_p]),
+    'fes_plan_n_run_tiles': (_i64, [_p]),
+    'fes_plan_run_nodes': (_i64, [_p]),
     'fes_plan_bytes': (_i64, [_p]),
     'fes_plan_read_bytes': (_i64, [_p]),
     'fes_plan_indptr': (_p, [_p]),

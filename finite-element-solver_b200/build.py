@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libfes_b200.so')
-SOURCES = ['core.cu', 'plan.cu', 'assemble.cu', 'pcg.cu', 'simp.cu', 'fields.cu']
+SOURCES = ['core.cu', 'plan.cu', 'plan_runs.cu', 'assemble.cu', 'pcg.cu', 'simp.cu', 'fields.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 
@@ -27,7 +27,7 @@ def _stale(target, deps):
 
 
 def build(force=False, verbose=False):
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh')]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.hpp'))]
     headers.append(os.path.join(os.path.dirname(HERE), 'include', 'fes_b200.h'))
     objdir = os.path.join(HERE, 'build')
     os.makedirs(objdir, exist_ok=True)

@@ -14,6 +14,7 @@
 
 #include "elements.cuh"
 #include "plan.cuh"
+#include "runs_template.hpp"
 #include "tma.cuh"
 
 namespace fes {
@@ -169,7 +170,7 @@ template <int T, int SD> constexpr int rec_batch() { return (T >= 256 || SD == 3
 #endif
 constexpr int kHdrRing = 4, kNodRing = 3;
 __host__ __device__ constexpr int item_len_of(int N) { return (N == 3) ? 2 : (N == 4) ? 6 : 2; }  // = tile_item_len(N)
-constexpr int kHdrBytes = fes_plan::kHdrInts * 4;
+constexpr int kHdrBytes = fes_tileset::kHdrInts * 4;
 
 __host__ __device__ constexpr size_t up16(size_t b) { return (b + 15) & ~(size_t)15; }
 
@@ -270,14 +271,14 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
   auto issue_hdr = [&](int k) {
     uint64_t* bar = &bar_h[k & (kHdrRing - 1)];
     mbar_arrive_expect_tx(bar, kHdrBytes);
-    bulk_g2s(const_cast<int4*>(hdr_of(k)), tile_hdr + (int64_t)tile_of(k) * fes_plan::kHdrInts, kHdrBytes, bar);
+    bulk_g2s(const_cast<int4*>(hdr_of(k)), tile_hdr + (int64_t)tile_of(k) * fes_tileset::kHdrInts, kHdrBytes, bar);
   };
   auto issue_nod = [&](int k) {
     mbar_wait(&bar_h[k & (kHdrRing - 1)], (uint32_t)(k >> 2) & 1u);
     const uint32_t b_nod = ((uint32_t)hdr_of(k)[1].z * 4u + 15u) & ~15u;
     uint64_t* bar = &bar_n[k % kNodRing];
     mbar_arrive_expect_tx(bar, b_nod);
-    if (b_nod) bulk_g2s(const_cast<int32_t*>(nod_of(k)), tile_nodes + (int64_t)tile_of(k) * fes_plan::kTileNodeStride, b_nod, bar);
+    if (b_nod) bulk_g2s(const_cast<int32_t*>(nod_of(k)), tile_nodes + (int64_t)tile_of(k) * fes_tileset::kTileNodeStride, b_nod, bar);
   };
   auto win = [](uint32_t i0, uint32_t count, uint32_t es) {
     return (uint32_t)(((((uint64_t)i0 * es) & 15) + (uint64_t)count * es + 15) & ~(uint64_t)15);
@@ -788,9 +789,11 @@ struct Job {
   bool untiled = false;  // force the reference-order (untiled) kernel
 };
 
+#include "assemble_runs.cuh"
+
 template <int ELEM, int FORM, int C, int SD, int kTileThreads>
-int launch_tiles(const Job& j) {
-  const fes_plan* P = j.plan;
+int launch_tiles(const Job& j, const fes_tileset& T) {
+  const fes_tileset* P = &T;
   const TileDims dims{P->geo_stride, P->rec_max, P->pair_max, P->item_max, P->nod_max, P->slot_mode};
   const size_t smem = TileSmem<ELEM, FORM, C, SD>::total(dims.geo_stride, dims.rec_max, dims.pair_max, dims.item_max,
                                                          dims.nod_max);
@@ -835,10 +838,7 @@ int launch_tiles(const Job& j) {
                               (int)P->n_tiles, (const uint32_t*)P->tile_elems.p, (const uint32_t*)P->rec_local.p,
                               (const int32_t*)P->tile_nodes.p, (const uint32_t*)P->pair_meta.p,
                               (const uint32_t*)P->pair_codes.p, (const double*)j.coords, cf, dims, use_tma, j.out));
-  if (cf.sign < 0.0) {  // a negative global factor (ScaledForm): the kernel ran with |factor|
-    FES_LAUNCH_CHECK();
-    k_negate<<<grid_for(P->nnz, 256), 256, 0, j.stream>>>(j.out, P->nnz);
-  }
+  FES_LAUNCH_CHECK();
   return FES_OK;
 }
 
@@ -852,11 +852,22 @@ int run(const Job& j) {
   } else {
     const fes_plan* P = j.plan;
     if (P->n_pairs == 0) return FES_OK;
-    if (P->tiled && !j.untiled) {
+    if (P->full.tiled && !j.untiled) {
       static const int env_threads = getenv("FES_TILE_THREADS") ? atoi(getenv("FES_TILE_THREADS")) : 0;  // tuning knob
       const int threads = env_threads ? env_threads : tile_threads<FORM>();
-      if (threads == 256) FES_TRY((launch_tiles<ELEM, FORM, C, SD, 256>(j)));
-      else FES_TRY((launch_tiles<ELEM, FORM, C, SD, 128>(j)));
+      const bool no_runs = getenv("FES_NO_RUNS_LAUNCH") != nullptr;  // A-B knob, read per call: the tiled kernel on every node
+      const bool use_runs = runs_supported<ELEM, FORM, C, SD>() && P->runs.active && !no_runs &&
+                            (reinterpret_cast<uintptr_t>(j.out) & 15) == 0;  // the run kernel stores 16-byte units
+      const fes_tileset& T = use_runs ? P->rest : P->full;
+      if (T.n_tiles > 0) {
+        if (threads == 256) FES_TRY((launch_tiles<ELEM, FORM, C, SD, 256>(j, T)));
+        else FES_TRY((launch_tiles<ELEM, FORM, C, SD, 128>(j, T)));
+      }
+      if (use_runs) FES_TRY((launch_runs<ELEM, FORM, C, SD>(j)));
+      if (FORM != FES_FORM_MASS && j.cf.factor < 0.0)  // a negative global factor (ScaledForm): the kernels ran with |factor|
+        k_negate<<<grid_for(P->nnz, 256), 256, 0, j.stream>>>(j.out, P->nnz);
+      else
+        return FES_OK;
     } else {
       k_assemble_pairs<ELEM, FORM, C, SD><<<grid_for(P->n_pairs, kBlock), kBlock, 0, j.stream>>>(
           P->n_pairs, P->pair_start.p, P->pair_row.p, P->node_ptr.p, P->contrib.p, P->indptr.p, j.en, j.coords, j.cf,

@@ -169,7 +169,7 @@ k_tile_build(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__
   __shared__ uint8_t s_li[256];
   __shared__ uint16_t s_slot[kTileRecCap];  // record (rank in ascending element id) -> position in the kernel's tables
   const int t = blockIdx.x;
-  const int32_t g0 = ne_ptr[tile_node0[t]], g1 = ne_ptr[tile_node0[t + 1]];
+  const int32_t g0 = ne_ptr[tile_node0[2 * t]], g1 = ne_ptr[tile_node0[2 * t + 1]];
   const int n_rec = g1 - g0;  // <= inc_max <= kTileRecCap
   for (int i = threadIdx.x; i < n_rec; i += blockDim.x) ids[i] = ne_code[g0 + i] >> 3;
   __syncthreads();
@@ -186,7 +186,7 @@ k_tile_build(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__
   // whatever the element numbering's stride is (3 and 6 records on Kuhn tetrahedra), and the
   // quarter-warp gathers of phase 2 fall into distinct banks.
   if (slot_mode == 2) {
-    const int32_t v0 = tile_node0[t], v1 = tile_node0[t + 1], nn = v1 - v0;
+    const int32_t v0 = tile_node0[2 * t], v1 = tile_node0[2 * t + 1], nn = v1 - v0;
     for (int i = threadIdx.x; i < ne; i += blockDim.x) ids[i] = 0xffffffffu;
     __syncthreads();
     for (int i = threadIdx.x; i < n_rec; i += blockDim.x) {
@@ -303,7 +303,7 @@ k_tile_build(const int32_t* __restrict__ tile_node0, const int32_t* __restrict__
     __syncthreads();
   }
   if (threadIdx.x == 0) tile_cnt[2 * t + 1] = n_slots;
-  int32_t* my_nodes = tile_nodes + (int64_t)t * fes_plan::kTileNodeStride;
+  int32_t* my_nodes = tile_nodes + (int64_t)t * fes_tileset::kTileNodeStride;
   for (int i = threadIdx.x; i < n_slots; i += blockDim.x) my_nodes[i] = (int32_t)uniq[0];  // unused slots: any valid node
   __syncthreads();
   for (int i = threadIdx.x; i < nd; i += blockDim.x) my_nodes[s_li[i]] = (int32_t)uniq[i];
@@ -331,7 +331,7 @@ __global__ void k_tile_hdr(const int32_t* __restrict__ tile_node0, int64_t n_til
                            int* __restrict__ bad) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
-  const int32_t v0 = tile_node0[t], v1 = tile_node0[t + 1];
+  const int32_t v0 = tile_node0[2 * t], v1 = tile_node0[2 * t + 1];
   const int32_t p0 = node_ptr[v0], p1 = node_ptr[v1];
   const uint32_t c0 = pair_start[p0], c1 = pair_start[p1];
   int32_t items = 0;
@@ -342,7 +342,7 @@ __global__ void k_tile_hdr(const int32_t* __restrict__ tile_node0, int64_t n_til
     if (m > L) atomicExch(bad, 1);  // a pair shared by > 32 L elements: keep the untiled kernel
     items += 1 << lg;
   }
-  int32_t* h = hdr + t * fes_plan::kHdrInts;
+  int32_t* h = hdr + t * fes_tileset::kHdrInts;
   h[0] = ne_ptr[v0]; h[1] = tile_cnt[2 * t]; h[2] = p0; h[3] = p1 - p0;
   h[4] = (int32_t)c0; h[5] = (int32_t)(c1 - c0); h[6] = tile_cnt[2 * t + 1]; h[7] = v0;
   h[8] = 0; h[9] = items; h[10] = 0; h[11] = 0;
@@ -365,7 +365,7 @@ __global__ void k_tile_emit(const int32_t* __restrict__ hdr, int64_t n_tiles, co
                             uint32_t* __restrict__ meta, uint32_t* __restrict__ codes, int* __restrict__ bad) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
-  const int32_t* h = hdr + t * fes_plan::kHdrInts;
+  const int32_t* h = hdr + t * fes_tileset::kHdrInts;
   const int32_t g0 = h[0], ne = h[1], p0 = h[2], p1 = h[2] + h[3], v0 = h[7];
   const int N2 = N * N;
   const uint32_t zero_code = ((uint32_t)(gs - 1) << 4) * 0x10001u;
@@ -450,13 +450,12 @@ int bits_for(uint64_t max_value) {
   return b;
 }
 
-// Tile the node range for the fused assembly kernel.  The greedy split runs on the host over the
-// two prefix arrays (O(n_nodes), once per mesh); everything else stays on the device.
-int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, int inc_max, bool* retry) {
-  *retry = false;
+// Incident-element lists per node (ne_ptr / ne_code), shared by the tilings and the stencil-run detection.
+// Leaves P->n_geo = 0 when the mesh has degenerate elements (repeated nodes): nothing is tiled then.
+int build_incidence(fes_plan* P, cudaStream_t stream, std::vector<int32_t>& h_ne, std::vector<int32_t>& h_np) {
   const int64_t nn = P->n_nodes, np_ = P->n_pairs;
-  const int N = P->N, c = P->c;
-  P->tiled = false;
+  const int N = P->N;
+  P->n_geo = 0;
   if (np_ == 0) return FES_OK;
   DevBuf<int32_t> ne_cnt;
   FES_CUDA(ne_cnt.alloc(nn + 1));
@@ -465,14 +464,33 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
   FES_LAUNCH_CHECK();
   FES_CUDA(P->ne_ptr.alloc(nn + 1));
   FES_TRY((device_scan<int32_t, false>(ne_cnt.p, P->ne_ptr.p, nn + 1, stream)));
-  std::vector<int32_t> h_ne(nn + 1), h_np(nn + 1);
+  h_ne.resize(nn + 1); h_np.resize(nn + 1);
   FES_CUDA(cudaMemcpyAsync(h_ne.data(), P->ne_ptr.p, (nn + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   FES_CUDA(cudaMemcpyAsync(h_np.data(), P->node_ptr.p, (nn + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   FES_CUDA(cudaStreamSynchronize(stream));
-  P->n_geo = h_ne[nn];
-  if (P->n_geo != P->n_el * N) return FES_OK;  // degenerate elements (repeated nodes): keep the untiled kernel
+  if (h_ne[nn] != P->n_el * N) return FES_OK;  // degenerate elements (repeated nodes): keep the untiled kernel
   if (P->n_el >= ((int64_t)1 << 29)) return FES_OK;
-  P->inc_max = inc_max;
+  P->n_geo = h_ne[nn];
+  FES_CUDA(P->ne_code.alloc(P->n_geo));
+  k_fill_ne<<<grid_for(np_, kBlock), kBlock, 0, stream>>>(P->pair_row.p, P->node_adj.p, P->pair_start.p, P->contrib.p, np_,
+                                                          N, P->ne_ptr.p, P->ne_code.p);
+  FES_LAUNCH_CHECK();
+  return FES_OK;
+}
+
+// Tile the node ranges `ranges` = {begin0, end0, begin1, end1, ...} (ascending, disjoint) for the fused assembly
+// kernel.  The greedy split runs on the host over the two prefix arrays (O(n_nodes), once per mesh); everything else
+// stays on the device.  Tiles never straddle a range boundary.
+int build_tiles(fes_plan* P, fes_tileset& T, const std::vector<int32_t>& ranges, const std::vector<int32_t>& h_ne,
+                const std::vector<int32_t>& h_np, const int32_t* d_elem_nodes, cudaStream_t stream, int inc_max,
+                bool* retry) {
+  *retry = false;
+  const int64_t np_ = P->n_pairs;
+  const int N = P->N, c = P->c;
+  T.tiled = false;
+  T.n_tiles = 0;
+  if (np_ == 0 || P->n_geo == 0 || ranges.empty()) return FES_OK;
+  T.inc_max = inc_max;
   // a tile's value image stays under 32 KB of shared memory, its packed offsets under 16 bits
   const int pair_cap = std::min(32768 / (8 * c * c), 65535 / c);
   // Boundary nodes carry more pairs per incident element than interior ones, so a run of them within
@@ -481,51 +499,52 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
   // 1.25x the mesh-average pairs of a full tile (a single node always fits).
   const int pair_soft = (int)(1.25 * (double)np_ / (double)P->n_geo * inc_max) + 8;
   std::vector<int32_t> tiles;
-  tiles.push_back(0);
-  int64_t v0 = 0;
   // Runs whose length is a multiple of `node_mult` keep the lane groups of phase 2 (same relative neighbour of
   // consecutive nodes) aligned to quarter- and half-warps.  Tets: 16-node runs gather at 1.18x / 1.31x of their
   // conflict-free wavefronts, 17-node runs at 1.43x / 1.79x (tools/bank_sim.py model).
   const int64_t node_mult = getenv("FES_TILE_NODE_MULT") ? atoi(getenv("FES_TILE_NODE_MULT")) : tile_node_multiple(N);
-  for (int64_t v = 0; v < nn; ++v) {
-    if (h_ne[v + 1] - h_ne[v] > inc_max || h_np[v + 1] - h_np[v] > pair_cap) return FES_OK;  // one node overflows a tile
-    if (h_ne[v + 1] - h_ne[v0] > inc_max || h_np[v + 1] - h_np[v0] > pair_cap || v - v0 >= 255 ||
-        (h_np[v + 1] - h_np[v0] > pair_soft && v > v0)) {
-      int64_t cut = v;
-      if (node_mult > 1 && v - v0 > node_mult) cut = v0 + (v - v0) / node_mult * node_mult;
-      tiles.push_back((int32_t)cut);
-      v0 = cut;
-      v = cut - 1;  // re-scan from the cut
+  for (size_t r = 0; r + 1 < ranges.size(); r += 2) {
+    int64_t v0 = ranges[r];
+    const int64_t vend = ranges[r + 1];
+    for (int64_t v = v0; v < vend; ++v) {
+      if (h_ne[v + 1] - h_ne[v] > inc_max || h_np[v + 1] - h_np[v] > pair_cap) return FES_OK;  // one node overflows a tile
+      if (h_ne[v + 1] - h_ne[v0] > inc_max || h_np[v + 1] - h_np[v0] > pair_cap || v - v0 >= 255 ||
+          (h_np[v + 1] - h_np[v0] > pair_soft && v > v0)) {
+        int64_t cut = v;
+        if (node_mult > 1 && v - v0 > node_mult) cut = v0 + (v - v0) / node_mult * node_mult;
+        tiles.push_back((int32_t)v0); tiles.push_back((int32_t)cut);
+        v0 = cut;
+        v = cut - 1;  // re-scan from the cut
+      }
     }
+    if (vend > v0) { tiles.push_back((int32_t)v0); tiles.push_back((int32_t)vend); }
   }
-  tiles.push_back((int32_t)nn);
-  P->n_tiles = (int64_t)tiles.size() - 1;
-  const int64_t nt = P->n_tiles;
-  FES_CUDA(P->tile_node0.alloc(tiles.size()));
-  FES_CUDA(cudaMemcpyAsync(P->tile_node0.p, tiles.data(), tiles.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
-  FES_CUDA(P->ne_code.alloc(P->n_geo));
-  k_fill_ne<<<grid_for(np_, kBlock), kBlock, 0, stream>>>(P->pair_row.p, P->node_adj.p, P->pair_start.p, P->contrib.p, np_,
-                                                          N, P->ne_ptr.p, P->ne_code.p);
-  FES_LAUNCH_CHECK();
+  T.n_tiles = (int64_t)tiles.size() / 2;
+  const int64_t nt = T.n_tiles;
+  if (nt == 0) return FES_OK;
+  // per-tile tables live at the tile's offset into the global incidence list: sized to the last tile's end
+  const int64_t g_end = h_ne[tiles.back()];
+  FES_CUDA(T.tile_node0.alloc(tiles.size()));
+  FES_CUDA(cudaMemcpyAsync(T.tile_node0.p, tiles.data(), tiles.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
 
   // distinct elements and distinct corner nodes per tile
-  P->n_corner = (N == 6) ? 3 : N;
+  T.n_corner = (N == 6) ? 3 : N;
   DevBuf<int> bad;
   FES_CUDA(bad.alloc(1));
   FES_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), stream));
-  FES_CUDA(P->tile_elems.alloc(P->n_geo + 16));
-  FES_CUDA(P->elems_sorted.alloc(P->n_geo + 16));
-  FES_CUDA(P->slot_of.alloc(P->n_geo + 16));
-  P->slot_mode = getenv("FES_SLOT_MODE") ? atoi(getenv("FES_SLOT_MODE")) : tile_slot_mode(N);  // env: tuning knob
-  FES_CUDA(P->rec_local.alloc(P->n_geo + 16));
-  FES_CUDA(P->tile_nodes.alloc((size_t)nt * fes_plan::kTileNodeStride + 64));
-  FES_CUDA(P->tile_cnt.alloc(2 * nt));
+  FES_CUDA(T.tile_elems.alloc(g_end + 16));
+  FES_CUDA(T.elems_sorted.alloc(g_end + 16));
+  FES_CUDA(T.slot_of.alloc(g_end + 16));
+  T.slot_mode = getenv("FES_SLOT_MODE") ? atoi(getenv("FES_SLOT_MODE")) : tile_slot_mode(N);  // env: tuning knob
+  FES_CUDA(T.rec_local.alloc(g_end + 16));
+  FES_CUDA(T.tile_nodes.alloc((size_t)nt * fes_tileset::kTileNodeStride + 64));
+  FES_CUDA(T.tile_cnt.alloc(2 * nt));
   // coordinate-table slots coloured for 8 records per wavefront (16-byte xy pairs) or 16 (tets: 8-byte components)
   static const bool no_colour = getenv("FES_PLAN_NO_COLOUR") != nullptr;  // tuning knob: sorted ranks
   const int colour_groups = no_colour ? 0 : (N == 4 ? 16 : 8);
-  k_tile_build<<<(unsigned)nt, 256, 0, stream>>>(P->tile_node0.p, P->ne_ptr.p, P->ne_code.p, d_elem_nodes, N, P->n_corner,
-                                                 P->tile_elems.p, P->elems_sorted.p, P->slot_of.p, P->rec_local.p,
-                                                 P->tile_nodes.p, P->tile_cnt.p, colour_groups, P->slot_mode, bad.p);
+  k_tile_build<<<(unsigned)nt, 256, 0, stream>>>(T.tile_node0.p, P->ne_ptr.p, P->ne_code.p, d_elem_nodes, N, T.n_corner,
+                                                 T.tile_elems.p, T.elems_sorted.p, T.slot_of.p, T.rec_local.p,
+                                                 T.tile_nodes.p, T.tile_cnt.p, colour_groups, T.slot_mode, bad.p);
   FES_LAUNCH_CHECK();
   int h_bad = 0;
   FES_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -533,7 +552,7 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
   if (h_bad) {  // a tile touches > 255 distinct nodes (scattered node numbering): retry with smaller tiles
     if (getenv("FES_PLAN_DEBUG")) {
       std::vector<int32_t> cnts(2 * nt);
-      cudaMemcpy(cnts.data(), P->tile_cnt.p, cnts.size() * sizeof(int32_t), cudaMemcpyDeviceToHost);
+      cudaMemcpy(cnts.data(), T.tile_cnt.p, cnts.size() * sizeof(int32_t), cudaMemcpyDeviceToHost);
       int mr = 0, mn = 0;
       for (int64_t t = 0; t < nt; ++t) { mr = std::max(mr, cnts[2 * t]); mn = std::max(mn, cnts[2 * t + 1]); }
       fprintf(stderr, "[fes plan] retry: inc_max=%d tiles=%lld max distinct elements=%d max distinct nodes=%d\n", inc_max,
@@ -546,14 +565,14 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
   // so the summation tree of a pair is a function of its contribution count alone: a rank that
   // assembles a slab with ghost elements produces the same bits as the single-GPU assembly.
   const uint32_t L = (uint32_t)tile_item_len(N);
-  constexpr int HI = fes_plan::kHdrInts;
-  FES_CUDA(P->tile_hdr.alloc((size_t)nt * HI + 16));
+  constexpr int HI = fes_tileset::kHdrInts;
+  FES_CUDA(T.tile_hdr.alloc((size_t)nt * HI + 16));
   FES_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), stream));
-  k_tile_hdr<<<grid_for(nt, kBlock), kBlock, 0, stream>>>(P->tile_node0.p, nt, P->ne_ptr.p, P->node_ptr.p, P->pair_start.p,
-                                                          P->tile_cnt.p, L, P->tile_hdr.p, bad.p);
+  k_tile_hdr<<<grid_for(nt, kBlock), kBlock, 0, stream>>>(T.tile_node0.p, nt, P->ne_ptr.p, P->node_ptr.p, P->pair_start.p,
+                                                          T.tile_cnt.p, L, T.tile_hdr.p, bad.p);
   FES_LAUNCH_CHECK();
   std::vector<int32_t> hdr((size_t)nt * HI);
-  FES_CUDA(cudaMemcpyAsync(hdr.data(), P->tile_hdr.p, hdr.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  FES_CUDA(cudaMemcpyAsync(hdr.data(), T.tile_hdr.p, hdr.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   FES_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
   FES_CUDA(cudaStreamSynchronize(stream));
   if (h_bad) return FES_OK;
@@ -567,8 +586,8 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
     rd += 4 * HI + (int64_t)h[9] * 4 * (1 + L) + (int64_t)h[1] * 4 + (int64_t)h[6] * 4;
   }
   if (imax > 65535 || rmax > kTileRecCap || items * L >= ((int64_t)1 << 32)) return FES_OK;
-  P->rec_max = rmax; P->pair_max = pmax; P->con_max = cmax; P->item_max = imax; P->n_items = items;
-  P->nod_max = (nmax + 3) & ~3;
+  T.rec_max = rmax; T.pair_max = pmax; T.con_max = cmax; T.item_max = imax; T.n_items = items;
+  T.nod_max = (nmax + 3) & ~3;
   // slots are swizzled inside aligned groups of 8 (mode 0)
   {
     // Smallest stride above every (swizzled) slot with the wanted residue; the last slot holds the zero record.
@@ -581,32 +600,53 @@ int build_tiles(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream, i
     static const int gs_res = getenv("FES_GS_RES") ? atoi(getenv("FES_GS_RES")) : 0;
     int gs = ((rmax + 7) & ~7) + 1;
     while (gs % gs_align != gs_res % gs_align) ++gs;
-    P->geo_stride = gs;
+    T.geo_stride = gs;
   }
-  if ((int64_t)N * P->geo_stride * 16 > 65535) return FES_OK;  // 16-bit byte offsets in the codes
-  P->tile_read_bytes = rd;
+  if ((int64_t)N * T.geo_stride * 16 > 65535) return FES_OK;  // 16-bit byte offsets in the codes
+  T.tile_read_bytes = rd;
   if (getenv("FES_PLAN_DEBUG"))
     fprintf(stderr, "[fes plan] N=%d c=%d nodes=%lld pairs=%lld tiles=%lld inc_max=%d rec_max=%d pair_max=%d item_max=%d con_max=%d nod_max=%d items=%lld gs=%d\n",
-            N, c, (long long)nn, (long long)np_, (long long)nt, inc_max, rmax, pmax, imax, cmax, P->nod_max, (long long)items, P->geo_stride);
-  FES_CUDA(cudaMemcpyAsync(P->tile_hdr.p, hdr.data(), hdr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
-  P->item_len = (int)L;
-  FES_CUDA(P->pair_meta.alloc(items + 16));
-  FES_CUDA(P->pair_codes.alloc(items * L + 32));
-  k_tile_emit<<<grid_for(nt, 64), 64, 0, stream>>>(P->tile_hdr.p, nt, P->node_ptr.p, P->pair_row.p, P->node_adj.p,
-                                                   P->pair_start.p, P->contrib.p, P->elems_sorted.p, P->slot_of.p, N, c, P->geo_stride, P->slot_mode,
+            N, c, (long long)P->n_nodes, (long long)np_, (long long)nt, inc_max, rmax, pmax, imax, cmax, T.nod_max, (long long)items, T.geo_stride);
+  FES_CUDA(cudaMemcpyAsync(T.tile_hdr.p, hdr.data(), hdr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  T.item_len = (int)L;
+  FES_CUDA(T.pair_meta.alloc(items + 16));
+  FES_CUDA(T.pair_codes.alloc(items * L + 32));
+  k_tile_emit<<<grid_for(nt, 64), 64, 0, stream>>>(T.tile_hdr.p, nt, P->node_ptr.p, P->pair_row.p, P->node_adj.p,
+                                                   P->pair_start.p, P->contrib.p, T.elems_sorted.p, T.slot_of.p, N, c, T.geo_stride, T.slot_mode,
                                                    getenv("FES_ITEM_BY_DEGREE") ? atoi(getenv("FES_ITEM_BY_DEGREE")) : 1, L,
-                                                   P->pair_meta.p, P->pair_codes.p, bad.p);
+                                                   T.pair_meta.p, T.pair_codes.p, bad.p);
   FES_LAUNCH_CHECK();
   FES_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
   FES_CUDA(cudaStreamSynchronize(stream));  // also keeps `hdr` alive until the upload is done
   if (h_bad) return FES_OK;  // offsets beyond 16 bits: keep the untiled kernel
-  P->elems_sorted.release();  // plan-time lookups only
-  P->slot_of.release();
-  P->tiled = true;
+  T.elems_sorted.release();  // plan-time lookups only
+  T.slot_of.release();
+  T.tiled = true;
+  return FES_OK;
+}
+
+// tiles shrink until every tile references <= 255 distinct nodes; with elements*corners <= 255
+// that always holds, so a mesh with scattered node numbering is still tiled (smaller tiles)
+int tile_with_retries(fes_plan* P, fes_tileset& T, const std::vector<int32_t>& ranges, const std::vector<int32_t>& h_ne,
+                      const std::vector<int32_t>& h_np, const int32_t* d_elem_nodes, cudaStream_t stream) {
+  const int N = P->N;
+  int inc = tile_inc_budget(N);
+  if (const char* env = getenv("FES_TILE_INC")) inc = std::max(16, std::min(kTileRecCap, atoi(env)));  // tuning knob
+  const int n_corner = (N == 6) ? 3 : N;
+  for (;;) {
+    bool retry = false;
+    FES_TRY(build_tiles(P, T, ranges, h_ne, h_np, d_elem_nodes, stream, inc, &retry));
+    if (!retry) break;
+    if (inc * n_corner <= 255) break;  // cannot happen: such tiles always fit
+    inc = std::max(255 / n_corner, inc - std::max(1, inc / 8));  // shrink gently: usually a few tiles overflow
+  }
   return FES_OK;
 }
 
 }  // namespace
+
+int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32_t>& h_ne, const std::vector<int32_t>& h_np,
+               cudaStream_t stream, std::vector<int32_t>& rest_ranges);  // plan_runs.cu
 }  // namespace fes
 
 using namespace fes;
@@ -707,17 +747,17 @@ extern "C" int fes_plan_create(const int32_t* d_elem_nodes, int64_t n_el, int N,
   FES_LAUNCH_CHECK();
   FES_CUDA(cudaStreamSynchronize(stream));
   {
-    // tiles shrink until every tile references <= 255 distinct nodes; with elements*corners <= 255
-    // that always holds, so a mesh with scattered node numbering is still tiled (smaller tiles)
-    int inc = tile_inc_budget(N);
-    if (const char* env = getenv("FES_TILE_INC")) inc = std::max(16, std::min(kTileRecCap, atoi(env)));  // tuning knob
-    const int n_corner = (N == 6) ? 3 : N;
-    for (;;) {
-      bool retry = false;
-      FES_TRY(build_tiles(P, d_elem_nodes, stream, inc, &retry));
-      if (!retry) break;
-      if (inc * n_corner <= 255) break;  // cannot happen: such tiles always fit
-      inc = std::max(255 / n_corner, inc - std::max(1, inc / 8));  // shrink gently: usually a few tiles overflow
+    std::vector<int32_t> h_ne, h_np;
+    FES_TRY(build_incidence(P, stream, h_ne, h_np));
+    FES_TRY(tile_with_retries(P, P->full, {0, (int32_t)n_nodes}, h_ne, h_np, d_elem_nodes, stream));
+    // stencil runs + the tiling of whatever they leave uncovered (plan_runs.cu)
+    if (P->full.tiled && !getenv("FES_NO_RUNS")) {
+      std::vector<int32_t> rest;
+      FES_TRY(build_runs(P, d_elem_nodes, h_ne, h_np, stream, rest));
+      if (P->runs.active) {
+        FES_TRY(tile_with_retries(P, P->rest, rest, h_ne, h_np, d_elem_nodes, stream));
+        if (!rest.empty() && !P->rest.tiled) P->runs.active = false;  // cannot tile the remainder: keep the full tiling only
+      }
     }
   }
   guard.p = nullptr;
@@ -755,7 +795,9 @@ extern "C" void fes_plan_destroy(fes_plan* plan) { delete plan; }
 extern "C" int64_t fes_plan_n_dofs(const fes_plan* p) { return p ? p->n_dofs : 0; }
 extern "C" int64_t fes_plan_nnz(const fes_plan* p) { return p ? p->nnz : 0; }
 extern "C" int64_t fes_plan_n_pairs(const fes_plan* p) { return p ? p->n_pairs : 0; }
-extern "C" int64_t fes_plan_n_tiles(const fes_plan* p) { return (p && p->tiled) ? p->n_tiles : 0; }
+extern "C" int64_t fes_plan_n_tiles(const fes_plan* p) { return (p && p->full.tiled) ? p->full.n_tiles : 0; }
+extern "C" int64_t fes_plan_n_run_tiles(const fes_plan* p) { return (p && p->runs.active) ? p->runs.n_tiles : 0; }
+extern "C" int64_t fes_plan_run_nodes(const fes_plan* p) { return (p && p->runs.active) ? p->runs.n_nodes_covered : 0; }
 extern "C" const int32_t* fes_plan_indptr(const fes_plan* p) { return p ? p->indptr.p : nullptr; }
 extern "C" const int32_t* fes_plan_indices(const fes_plan* p) { return p ? p->indices.p : nullptr; }
 
@@ -763,15 +805,15 @@ extern "C" int64_t fes_plan_bytes(const fes_plan* p) {
   if (!p) return 0;
   return (int64_t)(p->node_ptr.bytes() + p->node_adj.bytes() + p->pair_row.bytes() + p->pair_start.bytes() +
                    p->contrib.bytes() + p->indptr.bytes() + p->indices.bytes() + p->ne_ptr.bytes() +
-                   p->ne_code.bytes() + p->tile_node0.bytes() + p->tile_elems.bytes() + p->rec_local.bytes() +
-                   p->tile_nodes.bytes() + p->tile_cnt.bytes() + p->tile_hdr.bytes() + p->pair_meta.bytes() +
-                   p->pair_codes.bytes());
+                   p->ne_code.bytes() + p->full.bytes() + p->rest.bytes() + p->runs.bytes());
 }
 
-// what one fused assembly streams from the plan (overhead on top of the algorithmic bytes)
+// what one fused assembly streams from the plan (overhead on top of the algorithmic bytes): the stencil-run
+// path reads 32 bytes per tile plus the index streams of the remainder tiling
 extern "C" int64_t fes_plan_read_bytes(const fes_plan* p) {
   if (!p) return 0;
-  if (p->tiled) return p->tile_read_bytes;
+  if (p->runs.active) return (int64_t)p->runs.n_tiles * fes_runs::kTileInts * 4 + p->rest.tile_read_bytes;
+  if (p->full.tiled) return p->full.tile_read_bytes;
   return (int64_t)(p->pair_row.bytes() + p->pair_start.bytes() + p->contrib.bytes() + p->node_ptr.bytes() +
                    p->indptr.bytes());
 }

@@ -2,37 +2,22 @@
 #pragma once
 #include "common.cuh"
 
-struct fes_plan {
-  int64_t n_el = 0, n_nodes = 0, n_dofs = 0, n_pairs = 0, nnz = 0, n_contrib = 0;
-  int N = 0, c = 0;
-  // node-level (block) CSR: row v holds its neighbour nodes in ascending order
-  fes::DevBuf<int32_t> node_ptr;    // n_nodes + 1
-  fes::DevBuf<int32_t> node_adj;    // n_pairs
-  fes::DevBuf<int32_t> pair_row;    // n_pairs : row node of each pair
-  // contributions: for pair p, contrib[pair_start[p] .. pair_start[p+1]) = e*N*N + a*N + b in
-  // ascending element id -- the order np.bincount sums them in (SURVEY A.5)
-  fes::DevBuf<uint32_t> pair_start;  // n_pairs + 1
-  fes::DevBuf<uint32_t> contrib;     // n_el * N * N
-  // scalar CSR, bit-identical to the reference's _ScatterPlan.indptr / .indices
-  fes::DevBuf<int32_t> indptr;   // n_dofs + 1
-  fes::DevBuf<int32_t> indices;  // nnz
-
-  // ---- tiled layout for the fused assembly kernel ------------------------------------------
-  // A tile is a run of consecutive nodes = a contiguous range of stored pairs = a contiguous range
-  // of CSR values.  Phase 1 of the kernel evaluates one geometry record per DISTINCT element
-  // touching the tile; phase 2 gathers the contributions of every pair of the tile into a
-  // shared-memory image of the tile's values, which one TMA bulk store writes out.
+// One tiling of (a subset of) the nodes for the fused assembly kernel k_assemble_tiles.
+// A tile is a run of consecutive nodes = a contiguous range of stored pairs = a contiguous range
+// of CSR values.  Phase 1 of the kernel evaluates one geometry record per DISTINCT element
+// touching the tile; phase 2 gathers the contributions of every pair of the tile into a
+// shared-memory image of the tile's values, which one TMA bulk store writes out.
+// A plan holds two: `full` covers every node; `rest` covers the nodes no stencil run covers (see fes_runs).
+struct fes_tileset {
   bool tiled = false;
-  int64_t n_tiles = 0, n_geo = 0, tile_read_bytes = 0;
+  int64_t n_tiles = 0, tile_read_bytes = 0;
   int inc_max = 0;                     // (node, incident element) records per tile: the tiling budget
   int geo_stride = 0;                  // shared-memory plane stride of the records: 0 (mod 8), > every slot
   int slot_mode = 0;                   // rec_slot mode the codes were emitted with
   int rec_max = 0, pair_max = 0, con_max = 0, item_max = 0, nod_max = 0;  // distinct elements / pairs / contributions / work items / distinct nodes per tile, upper bounds
   int64_t n_items = 0;
   int item_len = 0;                    // contribution codes per work item (= tile_item_len(N))
-  fes::DevBuf<int32_t> ne_ptr;         // n_nodes + 1 : incident-element ranges per node
-  fes::DevBuf<uint32_t> ne_code;       // n_geo : e*8 + a, ascending e per node
-  fes::DevBuf<int32_t> tile_node0;     // n_tiles + 1
+  fes::DevBuf<int32_t> tile_node0;     // 2 * n_tiles : tile t covers nodes [tile_node0[2t], tile_node0[2t+1])
   // distinct elements of a tile (ascending id) at [g0, g0 + ne), g0 = ne_ptr[first node]; each
   // element's corner nodes as indices into the tile's sorted distinct-node list
   static constexpr int kTileNodeStride = 256;
@@ -53,6 +38,54 @@ struct fes_plan {
   fes::DevBuf<uint32_t> pair_codes;    // n_items * item_len (+pad) : 16*(a*geo_stride + slot) | 16*(b*geo_stride + slot) << 16
                                        //   (byte offsets), slot = rec_slot(record index in tile); short items padded with
                                        //   the zero record (slot geo_stride-1); ascending element id within an item
+  size_t bytes() const {
+    return tile_node0.bytes() + tile_elems.bytes() + rec_local.bytes() + tile_nodes.bytes() + tile_cnt.bytes() +
+           tile_hdr.bytes() + pair_meta.bytes() + pair_codes.bytes();
+  }
+};
+
+// Stencil runs: maximal ranges of consecutive nodes whose RELATIVE stencil repeats with period P (1 or 2)
+// -- same neighbour offsets, same contributing elements up to a constant element-id shift per period, same
+// local indices.  Structured meshes are made of them (a mesh row of create_rect_mesh is one run of period 2,
+// a z-line of create_box_mesh one run of period 1); the detection reads the connectivity only, so a
+// structured mesh with arbitrary (jittered) coordinates qualifies.  Run tiles are assembled by
+// k_assemble_runs from a per-template program instead of per-tile index streams: lane t of a warp owns
+// lane-step t of the tile, every shared-memory address is affine in t (unit stride: no bank conflicts), and
+// nothing but the tile header, the coordinates and the per-element coefficients is read from HBM.
+struct fes_runs {
+  bool active = false;
+  int64_t n_tiles = 0, n_nodes_covered = 0, n_templates = 0;
+  // shared-memory sizing of k_assemble_runs: maxima over the templates
+  int max_rec_entries = 0;             // n_lines * N * TS
+  int max_coord_nodes = 0, max_img_units = 0, max_tmpl_words = 0;
+  static constexpr int kTileInts = 8;  // {v0, T, template word offset, E0, first pair, raw word offset, 0, 0}
+  fes::DevBuf<int32_t> tiles;
+  fes::DevBuf<int32_t> tmpl;           // all template programs, each 16-byte aligned (layout: runs_template.hpp)
+  size_t bytes() const { return tiles.bytes() + tmpl.bytes(); }
+};
+
+struct fes_plan {
+  int64_t n_el = 0, n_nodes = 0, n_dofs = 0, n_pairs = 0, nnz = 0, n_contrib = 0;
+  int N = 0, c = 0;
+  // node-level (block) CSR: row v holds its neighbour nodes in ascending order
+  fes::DevBuf<int32_t> node_ptr;    // n_nodes + 1
+  fes::DevBuf<int32_t> node_adj;    // n_pairs
+  fes::DevBuf<int32_t> pair_row;    // n_pairs : row node of each pair
+  // contributions: for pair p, contrib[pair_start[p] .. pair_start[p+1]) = e*N*N + a*N + b in
+  // ascending element id -- the order np.bincount sums them in (SURVEY A.5)
+  fes::DevBuf<uint32_t> pair_start;  // n_pairs + 1
+  fes::DevBuf<uint32_t> contrib;     // n_el * N * N
+  // scalar CSR, bit-identical to the reference's _ScatterPlan.indptr / .indices
+  fes::DevBuf<int32_t> indptr;   // n_dofs + 1
+  fes::DevBuf<int32_t> indices;  // nnz
+
+  // incident-element lists per node (shared by both tilings and the stencil-run detection)
+  int64_t n_geo = 0;
+  fes::DevBuf<int32_t> ne_ptr;         // n_nodes + 1 : incident-element ranges per node
+  fes::DevBuf<uint32_t> ne_code;       // n_geo : e*8 + a, ascending e per node
+  fes_tileset full;                    // every node: forms / element types the run kernel does not cover
+  fes_tileset rest;                    // the nodes outside stencil runs (used together with `runs`)
+  fes_runs runs;
 
   // staging for the host-buffer entry point (fes_assemble_host), allocated on first use
   mutable fes::DevBuf<double> stage_coords, stage_values, stage_E, stage_scale;

@@ -1,0 +1,353 @@
+// Stencil runs: host-side detection and template programs for k_assemble_runs (assemble_runs.cuh).
+// Pure C++ (no CUDA headers) so the same code is compiled into libfes_b200.so and into the CPU
+// emulator test (tests/host/runs_emulator.cpp), which replays a template program on the host and
+// compares it with a plain per-pair assembly of the same mesh.
+//
+// A RUN is a maximal range of consecutive nodes whose RELATIVE stencil repeats with period P (1 or 2):
+// node v0 + P t + phi (lane-step t, phase phi) has the incident elements E0 + t * delta + de_r with the
+// same local indices and the same corner nodes relative to v0 + P t for every t.  Structured meshes are
+// made of runs (a mesh row of the reference's create_rect_mesh is one run of period 2 -- the diagonals
+// alternate --, a z-line of create_box_mesh one run of period 1; ref fem/mesh/structured.py:17-96); the
+// detection reads the connectivity only, so a structured mesh with arbitrary coordinates qualifies.
+//
+// A run is cut into TILES of <= 32 lane-steps.  The kernel evaluates the geometry of every element LINE
+// {E0 + d0 + tau * delta} touching the tile once per tau into shared-memory planes indexed by tau, then
+// lane t of a warp sums the pairs of its P nodes from addresses (code + t): unit stride across the warp,
+// no bank conflicts, and nothing but a 32-byte tile header, the node coordinates and the per-element
+// coefficients is read from HBM.  The four warps of a CTA split the PAIRS of the period between them.
+//
+// Template blob (int32 words; offsets relative to the template's first word):
+//   [0] P  [1] n_lines  [2] TS (plane stride, entries)  [3] LUp (padded image row stride, units)
+//   [4] LU (image row, units)  [5] n_spans  [6] off_lines  [7] off_spans  [8..11] off_prog[warp]
+//   [12] n_words  [13] coordinate nodes staged per tile (32 lane-steps)  [14] delta  [15] magic = ceil(2^32 / LU)
+//   [16] doubles per image row (c^2 * pairs per period)  [17..19] reserved
+//   lines : n_lines x {eoff, ext, cidx[N]}   element of entry tau' = E0 + eoff + tau' * delta, entries
+//           tau' < T + ext; corner c sits at coordinate-table node cidx[c] + P * tau'
+//   spans : n_spans x {start, ext, base}     nodes v0 + start + i, i < P (T - 1) + ext + 1, staged at table
+//           node base + i
+//   prog  : per warp {n_pairs, then per pair: head, codes[cnt]}
+//           head = img (12) | deg (7) << 12 | cnt (6) << 19 | lg (3) << 25     img = c^2 * prefix_phi + c * k (doubles)
+//           code = entry_a | entry_b << 16, entry = (line * N + local) * TS + (shift - taumin_line); lane t adds t
+// An image UNIT is 16 bytes when c is even, 8 bytes otherwise; LUp = LU | 1 keeps the lanes' stores on distinct banks.
+#pragma once
+#include <stdint.h>
+
+#include <algorithm>
+#include <map>
+#include <tuple>
+#include <vector>
+
+namespace fes_runs_host {
+
+constexpr int kLaneSteps = 32;  // lane-steps per tile: one warp wide
+constexpr int kWarps = 4;       // warps per CTA = pair groups of a template
+constexpr int kMinPeriods = 8;  // shorter repeats stay with the tiled kernel
+constexpr int kHdrWords = 20;
+constexpr int kTileInts = 8;    // {v0, T, template word offset, E0, first pair, raw word offset, 0, 0}
+
+// 64-bit mix shared by the device signature kernel and the host emulator
+#if defined(__CUDACC__)
+#define FES_RUNS_HD __host__ __device__
+#else
+#define FES_RUNS_HD
+#endif
+FES_RUNS_HD inline uint64_t sig_mix(uint64_t h, uint64_t x) {
+  h = (h ^ x) * 0x9E3779B97F4A7C15ull;
+  return h ^ (h >> 29);
+}
+// signature of a node's relative stencil: incident elements (ascending id) as (e - e_first, local index, corner - v)
+FES_RUNS_HD inline uint64_t node_signature(int32_t v, int32_t ninc, const uint32_t* ne_code, const int32_t* en, int N) {
+  uint64_t h = sig_mix(0x243F6A8885A308D3ull, (uint64_t)ninc);
+  if (ninc == 0) return h;
+  const int64_t e0 = (int64_t)(ne_code[0] >> 3);
+  for (int32_t r = 0; r < ninc; ++r) {
+    const int64_t e = (int64_t)(ne_code[r] >> 3);
+    h = sig_mix(h, (uint64_t)(e - e0) * 8u + (ne_code[r] & 7u));
+    for (int c = 0; c < N; ++c) h = sig_mix(h, (uint64_t)((int64_t)en[e * N + c] - v));
+  }
+  return h;
+}
+
+struct Run {
+  int32_t v0;
+  int32_t P;
+  int32_t periods;
+  int64_t delta;
+};
+
+// Greedy segmentation of the node range into runs; everything else is left to the tiled kernel.
+inline std::vector<Run> segment_runs(const uint64_t* sig, const int32_t* eref, const int32_t* ninc, int64_t n,
+                                     int min_periods = kMinPeriods) {
+  std::vector<Run> runs;
+  int64_t v = 0;
+  while (v < n) {
+    bool found = false;
+    for (int P = 1; P <= 2 && !found; ++P) {
+      if (v + 2 * (int64_t)P > n) break;
+      bool ok = true;
+      for (int phi = 0; phi < P; ++phi) ok = ok && ninc[v + phi] > 0;
+      if (!ok) continue;
+      const int64_t delta = (int64_t)eref[v + P] - eref[v];
+      if (delta <= 0) continue;
+      int64_t w = v + P;
+      while (w < n && sig[w] == sig[w - P] && (int64_t)eref[w] - eref[w - P] == delta) ++w;
+      const int64_t periods = (w - v) / P;
+      if (periods >= min_periods) {
+        runs.push_back(Run{(int32_t)v, P, (int32_t)periods, delta});
+        v += periods * P;
+        found = true;
+      }
+    }
+    if (!found) ++v;
+  }
+  return runs;
+}
+
+// incident elements of node v0 + phi of a period, ascending element id
+struct PhaseStencil {
+  std::vector<int32_t> de;      // element id - E0 (E0 = first incident element of node v0)
+  std::vector<int32_t> a;       // local index of the node in the element
+  std::vector<int32_t> corner;  // N per element: corner node - v0
+};
+
+struct Template {
+  int P = 0, N = 0, c = 0;
+  int64_t delta = 0;
+  int n_lines = 0, TS = 0, LU = 0, LUp = 0, coord_nodes = 0, ppp = 0, n_spans = 0;
+  std::vector<int32_t> words;  // the kernel's program (layout above)
+  std::vector<int32_t> raw;    // the stencil itself, for the verification kernel:
+                               //   {P, delta, ppp, 0, then per phase: ninc, deg, prefix, ninc x (de, a, corner[N])}
+};
+
+inline int64_t floor_div(int64_t a, int64_t b) {  // b > 0
+  int64_t q = a / b;
+  if ((a % b) < 0) --q;
+  return q;
+}
+
+inline void item_split_host(uint32_t cnt, uint32_t L, uint32_t& lg, uint32_t& m) {  // = item_split of plan.cu
+  const uint32_t need = (cnt + L - 1) / L;
+  lg = 0;
+  while ((1u << lg) < need && lg < 5) ++lg;
+  m = (cnt + (1u << lg) - 1) >> lg;
+}
+
+// Build the program of one template.  Returns false when the stencil cannot be encoded (the nodes then stay
+// with the tiled kernel).  L = contributions per partial sum (tile_item_len(N)): the summation tree of a pair
+// is the tiled kernel's, so both kernels produce the same bits for the same pair.
+inline bool build_template(int N, int c, int P, int64_t delta, const std::vector<PhaseStencil>& ph, int L, Template& out) {
+  out = Template();
+  out.P = P; out.N = N; out.c = c; out.delta = delta;
+  if (delta <= 0 || delta > 0x7fffffff || (int)ph.size() != P) return false;
+  struct Line {
+    int64_t d0;
+    int64_t tmin, tmax;
+    std::vector<int64_t> ocan;  // corner offsets relative to v0 + P tau
+  };
+  std::vector<Line> lines;
+  // a line = one residue of the element id modulo delta AND one set of canonical corner offsets: references with
+  // equal residues but other corners (tets: the same Kuhn tet of a neighbouring cell column, (nz - 1) steps along
+  // the same arithmetic progression) are separate lines.  Merging references is only a deduplication: each
+  // reference's corners are verified per lane, so every line is right for the lanes that read it.
+  std::map<std::pair<int64_t, std::vector<int64_t>>, int> line_of;
+  // per reference (phase, r): line and shift
+  std::vector<std::vector<int>> ref_line(P);
+  std::vector<std::vector<int64_t>> ref_shift(P);
+  for (int phi = 0; phi < P; ++phi) {
+    const PhaseStencil& s = ph[phi];
+    const int ninc = (int)s.de.size();
+    if (ninc == 0 || (int)s.a.size() != ninc || (int)s.corner.size() != ninc * N) return false;
+    ref_line[phi].resize(ninc);
+    ref_shift[phi].resize(ninc);
+    for (int r = 0; r < ninc; ++r) {
+      const int64_t q = floor_div(s.de[r], delta), d0 = s.de[r] - q * delta;
+      std::vector<int64_t> oc(N);
+      for (int k = 0; k < N; ++k) oc[k] = (int64_t)s.corner[r * N + k] - (int64_t)P * q;
+      if (s.a[r] < 0 || s.a[r] >= N || s.corner[r * N + s.a[r]] != phi) return false;  // the node itself
+      const auto lkey = std::make_pair(d0, oc);
+      auto it = line_of.find(lkey);
+      int li;
+      if (it == line_of.end()) {
+        li = (int)lines.size();
+        line_of[lkey] = li;
+        lines.push_back(Line{d0, q, q, oc});
+      } else {
+        li = it->second;
+        lines[li].tmin = std::min(lines[li].tmin, q);
+        lines[li].tmax = std::max(lines[li].tmax, q);
+      }
+      ref_line[phi][r] = li;
+      ref_shift[phi][r] = q;
+    }
+  }
+  // lines in ascending d0 (deterministic layout)
+  {
+    std::vector<int> order(lines.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::sort(order.begin(), order.end(), [&](int x, int y) {
+      const int64_t ex = lines[x].d0 + lines[x].tmin * delta, ey = lines[y].d0 + lines[y].tmin * delta;
+      return ex != ey ? ex < ey : lines[x].ocan < lines[y].ocan;
+    });
+    std::vector<int> rank(lines.size());
+    std::vector<Line> sorted;
+    for (size_t i = 0; i < order.size(); ++i) { rank[order[i]] = (int)i; sorted.push_back(lines[order[i]]); }
+    lines.swap(sorted);
+    for (int phi = 0; phi < P; ++phi)
+      for (auto& li : ref_line[phi]) li = rank[li];
+  }
+  const int n_lines = (int)lines.size();
+  int64_t max_ext = 0;
+  for (auto& ln : lines) max_ext = std::max(max_ext, ln.tmax - ln.tmin);
+  if (max_ext > 8) return false;
+  const int TS = kLaneSteps + (int)max_ext;
+  if ((int64_t)n_lines * N * TS > 65535) return false;
+
+  // coordinate spans: every corner of every line covers nodes [o + P tmin, o + P tmax + P (T - 1)]
+  struct Iv { int64_t lo, hi; };
+  std::vector<Iv> ivs;
+  for (auto& ln : lines)
+    for (int k = 0; k < N; ++k) ivs.push_back(Iv{ln.ocan[k] + P * ln.tmin, ln.ocan[k] + P * ln.tmax});
+  std::sort(ivs.begin(), ivs.end(), [](const Iv& x, const Iv& y) { return x.lo < y.lo; });
+  struct Span { int64_t start, ext, base; };
+  std::vector<Span> spans;
+  for (auto& iv : ivs) {
+    if (!spans.empty() && iv.lo <= spans.back().start + spans.back().ext + (int64_t)P * (kMinPeriods - 1) + 1) {
+      spans.back().ext = std::max(spans.back().ext, iv.hi - spans.back().start);
+    } else {
+      spans.push_back(Span{iv.lo, iv.hi - iv.lo, 0});
+    }
+  }
+  int64_t coord_nodes = 0;
+  for (auto& sp : spans) {
+    if (sp.start < -0x3fffffff || sp.start > 0x3fffffff || sp.ext > 4096) return false;
+    sp.base = coord_nodes;
+    coord_nodes += (int64_t)P * (kLaneSteps - 1) + sp.ext + 1;
+    coord_nodes = (coord_nodes + 1) & ~(int64_t)1;  // even: keeps 16-byte alignment of 3-D rows irrelevant, 2-D rows aligned
+  }
+  if (coord_nodes > 8192 || spans.size() > 64) return false;
+  auto cidx_of = [&](int64_t node_rel) -> int64_t {
+    for (auto& sp : spans)
+      if (node_rel >= sp.start && node_rel <= sp.start + sp.ext) return sp.base + (node_rel - sp.start);
+    return -1;
+  };
+
+  // pairs of each phase: distinct corner offsets in ascending order; contributions in ascending element id
+  struct Pair {
+    int phi, k, deg, prefix;
+    std::vector<uint32_t> codes;
+  };
+  std::vector<Pair> pairs;
+  std::vector<int> deg_phi(P), prefix_phi(P);
+  int ppp = 0;
+  for (int phi = 0; phi < P; ++phi) {
+    const PhaseStencil& s = ph[phi];
+    std::vector<int32_t> nb(s.corner);
+    std::sort(nb.begin(), nb.end());
+    nb.erase(std::unique(nb.begin(), nb.end()), nb.end());
+    deg_phi[phi] = (int)nb.size();
+    prefix_phi[phi] = ppp;
+    ppp += deg_phi[phi];
+    for (int k = 0; k < (int)nb.size(); ++k) {
+      Pair p{phi, k, deg_phi[phi], prefix_phi[phi], {}};
+      for (int r = 0; r < (int)s.de.size(); ++r)
+        for (int b = 0; b < N; ++b)
+          if (s.corner[r * N + b] == nb[k]) {
+            const Line& ln = lines[ref_line[phi][r]];
+            const int64_t sh = ref_shift[phi][r] - ln.tmin;
+            const uint32_t ea = (uint32_t)((ref_line[phi][r] * N + s.a[r]) * TS + sh);
+            const uint32_t eb = (uint32_t)((ref_line[phi][r] * N + b) * TS + sh);
+            p.codes.push_back(ea | (eb << 16));
+          }
+      uint32_t lg, m;
+      item_split_host((uint32_t)p.codes.size(), (uint32_t)L, lg, m);
+      if (p.codes.empty() || p.codes.size() > 63 || m > (uint32_t)L || lg > 3) return false;
+      pairs.push_back(p);
+    }
+    if (deg_phi[phi] > 127) return false;
+  }
+  const int row_doubles = c * c * ppp;
+  if (row_doubles > 4095) return false;
+  const int unit_doubles = (c % 2 == 0) ? 2 : 1;
+  const int LU = row_doubles / unit_doubles, LUp = LU | 1;
+
+  // longest-processing-time split of the pairs over the warps (cost: contributions + a constant per pair)
+  std::vector<int> order(pairs.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return pairs[x].codes.size() > pairs[y].codes.size(); });
+  std::vector<std::vector<int>> group(kWarps);
+  std::vector<double> load(kWarps, 0.0);
+  for (int i : order) {
+    int w = 0;
+    for (int x = 1; x < kWarps; ++x)
+      if (load[x] < load[w]) w = x;
+    group[w].push_back(i);
+    load[w] += (double)pairs[i].codes.size() + 1.5;
+  }
+
+  // emit
+  std::vector<int32_t>& W = out.words;
+  W.assign(kHdrWords, 0);
+  W[0] = P; W[1] = n_lines; W[2] = TS; W[3] = LUp; W[4] = LU; W[5] = (int32_t)spans.size();
+  W[13] = (int32_t)coord_nodes; W[14] = (int32_t)delta;
+  W[15] = (int32_t)(uint32_t)((((uint64_t)1 << 32) + (uint64_t)LU - 1) / (uint64_t)LU);
+  W[16] = row_doubles;
+  W[6] = (int32_t)W.size();
+  for (auto& ln : lines) {
+    const int64_t eoff = ln.d0 + ln.tmin * delta;
+    if (eoff < -0x7fffffff || eoff > 0x7fffffff) return false;
+    W.push_back((int32_t)eoff);
+    W.push_back((int32_t)(ln.tmax - ln.tmin));
+    for (int k = 0; k < N; ++k) {
+      const int64_t ci = cidx_of(ln.ocan[k] + P * ln.tmin);
+      if (ci < 0) return false;
+      W.push_back((int32_t)ci);
+    }
+  }
+  W[7] = (int32_t)W.size();
+  for (auto& sp : spans) { W.push_back((int32_t)sp.start); W.push_back((int32_t)sp.ext); W.push_back((int32_t)sp.base); }
+  for (int w = 0; w < kWarps; ++w) {
+    W[8 + w] = (int32_t)W.size();
+    W.push_back((int32_t)group[w].size());
+    for (int i : group[w]) {
+      const Pair& p = pairs[i];
+      uint32_t lg, m;
+      item_split_host((uint32_t)p.codes.size(), (uint32_t)L, lg, m);
+      const uint32_t img = (uint32_t)(c * c * p.prefix + c * p.k);
+      W.push_back((int32_t)(img | ((uint32_t)p.deg << 12) | ((uint32_t)p.codes.size() << 19) | (lg << 25)));
+      for (uint32_t cd : p.codes) W.push_back((int32_t)cd);
+    }
+  }
+  while (W.size() % 4) W.push_back(0);  // 16-byte granularity
+  W[12] = (int32_t)W.size();
+  out.n_lines = n_lines; out.TS = TS; out.LU = LU; out.LUp = LUp; out.coord_nodes = (int)coord_nodes; out.ppp = ppp;
+  out.n_spans = (int)spans.size();
+
+  std::vector<int32_t>& R = out.raw;
+  R = {P, (int32_t)delta, ppp, 0};
+  for (int phi = 0; phi < P; ++phi) {
+    const PhaseStencil& s = ph[phi];
+    R.push_back((int32_t)s.de.size());
+    R.push_back(deg_phi[phi]);
+    R.push_back(prefix_phi[phi]);
+    for (int r = 0; r < (int)s.de.size(); ++r) {
+      R.push_back(s.de[r]);
+      R.push_back(s.a[r]);
+      for (int k = 0; k < N; ++k) R.push_back(s.corner[r * N + k]);
+    }
+  }
+  return true;
+}
+
+// tiles of one run: balanced chunks of <= 32 lane-steps
+inline void split_run(const Run& r, std::vector<std::pair<int32_t, int32_t>>& out /* (first lane-step, T) */) {
+  const int n = (r.periods + kLaneSteps - 1) / kLaneSteps;
+  const int base = r.periods / n, extra = r.periods % n;
+  int32_t t0 = 0;
+  for (int i = 0; i < n; ++i) {
+    const int32_t T = base + (i < extra ? 1 : 0);
+    out.emplace_back(t0, T);
+    t0 += T;
+  }
+}
+
+}  // namespace fes_runs_host

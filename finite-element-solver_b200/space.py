@@ -97,6 +97,16 @@ class ScatterPlan:
         return int(_lib.lib().fes_plan_n_tiles(self._h))
 
     @property
+    def n_run_tiles(self):
+        """Tiles of the stencil-run kernel (structured node ranges); 0 when no run was detected."""
+        return int(_lib.lib().fes_plan_n_run_tiles(self._h))
+
+    @property
+    def run_nodes(self):
+        """Nodes the stencil-run tiles cover."""
+        return int(_lib.lib().fes_plan_run_nodes(self._h))
+
+    @property
     def bytes(self):
         return int(_lib.lib().fes_plan_bytes(self._h))
 

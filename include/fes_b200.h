@@ -86,6 +86,10 @@ int64_t fes_plan_n_pairs(const fes_plan* plan);    /* node-level (block) entries
 int64_t fes_plan_bytes(const fes_plan* plan);      /* device bytes held by the plan                */
 int64_t fes_plan_read_bytes(const fes_plan* plan); /* plan bytes one assembly reads (overhead)     */
 int64_t fes_plan_n_tiles(const fes_plan* plan);    /* tiles of the fused kernel; 0 = untiled fallback */
+/* Stencil runs (structured node ranges assembled from a per-template program instead of per-tile index
+ * streams; P1 triangles / tets, Laplacian and elasticity): tiles and nodes they cover, 0 = none detected. */
+int64_t fes_plan_n_run_tiles(const fes_plan* plan);
+int64_t fes_plan_run_nodes(const fes_plan* plan);
 const int32_t* fes_plan_indptr(const fes_plan* plan);  /* device, n_dofs+1                         */
 const int32_t* fes_plan_indices(const fes_plan* plan); /* device, nnz                              */
 /* host export as int64, the dtypes scipy's csr_array holds in the reference */
