@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "elements.cuh"
 #include "plan.cuh"
@@ -792,7 +793,7 @@ struct Job {
 #include "assemble_runs.cuh"
 
 template <int ELEM, int FORM, int C, int SD, int kTileThreads>
-int launch_tiles(const Job& j, const fes_tileset& T) {
+int launch_tiles(const Job& j, const fes_tileset& T, cudaStream_t stream, bool pdl = true) {
   const fes_tileset* P = &T;
   const TileDims dims{P->geo_stride, P->rec_max, P->pair_max, P->item_max, P->nod_max, P->slot_mode};
   const size_t smem = TileSmem<ELEM, FORM, C, SD>::total(dims.geo_stride, dims.rec_max, dims.pair_max, dims.item_max,
@@ -828,12 +829,12 @@ int launch_tiles(const Job& j, const fes_tileset& T) {
   lc.gridDim = dim3((unsigned)grid);
   lc.blockDim = dim3(kTileThreads);
   lc.dynamicSmemBytes = smem;
-  lc.stream = j.stream;
+  lc.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
-  lc.numAttrs = no_pdl ? 0 : 1;
+  lc.numAttrs = (no_pdl || !pdl) ? 0 : 1;
   FES_CUDA(cudaLaunchKernelEx(&lc, k_assemble_tiles<ELEM, FORM, C, SD, kTileThreads>, (const int32_t*)P->tile_hdr.p,
                               (int)P->n_tiles, (const uint32_t*)P->tile_elems.p, (const uint32_t*)P->rec_local.p,
                               (const int32_t*)P->tile_nodes.p, (const uint32_t*)P->pair_meta.p,
@@ -857,13 +858,26 @@ int run(const Job& j) {
       const int threads = env_threads ? env_threads : tile_threads<FORM>();
       const bool no_runs = getenv("FES_NO_RUNS_LAUNCH") != nullptr;  // A-B knob, read per call: the tiled kernel on every node
       const bool use_runs = runs_supported<ELEM, FORM, C, SD>() && P->runs.active && !no_runs &&
-                            (reinterpret_cast<uintptr_t>(j.out) & 15) == 0;  // the run kernel stores 16-byte units
+                            ((reinterpret_cast<uintptr_t>(j.out) | reinterpret_cast<uintptr_t>(j.coords)) & 15) == 0;  // 16-byte units
       const fes_tileset& T = use_runs ? P->rest : P->full;
-      if (T.n_tiles > 0) {
-        if (threads == 256) FES_TRY((launch_tiles<ELEM, FORM, C, SD, 256>(j, T)));
-        else FES_TRY((launch_tiles<ELEM, FORM, C, SD, 128>(j, T)));
+      static const bool skip_rest = getenv("FES_EXP_SKIP_REST") != nullptr;  // timing experiment only: leaves the remainder rows unwritten
+      if (use_runs) {
+        // the remainder tiles on the plan's side stream, concurrently with the run kernel
+        const fes_runs& R = P->runs;
+        const bool rest = T.n_tiles > 0 && !skip_rest;
+        if (rest) {
+          FES_CUDA(cudaEventRecord(R.ev_fork, j.stream));
+          FES_CUDA(cudaStreamWaitEvent(R.side, R.ev_fork, 0));
+          if (threads == 256) FES_TRY((launch_tiles<ELEM, FORM, C, SD, 256>(j, T, R.side, false)));
+          else FES_TRY((launch_tiles<ELEM, FORM, C, SD, 128>(j, T, R.side, false)));
+          FES_CUDA(cudaEventRecord(R.ev_join, R.side));
+        }
+        FES_TRY((launch_runs<ELEM, FORM, C, SD>(j, j.stream)));
+        if (rest) FES_CUDA(cudaStreamWaitEvent(j.stream, R.ev_join, 0));
+      } else if (T.n_tiles > 0) {
+        if (threads == 256) FES_TRY((launch_tiles<ELEM, FORM, C, SD, 256>(j, T, j.stream)));
+        else FES_TRY((launch_tiles<ELEM, FORM, C, SD, 128>(j, T, j.stream)));
       }
-      if (use_runs) FES_TRY((launch_runs<ELEM, FORM, C, SD>(j)));
       if (FORM != FES_FORM_MASS && j.cf.factor < 0.0)  // a negative global factor (ScaledForm): the kernels ran with |factor|
         k_negate<<<grid_for(P->nnz, 256), 256, 0, j.stream>>>(j.out, P->nnz);
       else
@@ -930,6 +944,36 @@ int check_coeffs(const fes_coeffs* c, Coeffs& out) {
 }
 
 }  // namespace
+
+// ---- template slots of the stencil-run kernel (c_run_tmpl, assemble_runs.cuh) ------------------
+namespace {
+std::atomic<int> g_slot_used[fes_runs::kSlots];
+}
+int runs_slot_acquire(const int32_t* words, size_t n_words, cudaStream_t stream, int* slot) {
+  *slot = -1;
+  if (n_words > (size_t)fes_runs::kMaxTmplWords) return FES_OK;
+  for (int s = 0; s < fes_runs::kSlots; ++s) {
+    int expect = 0;
+    if (!g_slot_used[s].compare_exchange_strong(expect, 1)) continue;
+    // kernels of a plan that released this slot may still be running: wait before overwriting it (plan creation
+    // synchronises anyway)
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess)
+      e = cudaMemcpyToSymbolAsync(c_run_tmpl, words, n_words * sizeof(int32_t), (size_t)s * fes_runs::kMaxTmplWords * sizeof(int32_t),
+                                  cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+      g_slot_used[s].store(0);
+      return set_error(FES_ERR_CUDA, "template upload failed: %s", cudaGetErrorString(e));
+    }
+    *slot = s;
+    return FES_OK;
+  }
+  return FES_OK;
+}
+void runs_slot_release(int slot) {
+  if (slot >= 0 && slot < fes_runs::kSlots) g_slot_used[slot].store(0);
+}
 }  // namespace fes
 
 using namespace fes;

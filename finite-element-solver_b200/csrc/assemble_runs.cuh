@@ -2,20 +2,28 @@
 // plan_runs.cu).  Included by assemble.cu inside namespace fes { namespace {, after Coeffs / element_coeffs.
 //
 // A tile is T <= 32 lane-steps of a run; lane t of every warp owns lane-step t (the P nodes v0 + P t + phi).
-//   staging : the coordinate spans of the tile, global -> shared memory (contiguous ranges, coalesced)
+// The template programs of a plan live in a slot of __constant__ memory (uploaded when the plan is built): every
+// descriptor and program word is a warp-uniform constant-bank load, not a shared-memory or L1 access.
+//   staging : the coordinate spans of the NEXT tile, global -> shared memory with cp.async (contiguous node
+//             ranges; de-interleaved by period phase), issued after phase 1 so they land under phase 2
 //   phase 1 : thread per (element line, entry): cofactors, one rsqrt, the N gradients scaled by sqrt(w mu vol)
 //             -- the arithmetic of k_assemble_tiles, to the bit -- into planes indexed by the entry
-//   phase 2 : warp w walks its share of the period's pairs from the template program (uniform reads); a
-//             contribution is two gradient loads at (code + t): unit stride across the warp, conflict-free.
-//             Partial sums of L contributions are combined in the balanced tree the tiled kernel's xor
-//             shuffles form, so a pair gets the same bits from either kernel.  The block goes into a padded
-//             shared-memory image (odd row stride: the lanes' stores hit distinct banks)
+//   phase 2 : warp w walks its share of the period's pairs; a contribution is two gradient loads at
+//             (code + t): unit stride across the warp, conflict-free, no predicates (short partial sums are
+//             padded with the zero entries).  The partial sums of L contributions are combined in the balanced
+//             tree the tiled kernel's xor shuffles form, so a pair gets the same bits from either kernel.  The
+//             block goes into a padded shared-memory image (odd row stride: the lanes' stores hit distinct banks)
 //   store   : coalesced copy of the image rows to the tile's contiguous slice of `values`
-// Nothing but the 32-byte tile header, the coordinates and the per-element coefficients comes from HBM.
+// Two barriers per tile.  Nothing but the 32-byte tile header, the coordinates and the per-element coefficients
+// comes from HBM.
 
 struct RunDims {
-  int rec_entries, coord_nodes, img_units, tmpl_words;
+  int rec_entries, coord_nodes, img_units;
 };
+
+// Template slots: a plan with runs owns one from fes_plan_create to fes_plan_destroy; a plan that finds none free
+// keeps the tiled kernel for every node.  (A by-value kernel parameter of this size made every launch ~15 us slower.)
+__constant__ int32_t c_run_tmpl[fes_runs::kSlots][fes_runs::kMaxTmplWords];
 
 template <int ELEM, int FORM, int C, int SD>
 constexpr bool runs_supported() {
@@ -26,36 +34,124 @@ constexpr bool runs_supported() {
 template <int C, int SD>
 struct RunSmem {
   static constexpr int UB = (C % 2 == 0) ? 16 : 8;  // bytes per image unit
-  __host__ __device__ static size_t tmpl_bytes(int words) { return up16((size_t)words * 4); }
   __host__ __device__ static size_t xyz_bytes(int nodes) { return up16((size_t)nodes * SD * 8); }
   __host__ __device__ static size_t v2_bytes(int entries) { return up16((size_t)entries * 16); }
   __host__ __device__ static size_t v1_bytes(int entries) { return (SD & 1) ? up16((size_t)entries * 8) : 0; }
   __host__ __device__ static size_t img_bytes(int units) { return up16((size_t)units * UB); }
   __host__ __device__ static size_t total(const RunDims& d) {
-    return tmpl_bytes(d.tmpl_words) + xyz_bytes(d.coord_nodes) + v2_bytes(d.rec_entries) + v1_bytes(d.rec_entries) +
-           img_bytes(d.img_units);
+    return xyz_bytes(d.coord_nodes) + v2_bytes(d.rec_entries) + v1_bytes(d.rec_entries) + img_bytes(d.img_units);
   }
 };
 
-constexpr int kRunThreads = 128;
-static_assert(kRunThreads / 32 == fes_runs_host::kWarps, "one pair group per warp");
 
-template <int ELEM, int FORM, int C, int SD>
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// One partial sum of a pair: exactly L contributions, codes at program words [cw, cw + L); every load is issued
+// before the FMAs.  kDiag: the pair (v, v), both gradients of a contribution are the same vector.
+template <int FORM, int C, int SD, int N, bool kDiag, int NACC>
+__device__ __forceinline__ void run_partial(const int32_t* __restrict__ tmw, int cw, uint32_t lane2, uint32_t lane1,
+                                            double (&acc)[NACC]) {
+  constexpr int L = item_len_of(N);
+  double2 ta[L], tb[L];
+  [[maybe_unused]] double za[L], zb[L];
+#pragma unroll
+  for (int x = 0; x < L; ++x) {
+    const uint32_t code = (uint32_t)tmw[cw + x];
+    const uint32_t oa = code & 0xffffu;
+    ta[x] = lds_f64x2(lane2 + oa);
+    if constexpr (SD & 1) za[x] = lds_f64(lane1 + (oa >> 1));
+    if constexpr (!kDiag) {
+      const uint32_t ob = code >> 16;
+      tb[x] = lds_f64x2(lane2 + ob);
+      if constexpr (SD & 1) zb[x] = lds_f64(lane1 + (ob >> 1));
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < NACC; ++x) acc[x] = 0.0;
+#pragma unroll
+  for (int x = 0; x < L; ++x) {
+    double A_[SD], B_[SD];
+    A_[0] = ta[x].x; A_[1] = ta[x].y;
+    if constexpr (SD & 1) A_[SD - 1] = za[x];
+    if constexpr (kDiag) {
+#pragma unroll
+      for (int s = 0; s < SD; ++s) B_[s] = A_[s];
+    } else {
+      B_[0] = tb[x].x; B_[1] = tb[x].y;
+      if constexpr (SD & 1) B_[SD - 1] = zb[x];
+    }
+    if constexpr (FORM == FES_FORM_LAPLACIAN) {
+#pragma unroll
+      for (int s = 0; s < SD; ++s) acc[0] = fma(A_[s], B_[s], acc[0]);
+    } else {
+#pragma unroll
+      for (int a_ = 0; a_ < C; ++a_)
+#pragma unroll
+        for (int b_ = 0; b_ < C; ++b_) acc[a_ * C + b_] = fma(A_[a_], B_[b_], acc[a_ * C + b_]);
+    }
+  }
+}
+
+template <int NACC>
+__device__ __forceinline__ void run_add(double (&a)[NACC], const double (&b)[NACC]) {
+#pragma unroll
+  for (int x = 0; x < NACC; ++x) a[x] = a[x] + b[x];
+}
+
+// Balanced tree over the 2^lg partial sums of a pair: the order of the tiled kernel's xor-shuffle tree.
+template <int FORM, int C, int SD, int N, bool kDiag, int NACC>
+__device__ __forceinline__ void run_pair_sum(const int32_t* __restrict__ tmw, int cw, uint32_t lg, uint32_t lane2,
+                                             uint32_t lane1, double (&acc)[NACC]) {
+  constexpr int L = item_len_of(N);
+  run_partial<FORM, C, SD, N, kDiag>(tmw, cw, lane2, lane1, acc);
+  if (lg >= 1) {
+    double b[NACC];
+    run_partial<FORM, C, SD, N, kDiag>(tmw, cw + L, lane2, lane1, b);
+    run_add(acc, b);
+    if (lg >= 2) {
+      double c_[NACC];
+      run_partial<FORM, C, SD, N, kDiag>(tmw, cw + 2 * L, lane2, lane1, c_);
+      run_partial<FORM, C, SD, N, kDiag>(tmw, cw + 3 * L, lane2, lane1, b);
+      run_add(c_, b);
+      if constexpr (N == 3) {
+        if (lg >= 3) {  // ((p0 + p1) + (p2 + p3)) + ((p4 + p5) + (p6 + p7))
+          run_add(acc, c_);
+          double d_[NACC];
+          run_partial<FORM, C, SD, N, kDiag>(tmw, cw + 4 * L, lane2, lane1, c_);
+          run_partial<FORM, C, SD, N, kDiag>(tmw, cw + 5 * L, lane2, lane1, b);
+          run_add(c_, b);
+          run_partial<FORM, C, SD, N, kDiag>(tmw, cw + 6 * L, lane2, lane1, d_);
+          run_partial<FORM, C, SD, N, kDiag>(tmw, cw + 7 * L, lane2, lane1, b);
+          run_add(d_, b);
+          run_add(c_, d_);
+        }
+      }
+      run_add(acc, c_);
+    }
+  }
+}
+
+template <int ELEM, int FORM, int C, int SD, int kRunThreads>
 __global__ void __launch_bounds__(kRunThreads)
-k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, const int32_t* __restrict__ tmpl,
-                const double* __restrict__ coords, int64_t n_nodes, int64_t n_el, Coeffs cf, RunDims dims,
+k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const double* __restrict__ coords, int64_t n_nodes, int64_t n_el, Coeffs cf, RunDims dims,
                 double* __restrict__ values) {
   using RS = RunSmem<C, SD>;
   constexpr int N = ET<ELEM>::N, RD = ET<ELEM>::RD;
   static_assert(ET<ELEM>::NQ == 1 && RD == SD, "run tiles: P1 volume elements");
   constexpr int L = item_len_of(N);
-  constexpr int CH = (SD == 3) ? 3 : 2;  // contributions gathered per chunk (loads issued before their FMAs)
-  static_assert(L % CH == 0, "chunks tile a partial sum");
   constexpr int UB = RS::UB;
   constexpr int NACC = (FORM == FES_FORM_ELASTIC) ? C * C : 1;
+  constexpr int kZero = fes_runs_host::kZeroEntries;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int32_t* s_t = reinterpret_cast<int32_t*>(smem_raw);
-  unsigned char* sp = smem_raw + RS::tmpl_bytes(dims.tmpl_words);
+  struct TmView { const int32_t* w; };
+  const TmView tm{c_run_tmpl[slot]};
+  unsigned char* sp = smem_raw;
   double* s_xyz = reinterpret_cast<double*>(sp);    sp += RS::xyz_bytes(dims.coord_nodes);
   double2* v2 = reinterpret_cast<double2*>(sp);     sp += RS::v2_bytes(dims.rec_entries);
   double* v1 = reinterpret_cast<double*>(sp);       sp += RS::v1_bytes(dims.rec_entries);
@@ -69,67 +165,65 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, const int32_t* _
     if constexpr (FORM == FES_FORM_ELASTIC) c2 *= cf.E * cf.mu1;
     sq_uniform = sqrt(c2);
   }
-  asm volatile("griddepcontrol.launch_dependents;");
+  // the zero entries that pad short partial sums
+  if (tid < kZero) {
+    v2[tid] = make_double2(0.0, 0.0);
+    if constexpr (SD & 1) v1[tid] = 0.0;
+  }
   const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   if (n_my <= 0) return;
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  int cur_tmpl = -1;
   const int4* hdr4 = reinterpret_cast<const int4*>(tiles);
-  int4 h0 = __ldg(hdr4 + 2 * (int64_t)blockIdx.x), h1 = __ldg(hdr4 + 2 * (int64_t)blockIdx.x + 1);
-  for (int k = 0; k < n_my; ++k) {
-    const int32_t v0 = h0.x, T = h0.y, toff = h0.z, E0 = h0.w, pair0 = h1.x;
-    if (k + 1 < n_my) {  // the next header flies under this tile
-      const int64_t nx = (int64_t)blockIdx.x + (int64_t)(k + 1) * gridDim.x;
-      h0 = __ldg(hdr4 + 2 * nx);
-      h1 = __ldg(hdr4 + 2 * nx + 1);
-    }
-    if (toff != cur_tmpl) {  // rare: a CTA mostly stays within one template
-      __syncthreads();
-      const int nw = __ldg(tmpl + toff + 12);
-      for (int i = tid; i < nw; i += kRunThreads) s_t[i] = __ldg(tmpl + toff + i);
-      cur_tmpl = toff;
-      __syncthreads();
-    }
-    const int P = s_t[0], n_lines = s_t[1], TS = s_t[2], LUp = s_t[3], LU = s_t[4], n_spans = s_t[5];
-    const int off_lines = s_t[6], off_spans = s_t[7];
-    const int32_t delta = s_t[14];
-    const uint32_t magic = (uint32_t)s_t[15];
+  int4 h0 = __ldg(hdr4 + 2 * (int64_t)blockIdx.x);
+  int32_t pair0 = __ldg(tiles + 8 * (int64_t)blockIdx.x + 4);
 
-    // ---- staging: coordinate spans (contiguous node ranges), granularity = one node (2D) / one double (3D)
-    {
-      constexpr int G = (SD == 2) ? 1 : SD;  // copy items per node
-      int total = 0;
-      for (int s = 0; s < n_spans; ++s) total += (P * (T - 1) + s_t[off_spans + 3 * s + 1] + 1) * G;
-      for (int i = tid; i < total; i += kRunThreads) {
-        int s = 0, j = i;
-        for (;;) {
-          const int len = (P * (T - 1) + s_t[off_spans + 3 * s + 1] + 1) * G;
-          if (j < len) break;
-          j -= len;
-          ++s;
-        }
-        const int64_t g = ((int64_t)v0 + s_t[off_spans + 3 * s]) * G + j;  // global item index
-        const int d = s_t[off_spans + 3 * s + 2] * G + j;                     // table item index
-        if (g >= 0 && g < n_nodes * G) {
-          if constexpr (SD == 2) reinterpret_cast<double2*>(s_xyz)[d] = __ldg(reinterpret_cast<const double2*>(coords) + g);
-          else s_xyz[d] = __ldg(coords + g);
-        }
+  // staging of one tile's coordinate spans: warp w takes spans w, w + 4, ...
+  auto stage = [&](int32_t v0, int32_t T, int32_t toff) {
+    const int P = tm.w[toff], n_spans = tm.w[toff + 5], so = toff + tm.w[toff + 7];
+    constexpr int G = (SD == 2) ? 1 : SD;  // copy items per node: one 16-byte node (2D) or SD doubles
+    for (int s = warp; s < n_spans; s += kRunThreads / 32) {
+      const int32_t start = tm.w[so + 4 * s], ext = tm.w[so + 4 * s + 1], base = tm.w[so + 4 * s + 2], blk = tm.w[so + 4 * s + 3];
+      const int len = (P * (T - 1) + ext + 1) * G;
+      const int64_t g0 = ((int64_t)v0 + start) * G;
+      for (int j = lane; j < len; j += 32) {
+        const int64_t g = g0 + j;
+        if (g < 0 || g >= n_nodes * G) continue;  // entries no lane references may fall outside the mesh
+        const int i = j / G, comp = j - i * G;
+        const int slot = base + (P == 2 ? (i & 1) * blk + (i >> 1) : (P == 1 ? i : (i % P) * blk + i / P));
+        if constexpr (SD == 2) cp_async16(reinterpret_cast<double2*>(s_xyz) + slot, reinterpret_cast<const double2*>(coords) + g);
+        else cp_async8(s_xyz + slot * SD + comp, coords + g);
       }
     }
-    __syncthreads();  // coordinates visible; the previous tile's image has been copied out by everyone
+  };
+  stage(h0.x, h0.y, h0.z);
+  cp_async_wait_all();
+  __syncthreads();
+
+  for (int k = 0; k < n_my; ++k) {
+    const int32_t T = h0.y, toff = h0.z, E0 = h0.w;
+    const int32_t my_pair0 = pair0;
+    const bool has_next = k + 1 < n_my;
+    if (has_next) {  // the next header flies under phase 1
+      const int64_t nx = (int64_t)blockIdx.x + (int64_t)(k + 1) * gridDim.x;
+      h0 = __ldg(hdr4 + 2 * nx);
+      pair0 = __ldg(tiles + 8 * nx + 4);
+    }
+    const int P = tm.w[toff], n_lines = tm.w[toff + 1], TS = tm.w[toff + 2], LUp = tm.w[toff + 3], LU = tm.w[toff + 4];
+    (void)P;
 
     // ---- phase 1: one geometry record per (line, entry)
     {
       const int n_items = n_lines * TS;
       const uint32_t inv_ts = ((1u << 20) + (uint32_t)TS - 1u) / (uint32_t)TS;
+      const int lo = toff + tm.w[toff + 6];
+      const int32_t delta = tm.w[toff + 14];
       for (int i = tid; i < n_items; i += kRunThreads) {
         const int l = (int)(((uint32_t)i * inv_ts) >> 20), tp = i - l * TS;
-        const int32_t* ld = s_t + off_lines + l * (2 + N);
-        if (tp >= T + ld[1]) continue;
+        const int ld = lo + l * (2 + N);
+        if (tp >= T + tm.w[ld + 1]) continue;
         double X[RD + 1][SD];
 #pragma unroll
         for (int n = 0; n <= RD; ++n) {
-          const int ci = ld[2 + n] + P * tp;
+          const int ci = tm.w[ld + 2 + n] + tp;
           if constexpr (SD == 2) {
             const double2 xy = reinterpret_cast<const double2*>(s_xyz)[ci];
             X[n][0] = xy.x; X[n][1] = xy.y;
@@ -142,7 +236,7 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, const int32_t* _
         make_cof<RD, SD>(X, cof, det);
         double f = sq_uniform;
         if (per_elem) {
-          int64_t e = (int64_t)E0 + ld[0] + (int64_t)tp * delta;
+          int64_t e = (int64_t)E0 + tm.w[ld] + (int64_t)tp * delta;
           e = e < 0 ? 0 : (e >= n_el ? n_el - 1 : e);  // entries no lane references may fall outside the mesh
           Material m; double w;
           element_coeffs(cf, e, m, w);
@@ -159,181 +253,119 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, const int32_t* _
         for (int n = 0; n < N; ++n) {
           double gn[SD];
           shape_grad_rows<ELEM, SD>(cof, 0, n, gn);
-          const int ent = (l * N + n) * TS + tp;
+          const int ent = kZero + (l * N + n) * TS + tp;
           v2[ent] = make_double2(gn[0], gn[1]);
           if constexpr (SD & 1) v1[ent] = gn[SD - 1];
         }
       }
     }
-    __syncthreads();  // records visible
+    __syncthreads();  // records visible; the coordinate table is free; the previous image has been copied out
+
+    if (has_next) stage(h0.x, h0.y, h0.z);  // lands under phase 2
 
     // ---- phase 2: warp = pair group, lane = lane-step
-    {
-      const int32_t* prog = s_t + s_t[8 + warp];
-      const int np = prog[0];
-      const bool active = lane < T;
-      const uint32_t lane2 = 16u * (uint32_t)lane, lane1 = 8u * (uint32_t)lane;
+    if (lane < T) {
+      const uint32_t lane2 = v2_b + 16u * (uint32_t)lane, lane1 = v1_b + 8u * (uint32_t)lane;
       const uint32_t img_lane = img_b + (uint32_t)lane * (uint32_t)LUp * (uint32_t)UB;
-      int w = 1;
+      const int pb = toff + tm.w[toff + 20 + warp];
+      const int np = tm.w[pb];
+      int w = pb + 1;
+#pragma unroll 1
       for (int pi = 0; pi < np; ++pi) {
-        const uint32_t head = (uint32_t)prog[w];
-        const uint32_t img = head & 0xfffu, deg = (head >> 12) & 127u, cnt = (head >> 19) & 63u, lg = (head >> 25) & 7u;
-        const uint32_t m = (cnt + (1u << lg) - 1u) >> lg;
-        double lvl[3][NACC];
-        double acc[C][C];
-        for (uint32_t j = 0; j < (1u << lg); ++j) {
-#pragma unroll
-          for (int a_ = 0; a_ < C; ++a_)
-#pragma unroll
-            for (int b_ = 0; b_ < C; ++b_) acc[a_][b_] = 0.0;
-#pragma unroll
-          for (int x0 = 0; x0 < L; x0 += CH) {
-            if ((uint32_t)x0 >= m || j * m + (uint32_t)x0 >= cnt) break;  // uniform
-            uint32_t code[CH];
-            bool on[CH];
-#pragma unroll
-            for (int x = 0; x < CH; ++x) {
-              const uint32_t kk = j * m + (uint32_t)(x0 + x);
-              on[x] = (uint32_t)(x0 + x) < m && kk < cnt;
-              code[x] = on[x] ? (uint32_t)prog[w + 1 + (int)kk] : 0u;
-            }
-            if (active) {
-              double2 ta[CH], tb[CH];
-              [[maybe_unused]] double za[CH], zb[CH];
-#pragma unroll
-              for (int x = 0; x < CH; ++x) {
-                if (!on[x]) continue;
-                const uint32_t ea = code[x] & 0xffffu, eb = code[x] >> 16;
-                ta[x] = lds_f64x2(v2_b + 16u * ea + lane2);
-                if constexpr (SD & 1) za[x] = lds_f64(v1_b + 8u * ea + lane1);
-                if (ea != eb) {
-                  tb[x] = lds_f64x2(v2_b + 16u * eb + lane2);
-                  if constexpr (SD & 1) zb[x] = lds_f64(v1_b + 8u * eb + lane1);
-                } else {
-                  tb[x] = ta[x];
-                  if constexpr (SD & 1) zb[x] = za[x];
-                }
-              }
-#pragma unroll
-              for (int x = 0; x < CH; ++x) {
-                if (!on[x]) continue;
-                double A_[SD], B_[SD];
-                A_[0] = ta[x].x; A_[1] = ta[x].y;
-                B_[0] = tb[x].x; B_[1] = tb[x].y;
-                if constexpr (SD & 1) { A_[SD - 1] = za[x]; B_[SD - 1] = zb[x]; }
-                if constexpr (FORM == FES_FORM_LAPLACIAN) {
-#pragma unroll
-                  for (int s = 0; s < SD; ++s) acc[0][0] = fma(A_[s], B_[s], acc[0][0]);
-                } else {
-#pragma unroll
-                  for (int a_ = 0; a_ < C; ++a_)
-#pragma unroll
-                    for (int b_ = 0; b_ < C; ++b_) acc[a_][b_] = fma(A_[a_], B_[b_], acc[a_][b_]);
-                }
-              }
-            }
-          }
-          // balanced tree over the partial sums: partial j joins level o when bit o of j is set
-          bool parked = false;
-#pragma unroll
-          for (int o = 0; o < 3; ++o) {
-            if (!parked && (uint32_t)o < lg) {
-              if ((j >> o) & 1u) {
-#pragma unroll
-                for (int x = 0; x < NACC; ++x) acc[x / C][x % C] = lvl[o][x] + acc[x / C][x % C];
-              } else {
-#pragma unroll
-                for (int x = 0; x < NACC; ++x) lvl[o][x] = acc[x / C][x % C];
-                parked = true;
-              }
-            }
-          }
-        }
-        w += 1 + (int)cnt;
-        if (!active) continue;
+        const uint32_t head = (uint32_t)tm.w[w];
+        const uint32_t lg = (head >> 27) & 3u;
+        const int cw = w + 1;
+        w += 1 + (L << lg);
+        double acc[NACC];
+        if ((head >> 29) & 1u) run_pair_sum<FORM, C, SD, N, true>(tm.w, cw, lg, lane2, lane1, acc);
+        else run_pair_sum<FORM, C, SD, N, false>(tm.w, cw, lg, lane2, lane1, acc);
         double K[C][C];
         if constexpr (FORM == FES_FORM_ELASTIC) {
           double tr = 0.0;
 #pragma unroll
-          for (int a_ = 0; a_ < C; ++a_) tr += acc[a_][a_];
+          for (int a_ = 0; a_ < C; ++a_) tr += acc[a_ * C + a_];
 #pragma unroll
           for (int a_ = 0; a_ < C; ++a_)
 #pragma unroll
-            for (int b_ = 0; b_ < C; ++b_) K[a_][b_] = fma(cf.lam_over_mu, acc[a_][b_], acc[b_][a_]) + (a_ == b_ ? tr : 0.0);
+            for (int b_ = 0; b_ < C; ++b_)
+              K[a_][b_] = fma(cf.lam_over_mu, acc[a_ * C + b_], acc[b_ * C + a_]) + (a_ == b_ ? tr : 0.0);
         } else {
-          K[0][0] = acc[0][0];
+          K[0][0] = acc[0];
         }
+        const uint32_t r0 = img_lane + (head & 0x7fffu), row_b = (head >> 15) & 0xfffu;
         if constexpr (C == 2) {
-          const uint32_t r0 = img_lane + 16u * (img >> 1);
           sts_f64x2(r0, K[0][0], K[0][1]);
-          sts_f64x2(r0 + 16u * deg, K[1][0], K[1][1]);
+          sts_f64x2(r0 + row_b, K[1][0], K[1][1]);
         } else {
 #pragma unroll
           for (int a_ = 0; a_ < C; ++a_)
 #pragma unroll
-            for (int b_ = 0; b_ < C; ++b_) sts_f64(img_lane + 8u * (img + (uint32_t)(a_ * C) * deg + (uint32_t)b_), K[a_][b_]);
+            for (int b_ = 0; b_ < C; ++b_) sts_f64(r0 + (uint32_t)a_ * row_b + 8u * (uint32_t)b_, K[a_][b_]);
         }
       }
     }
-    __syncthreads();  // image complete; records and coordinates free
+    cp_async_wait_all();
+    __syncthreads();  // image complete; records free; the next tile's coordinates visible
 
-    // ---- store: image rows -> the tile's contiguous slice of `values`
+    // ---- store: image rows -> the tile's contiguous slice of `values`; thread x takes units x, x + 128, ...
     {
-      const int total = T * LU;
-      unsigned char* dst = reinterpret_cast<unsigned char*>(values + (int64_t)C * C * pair0);
+      unsigned char* dst = reinterpret_cast<unsigned char*>(values + (int64_t)C * C * my_pair0);
+      const int total = T * LU, dr = tm.w[toff + 10], du = tm.w[toff + 11];
+      int r = tid / LU, u = tid - r * LU;
+#pragma unroll 2
       for (int x = tid; x < total; x += kRunThreads) {
-        const uint32_t r = __umulhi((uint32_t)x, magic), u = (uint32_t)x - r * (uint32_t)LU;
-        const unsigned char* src = s_img + (size_t)(r * (uint32_t)LUp + u) * UB;
-        if constexpr (UB == 16) *reinterpret_cast<double2*>(dst + (size_t)x * 16) = *reinterpret_cast<const double2*>(src);
-        else *reinterpret_cast<double*>(dst + (size_t)x * 8) = *reinterpret_cast<const double*>(src);
+        const uint32_t src = img_b + (uint32_t)(r * LUp + u) * (uint32_t)UB;
+        if constexpr (UB == 16) {
+          const double2 v = lds_f64x2(src);
+          *reinterpret_cast<double2*>(dst + (size_t)(uint32_t)x * 16) = v;
+        } else {
+          *reinterpret_cast<double*>(dst + (size_t)(uint32_t)x * 8) = lds_f64(src);
+        }
+        r += dr; u += du;
+        if (u >= LU) { u -= LU; ++r; }
       }
     }
   }
 }
 
+template <int ELEM, int FORM, int C, int SD, int kRunThreads>
+int launch_runs_t(const Job& j, cudaStream_t stream) {
+  const fes_runs& R = j.plan->runs;
+  const RunDims dims{R.max_rec_entries, R.max_coord_nodes, R.max_img_units};
+  const size_t smem = RunSmem<C, SD>::total(dims);
+  static size_t configured = 0, occ_smem = 0;
+  static int per_sm = 0, sms = 0;
+  if (per_sm == 0 || smem != occ_smem) {
+    if (smem > configured && smem + 1024 > 48 * 1024)
+      FES_CUDA(cudaFuncSetAttribute(k_assemble_runs<ELEM, FORM, C, SD, kRunThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = std::max(configured, smem);
+    int dev = 0;
+    FES_CUDA(cudaGetDevice(&dev));
+    FES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_runs<ELEM, FORM, C, SD, kRunThreads>, kRunThreads, smem));
+    occ_smem = smem;
+    if (per_sm < 1) {
+      per_sm = 0;
+      return set_error(FES_ERR_CUDA, "run assembly kernel does not fit on an SM (%zu B smem)", smem);
+    }
+    if (getenv("FES_PLAN_DEBUG")) fprintf(stderr, "[fes assemble runs] threads=%d smem=%zu B CTAs/SM=%d\n", kRunThreads, smem, per_sm);
+  }
+  Coeffs cf = j.cf;
+  if (cf.factor < 0.0) { cf.factor = -cf.factor; cf.sign = -1.0; }
+  const int64_t grid = std::min<int64_t>(R.n_tiles, (int64_t)sms * per_sm);
+  k_assemble_runs<ELEM, FORM, C, SD, kRunThreads><<<(unsigned)grid, kRunThreads, smem, stream>>>(
+      (const int32_t*)R.tiles.p, (int)R.n_tiles, R.slot, (const double*)j.coords, (int64_t)j.plan->n_nodes,
+      (int64_t)j.plan->n_el, cf, dims, j.out);
+  FES_LAUNCH_CHECK();
+  return FES_OK;
+}
+
 template <int ELEM, int FORM, int C, int SD>
-int launch_runs(const Job& j) {
+int launch_runs(const Job& j, cudaStream_t stream) {
   if constexpr (!runs_supported<ELEM, FORM, C, SD>()) {
     return FES_OK;
   } else {
-    const fes_runs& R = j.plan->runs;
-    const RunDims dims{R.max_rec_entries, R.max_coord_nodes, R.max_img_units, R.max_tmpl_words};
-    const size_t smem = RunSmem<C, SD>::total(dims);
-    static size_t configured = 0, occ_smem = 0;
-    static int per_sm = 0, sms = 0;
-    if (per_sm == 0 || smem != occ_smem) {
-      if (smem > configured && smem + 1024 > 48 * 1024)
-        FES_CUDA(cudaFuncSetAttribute(k_assemble_runs<ELEM, FORM, C, SD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = std::max(configured, smem);
-      int dev = 0;
-      FES_CUDA(cudaGetDevice(&dev));
-      FES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      FES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_runs<ELEM, FORM, C, SD>, kRunThreads, smem));
-      occ_smem = smem;
-      if (per_sm < 1) {
-        per_sm = 0;
-        return set_error(FES_ERR_CUDA, "run assembly kernel does not fit on an SM (%zu B smem)", smem);
-      }
-      if (getenv("FES_PLAN_DEBUG")) fprintf(stderr, "[fes assemble runs] smem=%zu B CTAs/SM=%d\n", smem, per_sm);
-    }
-    Coeffs cf = j.cf;
-    if (cf.factor < 0.0) { cf.factor = -cf.factor; cf.sign = -1.0; }
-    const int64_t grid = std::min<int64_t>(R.n_tiles, (int64_t)sms * per_sm);
-    static const bool no_pdl = getenv("FES_NO_PDL") != nullptr;
-    cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3((unsigned)grid);
-    lc.blockDim = dim3(kRunThreads);
-    lc.dynamicSmemBytes = smem;
-    lc.stream = j.stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = attr;
-    lc.numAttrs = no_pdl ? 0 : 1;
-    FES_CUDA(cudaLaunchKernelEx(&lc, k_assemble_runs<ELEM, FORM, C, SD>, (const int32_t*)R.tiles.p, (int)R.n_tiles,
-                                (const int32_t*)R.tmpl.p, (const double*)j.coords, (int64_t)j.plan->n_nodes, (int64_t)j.plan->n_el,
-                                cf, dims, j.out));
-    FES_LAUNCH_CHECK();
-    return FES_OK;
+    if (j.plan->runs.n_warps == 8) return launch_runs_t<ELEM, FORM, C, SD, 256>(j, stream);
+    return launch_runs_t<ELEM, FORM, C, SD, 128>(j, stream);
   }
 }

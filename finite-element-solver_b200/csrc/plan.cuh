@@ -1,5 +1,7 @@
 // The CSR pattern + scatter plan handle shared between plan.cu (builder) and assemble.cu.
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 // One tiling of (a subset of) the nodes for the fused assembly kernel k_assemble_tiles.
@@ -56,13 +58,34 @@ struct fes_runs {
   bool active = false;
   int64_t n_tiles = 0, n_nodes_covered = 0, n_templates = 0;
   // shared-memory sizing of k_assemble_runs: maxima over the templates
-  int max_rec_entries = 0;             // n_lines * N * TS
-  int max_coord_nodes = 0, max_img_units = 0, max_tmpl_words = 0;
+  int max_rec_entries = 0;             // 32 zero entries + n_lines * N * TS
+  int max_coord_nodes = 0, max_img_units = 0;
   static constexpr int kTileInts = 8;  // {v0, T, template word offset, E0, first pair, raw word offset, 0, 0}
+  // Every template program of the plan (layout: runs_template.hpp) sits in one slot of the kernel's __constant__
+  // memory: the warp-uniform program reads of phase 2 and the line / span descriptors are constant-bank loads and
+  // cost no shared-memory or L1 bandwidth.  The slot is owned from plan creation to destruction.
+  static constexpr int kMaxTmplWords = 3072, kSlots = 4;
+  int slot = -1;
+  int n_warps = 4;                     // warps per CTA of the run kernel (= pair groups of the templates): 4 or 8
+  // The remainder tiles (fes_plan::rest) run concurrently with the run kernel on this side stream, forked from and
+  // joined back into the caller's stream with the two events (back to back on one stream the small kernel's drain
+  // and, with programmatic dependent launch, its early-resident CTAs cost 8-40 us per assembly).
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   fes::DevBuf<int32_t> tiles;
-  fes::DevBuf<int32_t> tmpl;           // all template programs, each 16-byte aligned (layout: runs_template.hpp)
-  size_t bytes() const { return tiles.bytes() + tmpl.bytes(); }
+  size_t bytes() const { return tiles.bytes(); }
+  ~fes_runs();
 };
+namespace fes {
+int runs_slot_acquire(const int32_t* words, size_t n_words, cudaStream_t stream, int* slot);  // assemble.cu; *slot = -1: none free
+void runs_slot_release(int slot);
+}
+inline fes_runs::~fes_runs() {
+  if (slot >= 0) fes::runs_slot_release(slot);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
+  if (side) cudaStreamDestroy(side);
+}
 
 struct fes_plan {
   int64_t n_el = 0, n_nodes = 0, n_dofs = 0, n_pairs = 0, nnz = 0, n_contrib = 0;

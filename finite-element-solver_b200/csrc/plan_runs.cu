@@ -105,6 +105,10 @@ int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32
   std::vector<int32_t> tiles;
   std::vector<int32_t> covered;  // {begin, end} node ranges, ascending
   const int L = tile_item_len(N);
+  // warps per CTA: tets carry 15 pairs / 96 contributions per node and 18 element lines per tile, enough for eight
+  // pair groups; the triangle templates (14 pairs per period) are split over four
+  int n_warps = (N == 4) ? 8 : 4;
+  if (const char* env = getenv("FES_RUNS_WARPS")) n_warps = atoi(env) == 8 ? 8 : 4;  // tuning knob
   int64_t n_cov = 0;
   for (const Run& r : runs) {
     const Key key{r.P, sig[r.v0], r.P > 1 ? sig[r.v0 + 1] : 0ull, r.delta,
@@ -136,7 +140,7 @@ int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32
         }
       }
       Template t;
-      if (build_template(N, c, r.P, r.delta, ph, L, t)) {
+      if (build_template(N, c, r.P, r.delta, ph, L, n_warps, t) && blob.size() + t.words.size() <= (size_t)fes_runs::kMaxTmplWords) {
         ti = (int)tmpls.size();
         word_off.push_back((int32_t)blob.size());
         raw_off.push_back((int32_t)raw.size());
@@ -150,7 +154,7 @@ int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32
     }
     if (ti < 0) continue;
     std::vector<std::pair<int32_t, int32_t>> parts;
-    split_run(r, parts);
+    split_run(r, tmpls[ti].Tmax, parts);
     for (auto& pt : parts) {
       const int32_t v0 = r.v0 + r.P * pt.first;
       const int32_t hdr[kTileInts] = {v0, pt.second, word_off[ti], eref[v0], h_np[v0], raw_off[ti], 0, 0};
@@ -166,14 +170,12 @@ int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32
   if (nt == 0 || (double)n_cov < min_cover * (double)nn) return FES_OK;
 
   FES_CUDA(Rn.tiles.alloc(tiles.size()));
-  FES_CUDA(Rn.tmpl.alloc(blob.size()));
   DevBuf<int32_t> d_raw;
   DevBuf<int> bad;
   FES_CUDA(d_raw.alloc(raw.size()));
   FES_CUDA(bad.alloc(1));
   FES_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), stream));
   FES_CUDA(cudaMemcpyAsync(Rn.tiles.p, tiles.data(), tiles.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
-  FES_CUDA(cudaMemcpyAsync(Rn.tmpl.p, blob.data(), blob.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
   FES_CUDA(cudaMemcpyAsync(d_raw.p, raw.data(), raw.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
   k_verify_runs<<<grid_for(nt * kLaneSteps, kBlock), kBlock, 0, stream>>>(Rn.tiles.p, nt, d_raw.p, P->ne_ptr.p, P->ne_code.p,
                                                                          P->node_ptr.p, d_elem_nodes, N, nn, P->n_el, bad.p);
@@ -184,18 +186,28 @@ int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32
   if (h_bad) {  // a signature collision or an inconsistent template: the tiled kernel keeps every node
     if (getenv("FES_PLAN_DEBUG")) fprintf(stderr, "[fes runs] verification failed: runs disabled\n");
     Rn.tiles.release();
-    Rn.tmpl.release();
     return FES_OK;
   }
   Rn.n_tiles = nt;
   Rn.n_nodes_covered = n_cov;
   Rn.n_templates = (int64_t)tmpls.size();
-  Rn.max_rec_entries = Rn.max_coord_nodes = Rn.max_img_units = Rn.max_tmpl_words = 0;
+  Rn.max_rec_entries = Rn.max_coord_nodes = Rn.max_img_units = 0;
   for (const Template& t : tmpls) {
-    Rn.max_rec_entries = std::max(Rn.max_rec_entries, t.n_lines * N * t.TS);
+    Rn.max_rec_entries = std::max(Rn.max_rec_entries, t.rec_entries);
     Rn.max_coord_nodes = std::max(Rn.max_coord_nodes, t.coord_nodes);
-    Rn.max_img_units = std::max(Rn.max_img_units, kLaneSteps * t.LUp);
-    Rn.max_tmpl_words = std::max(Rn.max_tmpl_words, (int)t.words.size());
+    Rn.max_img_units = std::max(Rn.max_img_units, t.Tmax * t.LUp);
+  }
+  if (Rn.slot >= 0) { runs_slot_release(Rn.slot); Rn.slot = -1; }
+  FES_TRY(runs_slot_acquire(blob.data(), blob.size(), stream, &Rn.slot));
+  if (Rn.slot < 0) {  // every template slot is held by a live plan: this one keeps the tiled kernel
+    Rn.tiles.release();
+    return FES_OK;
+  }
+  Rn.n_warps = n_warps;
+  if (!Rn.side) {
+    FES_CUDA(cudaStreamCreateWithFlags(&Rn.side, cudaStreamNonBlocking));
+    FES_CUDA(cudaEventCreateWithFlags(&Rn.ev_fork, cudaEventDisableTiming));
+    FES_CUDA(cudaEventCreateWithFlags(&Rn.ev_join, cudaEventDisableTiming));
   }
   int64_t prev = 0;
   for (size_t i = 0; i + 1 < covered.size(); i += 2) {

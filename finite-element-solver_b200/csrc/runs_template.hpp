@@ -18,16 +18,21 @@
 //
 // Template blob (int32 words; offsets relative to the template's first word):
 //   [0] P  [1] n_lines  [2] TS (plane stride, entries)  [3] LUp (padded image row stride, units)
-//   [4] LU (image row, units)  [5] n_spans  [6] off_lines  [7] off_spans  [8..11] off_prog[warp]
-//   [12] n_words  [13] coordinate nodes staged per tile (32 lane-steps)  [14] delta  [15] magic = ceil(2^32 / LU)
-//   [16] doubles per image row (c^2 * pairs per period)  [17..19] reserved
+//   [4] LU (image row, units)  [5] n_spans  [6] off_lines  [7] off_spans  [8] n_warps (CTA = 32 n_warps threads)
+//   [10] threads / LU  [11] threads mod LU (the store loop's row / unit increments per step of the CTA)
+//   [12] n_words  [13] coordinate slots staged per tile  [14] delta  [15] Tmax (lane-steps per tile, 31 or 32)
+//   [16] doubles per image row (c^2 * pairs per period)  [17] record entries (32 zero entries + n_lines * N * TS)
+//   [20..27] off_prog[warp]
 //   lines : n_lines x {eoff, ext, cidx[N]}   element of entry tau' = E0 + eoff + tau' * delta, entries
-//           tau' < T + ext; corner c sits at coordinate-table node cidx[c] + P * tau'
-//   spans : n_spans x {start, ext, base}     nodes v0 + start + i, i < P (T - 1) + ext + 1, staged at table
-//           node base + i
-//   prog  : per warp {n_pairs, then per pair: head, codes[cnt]}
-//           head = img (12) | deg (7) << 12 | cnt (6) << 19 | lg (3) << 25     img = c^2 * prefix_phi + c * k (doubles)
-//           code = entry_a | entry_b << 16, entry = (line * N + local) * TS + (shift - taumin_line); lane t adds t
+//           tau' < T + ext; corner c sits in coordinate slot cidx[c] + tau'
+//   spans : n_spans x {start, ext, base, blk}  nodes v0 + start + i, i < P (T - 1) + ext + 1, staged in slot
+//           base + (i mod P) * blk + i / P (de-interleaved by period phase)
+//   prog  : per warp {n_pairs, then per pair: head, codes[2^lg * L]}
+//           head = img_b (15) | row_b (12) << 15 | lg (2) << 27 | diag << 29: byte offset 8 (c^2 prefix_phi + c k) of the
+//                  block in the lane's image row, bytes 8 c deg between the block's rows
+//           code = 16 entry_a | 16 entry_b << 16 (byte offsets in the double2 planes; the z plane sits at half),
+//                  entry = 32 + (line * N + local) * TS + (shift - taumin_line); lane t adds t;
+//           partial sum j of a pair = its L codes [j L, j L + L), short ones padded with code 0 (the zero entries)
 // An image UNIT is 16 bytes when c is even, 8 bytes otherwise; LUp = LU | 1 keeps the lanes' stores on distinct banks.
 #pragma once
 #include <stdint.h>
@@ -40,9 +45,10 @@
 namespace fes_runs_host {
 
 constexpr int kLaneSteps = 32;  // lane-steps per tile: one warp wide
-constexpr int kWarps = 4;       // warps per CTA = pair groups of a template
+constexpr int kMaxWarps = 8;    // warps per CTA = pair groups of a template: 4 or 8 (the plan's choice)
+constexpr int kZeroEntries = 32;  // record entries [0, 32) hold zeros: the padding of short partial sums (lane t reads entry t)
 constexpr int kMinPeriods = 8;  // shorter repeats stay with the tiled kernel
-constexpr int kHdrWords = 20;
+constexpr int kHdrWords = 28;
 constexpr int kTileInts = 8;    // {v0, T, template word offset, E0, first pair, raw word offset, 0, 0}
 
 // 64-bit mix shared by the device signature kernel and the host emulator
@@ -113,7 +119,7 @@ struct PhaseStencil {
 struct Template {
   int P = 0, N = 0, c = 0;
   int64_t delta = 0;
-  int n_lines = 0, TS = 0, LU = 0, LUp = 0, coord_nodes = 0, ppp = 0, n_spans = 0;
+  int n_lines = 0, TS = 0, LU = 0, LUp = 0, coord_nodes = 0, ppp = 0, n_spans = 0, Tmax = 0, rec_entries = 0;
   std::vector<int32_t> words;  // the kernel's program (layout above)
   std::vector<int32_t> raw;    // the stencil itself, for the verification kernel:
                                //   {P, delta, ppp, 0, then per phase: ninc, deg, prefix, ninc x (de, a, corner[N])}
@@ -135,10 +141,12 @@ inline void item_split_host(uint32_t cnt, uint32_t L, uint32_t& lg, uint32_t& m)
 // Build the program of one template.  Returns false when the stencil cannot be encoded (the nodes then stay
 // with the tiled kernel).  L = contributions per partial sum (tile_item_len(N)): the summation tree of a pair
 // is the tiled kernel's, so both kernels produce the same bits for the same pair.
-inline bool build_template(int N, int c, int P, int64_t delta, const std::vector<PhaseStencil>& ph, int L, Template& out) {
+inline bool build_template(int N, int c, int P, int64_t delta, const std::vector<PhaseStencil>& ph, int L, int n_warps,
+                           Template& out) {
   out = Template();
   out.P = P; out.N = N; out.c = c; out.delta = delta;
-  if (delta <= 0 || delta > 0x7fffffff || (int)ph.size() != P) return false;
+  if (delta <= 0 || delta > 0x7fffffff || (int)ph.size() != P || n_warps < 1 || n_warps > kMaxWarps) return false;
+  const int kThreads = 32 * n_warps;
   struct Line {
     int64_t d0;
     int64_t tmin, tmax;
@@ -199,8 +207,13 @@ inline bool build_template(int N, int c, int P, int64_t delta, const std::vector
   int64_t max_ext = 0;
   for (auto& ln : lines) max_ext = std::max(max_ext, ln.tmax - ln.tmin);
   if (max_ext > 8) return false;
-  const int TS = kLaneSteps + (int)max_ext;
-  if ((int64_t)n_lines * N * TS > 65535) return false;
+  // lane-steps per tile: 32, or 32 - max_ext when that saves a whole pass of phase 1 (the CTA's 32 n_warps threads
+  // walk n_lines * TS records: with 128 threads 8 lines x 33 entries = 3 passes for 32 lane-steps, 8 x 32 = 2 for 31)
+  auto pass_cost = [&](int T) { return (double)((n_lines * (T + (int)max_ext) + kThreads - 1) / kThreads) / (double)T; };
+  const int Tmax = (max_ext > 0 && pass_cost(kLaneSteps - (int)max_ext) < pass_cost(kLaneSteps)) ? kLaneSteps - (int)max_ext : kLaneSteps;
+  const int TS = Tmax + (int)max_ext;
+  const int64_t rec_entries = kZeroEntries + (int64_t)n_lines * N * TS;
+  if (rec_entries > 4095) return false;  // 16-bit BYTE offsets of the double2 planes in the codes
 
   // coordinate spans: every corner of every line covers nodes [o + P tmin, o + P tmax + P (T - 1)]
   struct Iv { int64_t lo, hi; };
@@ -208,37 +221,47 @@ inline bool build_template(int N, int c, int P, int64_t delta, const std::vector
   for (auto& ln : lines)
     for (int k = 0; k < N; ++k) ivs.push_back(Iv{ln.ocan[k] + P * ln.tmin, ln.ocan[k] + P * ln.tmax});
   std::sort(ivs.begin(), ivs.end(), [](const Iv& x, const Iv& y) { return x.lo < y.lo; });
-  struct Span { int64_t start, ext, base; };
+  struct Span { int64_t start, ext, base, blk; };
   std::vector<Span> spans;
   for (auto& iv : ivs) {
     if (!spans.empty() && iv.lo <= spans.back().start + spans.back().ext + (int64_t)P * (kMinPeriods - 1) + 1) {
       spans.back().ext = std::max(spans.back().ext, iv.hi - spans.back().start);
     } else {
-      spans.push_back(Span{iv.lo, iv.hi - iv.lo, 0});
+      spans.push_back(Span{iv.lo, iv.hi - iv.lo, 0, 0});
     }
   }
-  int64_t coord_nodes = 0;
+  // A span is staged de-interleaved by node parity (period): node i of the span sits in slot
+  // base + (i mod P) * blk + i / P, so the corner of entry tau' (node i0 + P tau') is slot(i0) + tau': unit stride
+  // across the threads of phase 1 whatever the period
+  int64_t coord_slots = 0;
   for (auto& sp : spans) {
     if (sp.start < -0x3fffffff || sp.start > 0x3fffffff || sp.ext > 4096) return false;
-    sp.base = coord_nodes;
-    coord_nodes += (int64_t)P * (kLaneSteps - 1) + sp.ext + 1;
-    coord_nodes = (coord_nodes + 1) & ~(int64_t)1;  // even: keeps 16-byte alignment of 3-D rows irrelevant, 2-D rows aligned
+    sp.base = coord_slots;
+    sp.blk = ((int64_t)P * (Tmax - 1) + sp.ext + 1 + P - 1) / P;
+    if (P == 2) while (sp.blk % 8 != 4) ++sp.blk;  // a quarter-warp's even / odd nodes land in disjoint bank groups
+    coord_slots += (int64_t)P * sp.blk;
+    coord_slots = (coord_slots + 1) & ~(int64_t)1;
   }
-  if (coord_nodes > 8192 || spans.size() > 64) return false;
+  if (coord_slots > 8192 || spans.size() > 64) return false;
   auto cidx_of = [&](int64_t node_rel) -> int64_t {
     for (auto& sp : spans)
-      if (node_rel >= sp.start && node_rel <= sp.start + sp.ext) return sp.base + (node_rel - sp.start);
+      if (node_rel >= sp.start && node_rel <= sp.start + sp.ext) {
+        const int64_t i = node_rel - sp.start;
+        return sp.base + (i % P) * sp.blk + i / P;
+      }
     return -1;
   };
 
   // pairs of each phase: distinct corner offsets in ascending order; contributions in ascending element id
   struct Pair {
     int phi, k, deg, prefix;
+    bool diag;
     std::vector<uint32_t> codes;
   };
   std::vector<Pair> pairs;
   std::vector<int> deg_phi(P), prefix_phi(P);
   int ppp = 0;
+  const uint32_t lg_cap = (N == 3) ? 3u : 2u;  // partial sums per pair the kernel's summation trees are compiled for: 2^lg_cap
   for (int phi = 0; phi < P; ++phi) {
     const PhaseStencil& s = ph[phi];
     std::vector<int32_t> nb(s.corner);
@@ -248,49 +271,50 @@ inline bool build_template(int N, int c, int P, int64_t delta, const std::vector
     prefix_phi[phi] = ppp;
     ppp += deg_phi[phi];
     for (int k = 0; k < (int)nb.size(); ++k) {
-      Pair p{phi, k, deg_phi[phi], prefix_phi[phi], {}};
+      Pair p{phi, k, deg_phi[phi], prefix_phi[phi], true, {}};
       for (int r = 0; r < (int)s.de.size(); ++r)
         for (int b = 0; b < N; ++b)
           if (s.corner[r * N + b] == nb[k]) {
             const Line& ln = lines[ref_line[phi][r]];
             const int64_t sh = ref_shift[phi][r] - ln.tmin;
-            const uint32_t ea = (uint32_t)((ref_line[phi][r] * N + s.a[r]) * TS + sh);
-            const uint32_t eb = (uint32_t)((ref_line[phi][r] * N + b) * TS + sh);
-            p.codes.push_back(ea | (eb << 16));
+            const uint32_t ea = (uint32_t)(kZeroEntries + (ref_line[phi][r] * N + s.a[r]) * TS + sh);
+            const uint32_t eb = (uint32_t)(kZeroEntries + (ref_line[phi][r] * N + b) * TS + sh);
+            p.diag = p.diag && ea == eb;
+            p.codes.push_back((16u * ea) | ((16u * eb) << 16));
           }
       uint32_t lg, m;
       item_split_host((uint32_t)p.codes.size(), (uint32_t)L, lg, m);
-      if (p.codes.empty() || p.codes.size() > 63 || m > (uint32_t)L || lg > 3) return false;
+      if (p.codes.empty() || m > (uint32_t)L || lg > lg_cap) return false;
       pairs.push_back(p);
     }
     if (deg_phi[phi] > 127) return false;
   }
   const int row_doubles = c * c * ppp;
-  if (row_doubles > 4095) return false;
+  if (row_doubles > 4095 || 8 * c * 127 > 4095) return false;
   const int unit_doubles = (c % 2 == 0) ? 2 : 1;
   const int LU = row_doubles / unit_doubles, LUp = LU | 1;
 
-  // longest-processing-time split of the pairs over the warps (cost: contributions + a constant per pair)
+  // longest-processing-time split of the pairs over the warps (cost: gradient loads + a constant per pair)
+  auto pair_cost = [&](const Pair& p) { return (double)p.codes.size() * (p.diag ? 0.6 : 1.0) + 1.5; };
   std::vector<int> order(pairs.size());
   for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return pairs[x].codes.size() > pairs[y].codes.size(); });
-  std::vector<std::vector<int>> group(kWarps);
-  std::vector<double> load(kWarps, 0.0);
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return pair_cost(pairs[x]) > pair_cost(pairs[y]); });
+  std::vector<std::vector<int>> group(n_warps);
+  std::vector<double> load(n_warps, 0.0);
   for (int i : order) {
     int w = 0;
-    for (int x = 1; x < kWarps; ++x)
+    for (int x = 1; x < n_warps; ++x)
       if (load[x] < load[w]) w = x;
     group[w].push_back(i);
-    load[w] += (double)pairs[i].codes.size() + 1.5;
+    load[w] += pair_cost(pairs[i]);
   }
 
   // emit
   std::vector<int32_t>& W = out.words;
   W.assign(kHdrWords, 0);
   W[0] = P; W[1] = n_lines; W[2] = TS; W[3] = LUp; W[4] = LU; W[5] = (int32_t)spans.size();
-  W[13] = (int32_t)coord_nodes; W[14] = (int32_t)delta;
-  W[15] = (int32_t)(uint32_t)((((uint64_t)1 << 32) + (uint64_t)LU - 1) / (uint64_t)LU);
-  W[16] = row_doubles;
+  W[13] = (int32_t)coord_slots; W[14] = (int32_t)delta; W[15] = Tmax; W[16] = row_doubles; W[17] = (int32_t)rec_entries;
+  W[8] = n_warps; W[10] = kThreads / LU; W[11] = kThreads % LU;
   W[6] = (int32_t)W.size();
   for (auto& ln : lines) {
     const int64_t eoff = ln.d0 + ln.tmin * delta;
@@ -304,23 +328,30 @@ inline bool build_template(int N, int c, int P, int64_t delta, const std::vector
     }
   }
   W[7] = (int32_t)W.size();
-  for (auto& sp : spans) { W.push_back((int32_t)sp.start); W.push_back((int32_t)sp.ext); W.push_back((int32_t)sp.base); }
-  for (int w = 0; w < kWarps; ++w) {
-    W[8 + w] = (int32_t)W.size();
+  for (auto& sp : spans) {
+    W.push_back((int32_t)sp.start); W.push_back((int32_t)sp.ext); W.push_back((int32_t)sp.base); W.push_back((int32_t)sp.blk);
+  }
+  for (int w = 0; w < n_warps; ++w) {
+    W[20 + w] = (int32_t)W.size();
     W.push_back((int32_t)group[w].size());
     for (int i : group[w]) {
       const Pair& p = pairs[i];
       uint32_t lg, m;
       item_split_host((uint32_t)p.codes.size(), (uint32_t)L, lg, m);
-      const uint32_t img = (uint32_t)(c * c * p.prefix + c * p.k);
-      W.push_back((int32_t)(img | ((uint32_t)p.deg << 12) | ((uint32_t)p.codes.size() << 19) | (lg << 25)));
-      for (uint32_t cd : p.codes) W.push_back((int32_t)cd);
+      const uint32_t img_b = 8u * (uint32_t)(c * c * p.prefix + c * p.k), row_b = 8u * (uint32_t)(c * p.deg);
+      W.push_back((int32_t)(img_b | (row_b << 15) | (lg << 27) | ((p.diag ? 1u : 0u) << 29)));
+      // 2^lg partial sums of exactly L codes: partial j takes contributions [j m, j m + m), padded with the zero record
+      for (uint32_t j = 0; j < (1u << lg); ++j)
+        for (uint32_t x = 0; x < (uint32_t)L; ++x) {
+          const uint32_t kk = j * m + x;
+          W.push_back((x < m && kk < p.codes.size()) ? (int32_t)p.codes[kk] : 0);
+        }
     }
   }
   while (W.size() % 4) W.push_back(0);  // 16-byte granularity
   W[12] = (int32_t)W.size();
-  out.n_lines = n_lines; out.TS = TS; out.LU = LU; out.LUp = LUp; out.coord_nodes = (int)coord_nodes; out.ppp = ppp;
-  out.n_spans = (int)spans.size();
+  out.n_lines = n_lines; out.TS = TS; out.LU = LU; out.LUp = LUp; out.coord_nodes = (int)coord_slots; out.ppp = ppp;
+  out.n_spans = (int)spans.size(); out.Tmax = Tmax; out.rec_entries = (int)rec_entries;
 
   std::vector<int32_t>& R = out.raw;
   R = {P, (int32_t)delta, ppp, 0};
@@ -338,9 +369,9 @@ inline bool build_template(int N, int c, int P, int64_t delta, const std::vector
   return true;
 }
 
-// tiles of one run: balanced chunks of <= 32 lane-steps
-inline void split_run(const Run& r, std::vector<std::pair<int32_t, int32_t>>& out /* (first lane-step, T) */) {
-  const int n = (r.periods + kLaneSteps - 1) / kLaneSteps;
+// tiles of one run: balanced chunks of <= Tmax lane-steps (the template's choice)
+inline void split_run(const Run& r, int Tmax, std::vector<std::pair<int32_t, int32_t>>& out /* (first lane-step, T) */) {
+  const int n = (r.periods + Tmax - 1) / Tmax;
   const int base = r.periods / n, extra = r.periods % n;
   int32_t t0 = 0;
   for (int i = 0; i < n; ++i) {

@@ -164,23 +164,24 @@ static bool emulate_tile(const Emu& E, const int32_t* hdr, const std::vector<int
                          std::vector<double>& values) {
   const Mesh& m = E.m;
   const int N = m.N, SD = m.sd, C = E.c;
-  const int32_t v0 = hdr[0], T = hdr[1], toff = hdr[2], E0 = hdr[3], pair0 = hdr[4];
+  const int32_t v0 = hdr[0], T = hdr[1], toff = hdr[2], pair0 = hdr[4];
   const int32_t* s_t = blob.data() + toff;
   const int P = s_t[0], n_lines = s_t[1], TS = s_t[2], LUp = s_t[3], LU = s_t[4], n_spans = s_t[5];
   const int off_lines = s_t[6], off_spans = s_t[7];
-  const int32_t delta = s_t[14];
-  const uint32_t magic = (uint32_t)s_t[15];
   const int UD = (C % 2 == 0) ? 2 : 1;  // doubles per unit
-  const int64_t nn = m.n_nodes(), n_el = m.n_el();
+  const int64_t nn = m.n_nodes();
+  if (T > s_t[15] || T < 1) { printf("tile longer than Tmax\n"); return false; }
   std::vector<double> s_xyz((size_t)s_t[13] * SD, NAN);
-  std::vector<double> rec((size_t)n_lines * N * TS * SD, NAN);  // [entry][SD]
+  std::vector<double> rec((size_t)s_t[17] * SD, NAN);  // [entry][SD]
+  for (int i = 0; i < kZeroEntries * SD; ++i) rec[i] = 0.0;
   std::vector<double> img((size_t)kLaneSteps * LUp * UD, NAN);
   // staging
   for (int s = 0; s < n_spans; ++s) {
-    const int len = P * (T - 1) + s_t[off_spans + 3 * s + 1] + 1;
+    const int32_t* sp = s_t + off_spans + 4 * s;
+    const int len = P * (T - 1) + sp[1] + 1;
     for (int i = 0; i < len; ++i) {
-      const int64_t node = (int64_t)v0 + s_t[off_spans + 3 * s] + i;
-      const int d = s_t[off_spans + 3 * s + 2] + i;
+      const int64_t node = (int64_t)v0 + sp[0] + i;
+      const int d = sp[2] + (i % P) * sp[3] + i / P;
       if (d >= s_t[13]) { printf("span overflow\n"); return false; }
       if (node >= 0 && node < nn)
         for (int x = 0; x < SD; ++x) s_xyz[(size_t)d * SD + x] = m.xyz[node * SD + x];
@@ -193,65 +194,68 @@ static bool emulate_tile(const Emu& E, const int32_t* hdr, const std::vector<int
     if (l != i / TS) { printf("inv_ts division wrong\n"); return false; }
     const int32_t* ld = s_t + off_lines + l * (2 + N);
     if (tp >= T + ld[1]) continue;
-    const int64_t e = (int64_t)E0 + ld[0] + (int64_t)tp * delta;
     // geometry from the TEMPLATE's corner table (not from the connectivity), like the kernel
-    double X[4][3];
-    for (int n = 0; n < N; ++n) {
-      const int ci = ld[2 + n] + P * tp;
-      if (ci < 0 || ci >= s_t[13]) { printf("coordinate index out of the table\n"); return false; }
-      for (int x = 0; x < SD; ++x) X[n][x] = s_xyz[(size_t)ci * SD + x];
-    }
-    // if the element exists, the template's corners must be the element's (else nobody may reference it)
     Mesh tmp{N, SD, {}, {}};
-    for (int n = 0; n < N; ++n) { tmp.en.push_back(n); for (int x = 0; x < SD; ++x) tmp.xyz.push_back(X[n][x]); }
+    for (int n = 0; n < N; ++n) {
+      const int ci = ld[2 + n] + tp;
+      if (ci < 0 || ci >= s_t[13]) { printf("coordinate index out of the table\n"); return false; }
+      tmp.en.push_back(n);
+      for (int x = 0; x < SD; ++x) tmp.xyz.push_back(s_xyz[(size_t)ci * SD + x]);
+    }
     double g[12];
     element_grads(tmp, 0, g);
-    (void)e; (void)n_el;
-    for (int n = 0; n < N; ++n)
-      for (int x = 0; x < SD; ++x) rec[((size_t)(l * N + n) * TS + tp) * SD + x] = g[n * SD + x];
+    for (int n = 0; n < N; ++n) {
+      const size_t ent = (size_t)kZeroEntries + (size_t)(l * N + n) * TS + tp;
+      if ((int)ent >= s_t[17]) { printf("record entry out of range\n"); return false; }
+      for (int x = 0; x < SD; ++x) rec[ent * SD + x] = g[n * SD + x];
+    }
   }
   // phase 2
   const int L = (N == 3) ? 2 : 6;
-  for (int warp = 0; warp < kWarps; ++warp) {
-    const int32_t* prog = s_t + s_t[8 + warp];
+  for (int warp = 0; warp < s_t[8]; ++warp) {
+    const int32_t* prog = s_t + s_t[20 + warp];
     const int np = prog[0];
     for (int lane = 0; lane < T; ++lane) {
       int w = 1;
       for (int pi = 0; pi < np; ++pi) {
         const uint32_t head = (uint32_t)prog[w];
-        const uint32_t im = head & 0xfffu, deg = (head >> 12) & 127u, cnt = (head >> 19) & 63u, lg = (head >> 25) & 7u;
-        const uint32_t mm = (cnt + (1u << lg) - 1u) >> lg;
-        if (mm > (uint32_t)L) { printf("partial longer than L\n"); return false; }
+        const uint32_t im = (head & 0x7fffu) / 8u, row = ((head >> 15) & 0xfffu) / 8u, lg = (head >> 27) & 3u, diag = (head >> 29) & 1u;
         double S[3][3] = {{0}};
-        for (uint32_t kk = 0; kk < cnt; ++kk) {
-          const uint32_t code = (uint32_t)prog[w + 1 + (int)kk], ea = code & 0xffffu, eb = code >> 16;
-          if ((int)(ea % TS) + lane >= TS || (int)(eb % TS) + lane >= TS) { printf("entry leaves its plane\n"); return false; }
+        for (uint32_t kk = 0; kk < ((uint32_t)L << lg); ++kk) {
+          const uint32_t code = (uint32_t)prog[w + 1 + (int)kk], ea = (code & 0xffffu) / 16u, eb = (code >> 16) / 16u;
+          if ((code & 0xf000fu) != 0) { printf("code offsets not multiples of 16\n"); return false; }
+          if (diag && ea != eb) { printf("diag pair with a != b\n"); return false; }
+          if ((int)(ea + lane) >= s_t[17] || (int)(eb + lane) >= s_t[17]) { printf("entry out of range\n"); return false; }
           const double* A = &rec[(size_t)(ea + lane) * SD];
           const double* B = &rec[(size_t)(eb + lane) * SD];
           for (int i = 0; i < SD; ++i)
-            for (int j = 0; j < SD; ++j) S[i][j] += A[i] * B[j];
+            for (int j = 0; j < SD; ++j) S[i][j] += A[i] * B[j];   // a NaN here = an entry nobody computed
         }
-        w += 1 + (int)cnt;
-        double* row = &img[(size_t)lane * LUp * UD];
+        w += 1 + (L << lg);
+        double* rowp = &img[(size_t)lane * LUp * UD];
         if (C == 1) {
           double t = 0;
           for (int s = 0; s < SD; ++s) t += S[s][s];
-          row[im] = t;
+          rowp[im] = t;
         } else {
           double tr = 0;
           for (int i = 0; i < SD; ++i) tr += S[i][i];
           for (int i = 0; i < C; ++i)
-            for (int j = 0; j < C; ++j) row[im + (uint32_t)(i * C) * deg + j] = lam_over_mu * S[i][j] + S[j][i] + (i == j ? tr : 0.0);
+            for (int j = 0; j < C; ++j) rowp[im + (uint32_t)i * row + j] = lam_over_mu * S[i][j] + S[j][i] + (i == j ? tr : 0.0);
         }
       }
     }
   }
-  // store
-  const int total = T * LU;
-  for (int x = 0; x < total; ++x) {
-    const uint32_t r = (uint32_t)(((uint64_t)(uint32_t)x * magic) >> 32), u = (uint32_t)x - r * (uint32_t)LU;
-    if ((int)r != x / LU) { printf("magic division wrong\n"); return false; }
-    for (int d = 0; d < UD; ++d) values[(size_t)C * C * pair0 + (size_t)x * UD + d] = img[((size_t)r * LUp + u) * UD + d];
+  // store: row r of the image -> values[c^2 pair0 + r * row_doubles ...]
+  const int kThreads = 32 * s_t[8];
+  for (int tid = 0; tid < kThreads; ++tid) {  // the kernel's flat copy: thread tid takes units tid, tid + threads, ...
+    int r = tid / LU, u = tid % LU;
+    for (int x = tid; x < T * LU; x += kThreads) {
+      if (r != x / LU || u != x % LU) { printf("store increments wrong\n"); return false; }
+      for (int d = 0; d < UD; ++d) values[(size_t)C * C * pair0 + (size_t)x * UD + d] = img[((size_t)r * LUp + u) * UD + d];
+      r += s_t[10]; u += s_t[11];
+      if (u >= LU) { u -= LU; ++r; }
+    }
   }
   return true;
 }
@@ -287,7 +291,7 @@ static bool host_verify(const Emu& E, const int32_t* h, const std::vector<int32_
 }
 
 // returns the covered fraction (< 0 on failure)
-static double run_case(const char* name, const Mesh& m, int c, double min_cover) {
+static double run_case(const char* name, const Mesh& m, int c, double min_cover, int n_warps = 4) {
   Emu E(m, c);
   const int64_t nn = m.n_nodes();
   const int N = m.N;
@@ -315,16 +319,16 @@ static double run_case(const char* name, const Mesh& m, int c, double min_cover)
       }
     }
     Template t;  // the emulator builds one template per run (the library shares them by key)
-    if (!build_template(N, c, r.P, r.delta, ph, L, t)) { ++n_fail; continue; }
+    if (!build_template(N, c, r.P, r.delta, ph, L, n_warps, t)) { ++n_fail; continue; }
     ++n_tmpl;
     if (getenv("RUNS_EMU_VERBOSE"))
-      printf("  run v0=%d P=%d periods=%d delta=%lld: lines=%d TS=%d LU=%d LUp=%d coord nodes=%d spans=%d words=%zu\n", r.v0, r.P,
-             r.periods, (long long)r.delta, t.n_lines, t.TS, t.LU, t.LUp, t.coord_nodes, t.n_spans, t.words.size());
+      printf("  run v0=%d P=%d periods=%d delta=%lld: lines=%d Tmax=%d TS=%d LU=%d LUp=%d coord nodes=%d spans=%d words=%zu\n", r.v0, r.P,
+             r.periods, (long long)r.delta, t.n_lines, t.Tmax, t.TS, t.LU, t.LUp, t.coord_nodes, t.n_spans, t.words.size());
     const int32_t woff = (int32_t)blob.size(), roff = (int32_t)rawblob.size();
     blob.insert(blob.end(), t.words.begin(), t.words.end());
     rawblob.insert(rawblob.end(), t.raw.begin(), t.raw.end());
     std::vector<std::pair<int32_t, int32_t>> parts;
-    split_run(r, parts);
+    split_run(r, t.Tmax, parts);
     for (auto& pt : parts) {
       const int32_t v0 = r.v0 + r.P * pt.first;
       const int32_t hdr[kTileInts] = {v0, pt.second, woff, eref[v0], E.node_ptr[v0], roff, 0, 0};
@@ -376,6 +380,8 @@ int main() {
   ok &= run_case("box 7x6x45 elastic", box_mesh(7, 6, 45, 0.15, 5), 3, 0.8) >= 0;
   ok &= run_case("box 5x5x21 laplace", box_mesh(5, 5, 21, 0.15, 6), 1, 0.8) >= 0;
   ok &= run_case("box 6x5x80 elastic", box_mesh(6, 5, 80, 0.1, 7), 3, 0.9) >= 0;
+  ok &= run_case("box 6x5x80 elastic, 8 warps", box_mesh(6, 5, 80, 0.1, 7), 3, 0.9, 8) >= 0;
+  ok &= run_case("rect 140x12 elastic, 8 warps", rect_mesh(140, 12, 0.15, 3), 2, 0.9, 8) >= 0;
   printf(ok ? "RUNS_EMULATOR PASS\n" : "RUNS_EMULATOR FAIL\n");
   return ok ? 0 : 1;
 }
