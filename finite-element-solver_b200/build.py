@@ -51,7 +51,8 @@ def build(force=False, verbose=False):
         logs = list(ex.map(run, jobs))
     objs = [os.path.join(objdir, s.replace('.cu', '.o')) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        run([nvcc, '-shared', '-o', LIB] + objs)
+        # the shared CUDA runtime (the process already holds torch's): the library carries no copy of cudart
+        run([nvcc, '-shared', '-cudart', 'shared', '-Xlinker', '-rpath=/usr/local/cuda/lib64', '-o', LIB] + objs)
     if verbose:
         print('\n'.join(logs))
     return LIB

@@ -37,7 +37,7 @@ struct RunSmem {
   __host__ __device__ static size_t xyz_bytes(int nodes) { return up16((size_t)nodes * SD * 8); }
   __host__ __device__ static size_t v2_bytes(int entries) { return up16((size_t)entries * 16); }
   __host__ __device__ static size_t v1_bytes(int entries) { return (SD & 1) ? up16((size_t)entries * 8) : 0; }
-  __host__ __device__ static size_t img_bytes(int units) { return up16((size_t)units * UB); }
+  __host__ __device__ static size_t img_bytes(int units) { return up16((size_t)units * UB + 16); }
   __host__ __device__ static size_t total(const RunDims& d) {
     return xyz_bytes(d.coord_nodes) + v2_bytes(d.rec_entries) + v1_bytes(d.rec_entries) + img_bytes(d.img_units);
   }
@@ -137,10 +137,23 @@ __device__ __forceinline__ void run_pair_sum(const int32_t* __restrict__ tmw, in
   }
 }
 
+// resident CTAs per SM the register allocation aims at: shared memory allows 2 (tets) / 7 (triangles)
+#ifndef FES_RUN_KB2D
+#define FES_RUN_KB2D 1  // records per thread in flight in phase 1, triangles
+#endif
+#ifndef FES_RUN_KB3D
+#define FES_RUN_KB3D 2  // ... tets
+#endif
+#ifndef FES_RUN_MINCTA2D
+#define FES_RUN_MINCTA2D 7
+#endif
+template <int SD, int kRunThreads>
+constexpr int run_min_ctas() { return SD == 3 ? 2 : (kRunThreads >= 256 ? 3 : FES_RUN_MINCTA2D); }
+
 template <int ELEM, int FORM, int C, int SD, int kRunThreads>
-__global__ void __launch_bounds__(kRunThreads)
-k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const double* __restrict__ coords, int64_t n_nodes, int64_t n_el, Coeffs cf, RunDims dims,
-                double* __restrict__ values) {
+__global__ void __launch_bounds__(kRunThreads, run_min_ctas<SD, kRunThreads>())
+k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const double* __restrict__ coords,
+                int64_t n_nodes, int64_t n_el, Coeffs cf, RunDims dims, int use_bulk, double* __restrict__ values) {
   using RS = RunSmem<C, SD>;
   constexpr int N = ET<ELEM>::N, RD = ET<ELEM>::RD;
   static_assert(ET<ELEM>::NQ == 1 && RD == SD, "run tiles: P1 volume elements");
@@ -172,9 +185,18 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
   }
   const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   if (n_my <= 0) return;
+  // tile headers {v0, T, template offset, E0 | first pair ...}, fetched two tiles ahead so neither the staging of the
+  // next tile nor this tile's phases ever wait for one
   const int4* hdr4 = reinterpret_cast<const int4*>(tiles);
-  int4 h0 = __ldg(hdr4 + 2 * (int64_t)blockIdx.x);
-  int32_t pair0 = __ldg(tiles + 8 * (int64_t)blockIdx.x + 4);
+  auto load_hdr = [&](int k, int4& h, int32_t& p0) {
+    const int64_t t = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+    h = __ldg(hdr4 + 2 * t);
+    p0 = __ldg(tiles + 8 * t + 4);
+  };
+  int4 h0, h1 = make_int4(0, 0, 0, 0);
+  int32_t pair0, pair1 = 0;
+  load_hdr(0, h0, pair0);
+  if (n_my > 1) load_hdr(1, h1, pair1);
 
   // staging of one tile's coordinate spans: warp w takes spans w, w + 4, ...
   auto stage = [&](int32_t v0, int32_t T, int32_t toff) {
@@ -202,71 +224,136 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
     const int32_t T = h0.y, toff = h0.z, E0 = h0.w;
     const int32_t my_pair0 = pair0;
     const bool has_next = k + 1 < n_my;
-    if (has_next) {  // the next header flies under phase 1
-      const int64_t nx = (int64_t)blockIdx.x + (int64_t)(k + 1) * gridDim.x;
-      h0 = __ldg(hdr4 + 2 * nx);
-      pair0 = __ldg(tiles + 8 * nx + 4);
-    }
+    int4 h2 = make_int4(0, 0, 0, 0);
+    int32_t pair2 = 0;
+    if (k + 2 < n_my) load_hdr(k + 2, h2, pair2);
     const int P = tm.w[toff], n_lines = tm.w[toff + 1], TS = tm.w[toff + 2], LUp = tm.w[toff + 3], LU = tm.w[toff + 4];
     (void)P;
+    // 8-byte units and an odd row length: the image needs no padding (LUp == LU), i.e. it IS the tile's contiguous
+    // slice of `values` and one TMA bulk store writes it.  An odd first value index is mirrored by an 8-byte skew of
+    // the image, so both sides of the copy share their 16-byte phase.
+    const bool bulk = UB == 8 && LUp == LU && use_bulk;
+    const uint32_t skew = bulk ? (uint32_t)(((int64_t)C * C * my_pair0) & 1) : 0u;
 
-    // ---- phase 1: one geometry record per (line, entry)
+    // ---- phase 1: one geometry record per (line, entry); two records per thread in flight (their shared-memory
+    // loads and the long fp64 rsqrt chains overlap)
     {
       const int n_items = n_lines * TS;
       const uint32_t inv_ts = ((1u << 20) + (uint32_t)TS - 1u) / (uint32_t)TS;
       const int lo = toff + tm.w[toff + 6];
       const int32_t delta = tm.w[toff + 14];
-      for (int i = tid; i < n_items; i += kRunThreads) {
-        const int l = (int)(((uint32_t)i * inv_ts) >> 20), tp = i - l * TS;
-        const int ld = lo + l * (2 + N);
-        if (tp >= T + tm.w[ld + 1]) continue;
-        double X[RD + 1][SD];
+      constexpr int kB = (SD == 3) ? FES_RUN_KB3D : FES_RUN_KB2D;
+      if constexpr (kB == 1) {
+        for (int i = tid; i < n_items; i += kRunThreads) {
+          const int l = (int)(((uint32_t)i * inv_ts) >> 20), tp = i - l * TS;
+          const int ld = lo + l * (2 + N);
+          if (tp >= T + tm.w[ld + 1]) continue;
+          double X[RD + 1][SD];
 #pragma unroll
-        for (int n = 0; n <= RD; ++n) {
-          const int ci = tm.w[ld + 2 + n] + tp;
-          if constexpr (SD == 2) {
-            const double2 xy = reinterpret_cast<const double2*>(s_xyz)[ci];
-            X[n][0] = xy.x; X[n][1] = xy.y;
-          } else {
+          for (int n = 0; n <= RD; ++n) {
+            const int ci = tm.w[ld + 2 + n] + tp;
+            if constexpr (SD == 2) {
+              const double2 xy = reinterpret_cast<const double2*>(s_xyz)[ci];
+              X[n][0] = xy.x; X[n][1] = xy.y;
+            } else {
 #pragma unroll
-            for (int s = 0; s < SD; ++s) X[n][s] = s_xyz[ci * SD + s];
+              for (int s = 0; s < SD; ++s) X[n][s] = s_xyz[ci * SD + s];
+            }
+          }
+          double cof[RD][SD], det;
+          make_cof<RD, SD>(X, cof, det);
+          double f = sq_uniform;
+          if (per_elem) {
+            int64_t e = (int64_t)E0 + tm.w[ld] + (int64_t)tp * delta;
+            e = e < 0 ? 0 : (e >= n_el ? n_el - 1 : e);  // entries no lane references may fall outside the mesh
+            Material m; double w;
+            element_coeffs(cf, e, m, w);
+            double c2 = w * (ref_measure(RD) / 1.0);
+            if constexpr (FORM == FES_FORM_ELASTIC) c2 *= m.mu;
+            f = c2 > 0.0 ? c2 * rsqrt(c2) : 0.0;
+          }
+          f = copysign(f * rsqrt(fabs(det)), det);
+#pragma unroll
+          for (int i2 = 0; i2 < RD; ++i2)
+#pragma unroll
+            for (int s = 0; s < SD; ++s) cof[i2][s] *= f;
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            double gn[SD];
+            shape_grad_rows<ELEM, SD>(cof, 0, n, gn);
+            const int ent = kZero + (l * N + n) * TS + tp;
+            v2[ent] = make_double2(gn[0], gn[1]);
+            if constexpr (SD & 1) v1[ent] = gn[SD - 1];
           }
         }
-        double cof[RD][SD], det;
-        make_cof<RD, SD>(X, cof, det);
-        double f = sq_uniform;
-        if (per_elem) {
-          int64_t e = (int64_t)E0 + tm.w[ld] + (int64_t)tp * delta;
-          e = e < 0 ? 0 : (e >= n_el ? n_el - 1 : e);  // entries no lane references may fall outside the mesh
-          Material m; double w;
-          element_coeffs(cf, e, m, w);
-          double c2 = w * (ref_measure(RD) / 1.0);
-          if constexpr (FORM == FES_FORM_ELASTIC) c2 *= m.mu;
-          f = c2 > 0.0 ? c2 * rsqrt(c2) : 0.0;
+      } else
+      for (int i0 = tid; i0 < n_items; i0 += kB * kRunThreads) {
+        double X[kB][RD + 1][SD];
+        int ent0[kB], eo[kB];
+        bool live[kB];
+#pragma unroll
+        for (int r = 0; r < kB; ++r) {
+          const int i = i0 + r * kRunThreads;
+          const int l = (int)(((uint32_t)i * inv_ts) >> 20), tp = i - l * TS;
+          const int ld = lo + l * (2 + N);
+          live[r] = i < n_items && tp < T + tm.w[ld + 1];
+          ent0[r] = kZero + l * N * TS + tp;
+          eo[r] = 0;
+          if (live[r]) {
+            if (per_elem) eo[r] = tm.w[ld] + tp * delta;
+#pragma unroll
+            for (int n = 0; n <= RD; ++n) {
+              const int ci = tm.w[ld + 2 + n] + tp;
+              if constexpr (SD == 2) {
+                const double2 xy = reinterpret_cast<const double2*>(s_xyz)[ci];
+                X[r][n][0] = xy.x; X[r][n][1] = xy.y;
+              } else {
+#pragma unroll
+                for (int s = 0; s < SD; ++s) X[r][n][s] = s_xyz[ci * SD + s];
+              }
+            }
+          }
         }
-        f = copysign(f * rsqrt(fabs(det)), det);
 #pragma unroll
-        for (int i2 = 0; i2 < RD; ++i2)
+        for (int r = 0; r < kB; ++r) {
+          if (!live[r]) continue;
+          double cof[RD][SD], det;
+          make_cof<RD, SD>(X[r], cof, det);
+          double f = sq_uniform;
+          if (per_elem) {
+            int64_t e = (int64_t)E0 + eo[r];
+            e = e < 0 ? 0 : (e >= n_el ? n_el - 1 : e);  // entries no lane references may fall outside the mesh
+            Material m; double w;
+            element_coeffs(cf, e, m, w);
+            double c2 = w * (ref_measure(RD) / 1.0);
+            if constexpr (FORM == FES_FORM_ELASTIC) c2 *= m.mu;
+            f = c2 > 0.0 ? c2 * rsqrt(c2) : 0.0;
+          }
+          f = copysign(f * rsqrt(fabs(det)), det);
 #pragma unroll
-          for (int s = 0; s < SD; ++s) cof[i2][s] *= f;
+          for (int i2 = 0; i2 < RD; ++i2)
 #pragma unroll
-        for (int n = 0; n < N; ++n) {
-          double gn[SD];
-          shape_grad_rows<ELEM, SD>(cof, 0, n, gn);
-          const int ent = kZero + (l * N + n) * TS + tp;
-          v2[ent] = make_double2(gn[0], gn[1]);
-          if constexpr (SD & 1) v1[ent] = gn[SD - 1];
+            for (int s = 0; s < SD; ++s) cof[i2][s] *= f;
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            double gn[SD];
+            shape_grad_rows<ELEM, SD>(cof, 0, n, gn);
+            const int ent = ent0[r] + n * TS;
+            v2[ent] = make_double2(gn[0], gn[1]);
+            if constexpr (SD & 1) v1[ent] = gn[SD - 1];
+          }
         }
       }
     }
+    if (tid == 0) bulk_wait_read_all();  // the previous tile's bulk store has finished reading the image
     __syncthreads();  // records visible; the coordinate table is free; the previous image has been copied out
 
-    if (has_next) stage(h0.x, h0.y, h0.z);  // lands under phase 2
+    if (has_next) stage(h1.x, h1.y, h1.z);  // lands under phase 2
 
     // ---- phase 2: warp = pair group, lane = lane-step
     if (lane < T) {
       const uint32_t lane2 = v2_b + 16u * (uint32_t)lane, lane1 = v1_b + 8u * (uint32_t)lane;
-      const uint32_t img_lane = img_b + (uint32_t)lane * (uint32_t)LUp * (uint32_t)UB;
+      const uint32_t img_lane = img_b + 8u * skew + (uint32_t)lane * (uint32_t)LUp * (uint32_t)UB;
       const int pb = toff + tm.w[toff + 20 + warp];
       const int np = tm.w[pb];
       int w = pb + 1;
@@ -305,10 +392,21 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
       }
     }
     cp_async_wait_all();
+    if (bulk) fence_proxy_async_smem();  // the image writes (generic proxy) ordered before the bulk store's reads
     __syncthreads();  // image complete; records free; the next tile's coordinates visible
 
-    // ---- store: image rows -> the tile's contiguous slice of `values`; thread x takes units x, x + 128, ...
-    {
+    // ---- store: image rows -> the tile's contiguous slice of `values`
+    if (bulk) {
+      if (tid == 0) {
+        const int64_t val0 = (int64_t)C * C * my_pair0;
+        const int n_out = T * LU, head = (int)skew;
+        const int body = (n_out - head) & ~1, tail = n_out - head - body;
+        const double* img = reinterpret_cast<const double*>(s_img) + skew;
+        if (body > 0) bulk_s2g(values + val0 + head, img + head, (uint32_t)body * 8u);
+        if (head) values[val0] = img[0];
+        if (tail) values[val0 + n_out - 1] = img[n_out - 1];
+      }
+    } else {  // padded rows: thread x takes units x, x + threads, ...
       unsigned char* dst = reinterpret_cast<unsigned char*>(values + (int64_t)C * C * my_pair0);
       const int total = T * LU, dr = tm.w[toff + 10], du = tm.w[toff + 11];
       int r = tid / LU, u = tid - r * LU;
@@ -325,7 +423,10 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
         if (u >= LU) { u -= LU; ++r; }
       }
     }
+    h0 = h1; pair0 = pair1;
+    h1 = h2; pair1 = pair2;
   }
+  if (tid == 0) bulk_wait_read_all();  // shared memory must outlive the last bulk store's reads
 }
 
 template <int ELEM, int FORM, int C, int SD, int kRunThreads>
@@ -353,9 +454,10 @@ int launch_runs_t(const Job& j, cudaStream_t stream) {
   Coeffs cf = j.cf;
   if (cf.factor < 0.0) { cf.factor = -cf.factor; cf.sign = -1.0; }
   const int64_t grid = std::min<int64_t>(R.n_tiles, (int64_t)sms * per_sm);
+  static const bool no_bulk = getenv("FES_NO_TMA_STORE") != nullptr;  // tuning knob: the copy loop for every image
   k_assemble_runs<ELEM, FORM, C, SD, kRunThreads><<<(unsigned)grid, kRunThreads, smem, stream>>>(
       (const int32_t*)R.tiles.p, (int)R.n_tiles, R.slot, (const double*)j.coords, (int64_t)j.plan->n_nodes,
-      (int64_t)j.plan->n_el, cf, dims, j.out);
+      (int64_t)j.plan->n_el, cf, dims, no_bulk ? 0 : 1, j.out);
   FES_LAUNCH_CHECK();
   return FES_OK;
 }

@@ -166,8 +166,12 @@ int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32
     n_cov += e - b;
   }
   const int64_t nt = (int64_t)tiles.size() / kTileInts;
-  static const double min_cover = getenv("FES_RUNS_MIN_COVER") ? atof(getenv("FES_RUNS_MIN_COVER")) : 0.25;  // tuning knob
-  if (nt == 0 || (double)n_cov < min_cover * (double)nn) return FES_OK;
+  // Worth two kernels (run tiles + remainder tiles on a side stream) only when the runs cover a good part of a mesh
+  // that is large enough: below ~10^5 nodes an assembly is launch-latency bound and one kernel wins (config 1:
+  // 15 us tiled, 22 us split).  Both thresholds are knobs, read per plan (the tests force small meshes through).
+  const double min_cover = getenv("FES_RUNS_MIN_COVER") ? atof(getenv("FES_RUNS_MIN_COVER")) : 0.25;
+  const long long min_nodes = getenv("FES_RUNS_MIN_NODES") ? atoll(getenv("FES_RUNS_MIN_NODES")) : 100000;
+  if (nt == 0 || (double)n_cov < min_cover * (double)nn || n_cov < min_nodes) return FES_OK;
 
   FES_CUDA(Rn.tiles.alloc(tiles.size()));
   DevBuf<int32_t> d_raw;
