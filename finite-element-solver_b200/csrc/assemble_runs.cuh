@@ -13,7 +13,8 @@
 //             padded with the zero entries).  The partial sums of L contributions are combined in the balanced
 //             tree the tiled kernel's xor shuffles form, so a pair gets the same bits from either kernel.  The
 //             block goes into a padded shared-memory image (odd row stride: the lanes' stores hit distinct banks)
-//   store   : coalesced copy of the image rows to the tile's contiguous slice of `values`
+//   store   : TMA bulk stores (cp.async.bulk.global.shared::cta): one per tile when the image needs no padding,
+//             one per image row otherwise; they drain under the next tile's phase 1
 // Two barriers per tile.  Nothing but the 32-byte tile header, the coordinates and the per-element coefficients
 // comes from HBM.
 
@@ -148,7 +149,7 @@ __device__ __forceinline__ void run_pair_sum(const int32_t* __restrict__ tmw, in
 #define FES_RUN_MINCTA2D 7
 #endif
 template <int SD, int kRunThreads>
-constexpr int run_min_ctas() { return SD == 3 ? 2 : (kRunThreads >= 256 ? 3 : FES_RUN_MINCTA2D); }
+constexpr int run_min_ctas() { return SD == 3 ? 2 : (kRunThreads >= 256 ? 3 : (kRunThreads >= 192 ? 4 : FES_RUN_MINCTA2D)); }
 
 template <int ELEM, int FORM, int C, int SD, int kRunThreads>
 __global__ void __launch_bounds__(kRunThreads, run_min_ctas<SD, kRunThreads>())
@@ -190,8 +191,11 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
   const int4* hdr4 = reinterpret_cast<const int4*>(tiles);
   auto load_hdr = [&](int k, int4& h, int32_t& p0) {
     const int64_t t = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
-    h = __ldg(hdr4 + 2 * t);
-    p0 = __ldg(tiles + 8 * t + 4);
+    // volatile asm: the loads stay where they are written (two tiles ahead) and their results in vector registers
+    // (the compiler otherwise proves them warp-uniform and converts them to uniform registers right behind the
+    // load, a long-scoreboard stall per tile)
+    asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "l"(hdr4 + 2 * t));
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(p0) : "l"(tiles + 8 * t + 4));
   };
   int4 h0, h1 = make_int4(0, 0, 0, 0);
   int32_t pair0, pair1 = 0;
@@ -227,83 +231,34 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
     int4 h2 = make_int4(0, 0, 0, 0);
     int32_t pair2 = 0;
     if (k + 2 < n_my) load_hdr(k + 2, h2, pair2);
-    const int P = tm.w[toff], n_lines = tm.w[toff + 1], TS = tm.w[toff + 2], LUp = tm.w[toff + 3], LU = tm.w[toff + 4];
-    (void)P;
+    const int n_lines = tm.w[toff + 1], LUp = tm.w[toff + 3], LU = tm.w[toff + 4];
     // 8-byte units and an odd row length: the image needs no padding (LUp == LU), i.e. it IS the tile's contiguous
     // slice of `values` and one TMA bulk store writes it.  An odd first value index is mirrored by an 8-byte skew of
     // the image, so both sides of the copy share their 16-byte phase.
     const bool bulk = UB == 8 && LUp == LU && use_bulk;
+    const bool row_bulk = UB == 16 && (use_bulk & 2);
     const uint32_t skew = bulk ? (uint32_t)(((int64_t)C * C * my_pair0) & 1) : 0u;
 
-    // ---- phase 1: one geometry record per (line, entry); two records per thread in flight (their shared-memory
-    // loads and the long fp64 rsqrt chains overlap)
+    // ---- phase 1: one geometry record per (line, entry).  A warp takes whole lines (lane = entry; a line has at
+    // most 32 entries), kB of them at a time: the line descriptors are warp-uniform constant loads, the coordinate
+    // reads and record writes unit-stride, and the long fp64 rsqrt chains of the kB records overlap
     {
-      const int n_items = n_lines * TS;
-      const uint32_t inv_ts = ((1u << 20) + (uint32_t)TS - 1u) / (uint32_t)TS;
       const int lo = toff + tm.w[toff + 6];
       const int32_t delta = tm.w[toff + 14];
       constexpr int kB = (SD == 3) ? FES_RUN_KB3D : FES_RUN_KB2D;
-      if constexpr (kB == 1) {
-        for (int i = tid; i < n_items; i += kRunThreads) {
-          const int l = (int)(((uint32_t)i * inv_ts) >> 20), tp = i - l * TS;
-          const int ld = lo + l * (2 + N);
-          if (tp >= T + tm.w[ld + 1]) continue;
-          double X[RD + 1][SD];
-#pragma unroll
-          for (int n = 0; n <= RD; ++n) {
-            const int ci = tm.w[ld + 2 + n] + tp;
-            if constexpr (SD == 2) {
-              const double2 xy = reinterpret_cast<const double2*>(s_xyz)[ci];
-              X[n][0] = xy.x; X[n][1] = xy.y;
-            } else {
-#pragma unroll
-              for (int s = 0; s < SD; ++s) X[n][s] = s_xyz[ci * SD + s];
-            }
-          }
-          double cof[RD][SD], det;
-          make_cof<RD, SD>(X, cof, det);
-          double f = sq_uniform;
-          if (per_elem) {
-            int64_t e = (int64_t)E0 + tm.w[ld] + (int64_t)tp * delta;
-            e = e < 0 ? 0 : (e >= n_el ? n_el - 1 : e);  // entries no lane references may fall outside the mesh
-            Material m; double w;
-            element_coeffs(cf, e, m, w);
-            double c2 = w * (ref_measure(RD) / 1.0);
-            if constexpr (FORM == FES_FORM_ELASTIC) c2 *= m.mu;
-            f = c2 > 0.0 ? c2 * rsqrt(c2) : 0.0;
-          }
-          f = copysign(f * rsqrt(fabs(det)), det);
-#pragma unroll
-          for (int i2 = 0; i2 < RD; ++i2)
-#pragma unroll
-            for (int s = 0; s < SD; ++s) cof[i2][s] *= f;
-#pragma unroll
-          for (int n = 0; n < N; ++n) {
-            double gn[SD];
-            shape_grad_rows<ELEM, SD>(cof, 0, n, gn);
-            const int ent = kZero + (l * N + n) * TS + tp;
-            v2[ent] = make_double2(gn[0], gn[1]);
-            if constexpr (SD & 1) v1[ent] = gn[SD - 1];
-          }
-        }
-      } else
-      for (int i0 = tid; i0 < n_items; i0 += kB * kRunThreads) {
+      constexpr int kWarps = kRunThreads / 32;
+      for (int l0 = warp; l0 < n_lines; l0 += kB * kWarps) {
         double X[kB][RD + 1][SD];
-        int ent0[kB], eo[kB];
         bool live[kB];
 #pragma unroll
         for (int r = 0; r < kB; ++r) {
-          const int i = i0 + r * kRunThreads;
-          const int l = (int)(((uint32_t)i * inv_ts) >> 20), tp = i - l * TS;
+          const int l = l0 + r * kWarps;
           const int ld = lo + l * (2 + N);
-          live[r] = i < n_items && tp < T + tm.w[ld + 1];
-          ent0[r] = kZero + l * N * TS + tp;
-          eo[r] = 0;
+          live[r] = l < n_lines && lane < T + tm.w[ld + 1];
           if (live[r]) {
-            if (per_elem) eo[r] = tm.w[ld] + tp * delta;
 #pragma unroll
             for (int n = 0; n <= RD; ++n) {
-              const int ci = tm.w[ld + 2 + n] + tp;
+              const int ci = tm.w[ld + 2 + n] + lane;
               if constexpr (SD == 2) {
                 const double2 xy = reinterpret_cast<const double2*>(s_xyz)[ci];
                 X[r][n][0] = xy.x; X[r][n][1] = xy.y;
@@ -317,11 +272,12 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
 #pragma unroll
         for (int r = 0; r < kB; ++r) {
           if (!live[r]) continue;
+          const int l = l0 + r * kWarps;
           double cof[RD][SD], det;
           make_cof<RD, SD>(X[r], cof, det);
           double f = sq_uniform;
           if (per_elem) {
-            int64_t e = (int64_t)E0 + eo[r];
+            int64_t e = (int64_t)E0 + tm.w[lo + l * (2 + N)] + (int64_t)lane * delta;
             e = e < 0 ? 0 : (e >= n_el ? n_el - 1 : e);  // entries no lane references may fall outside the mesh
             Material m; double w;
             element_coeffs(cf, e, m, w);
@@ -338,14 +294,14 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
           for (int n = 0; n < N; ++n) {
             double gn[SD];
             shape_grad_rows<ELEM, SD>(cof, 0, n, gn);
-            const int ent = ent0[r] + n * TS;
+            const int ent = kZero + (l * N + n) * 32 + lane;
             v2[ent] = make_double2(gn[0], gn[1]);
             if constexpr (SD & 1) v1[ent] = gn[SD - 1];
           }
         }
       }
     }
-    if (tid == 0) bulk_wait_read_all();  // the previous tile's bulk store has finished reading the image
+    if (warp == 0) bulk_wait_read_all();  // the previous tile's bulk stores have finished reading the image
     __syncthreads();  // records visible; the coordinate table is free; the previous image has been copied out
 
     if (has_next) stage(h1.x, h1.y, h1.z);  // lands under phase 2
@@ -392,7 +348,7 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
       }
     }
     cp_async_wait_all();
-    if (bulk) fence_proxy_async_smem();  // the image writes (generic proxy) ordered before the bulk store's reads
+    if (bulk || row_bulk) fence_proxy_async_smem();  // the image writes (generic proxy) ordered before the bulk store's reads
     __syncthreads();  // image complete; records free; the next tile's coordinates visible
 
     // ---- store: image rows -> the tile's contiguous slice of `values`
@@ -406,6 +362,10 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
         if (head) values[val0] = img[0];
         if (tail) values[val0 + n_out - 1] = img[n_out - 1];
       }
+    } else if (row_bulk) {  // padded rows, 16-byte units: one bulk store per image row, issued by the lanes of warp 0
+      if (warp == 0 && lane < T)
+        bulk_s2g(reinterpret_cast<unsigned char*>(values + (int64_t)C * C * my_pair0) + (size_t)lane * LU * UB,
+                 s_img + (size_t)lane * LUp * UB, (uint32_t)(LU * UB));
     } else {  // padded rows: thread x takes units x, x + threads, ...
       unsigned char* dst = reinterpret_cast<unsigned char*>(values + (int64_t)C * C * my_pair0);
       const int total = T * LU, dr = tm.w[toff + 10], du = tm.w[toff + 11];
@@ -426,7 +386,7 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
     h0 = h1; pair0 = pair1;
     h1 = h2; pair1 = pair2;
   }
-  if (tid == 0) bulk_wait_read_all();  // shared memory must outlive the last bulk store's reads
+  if (warp == 0) bulk_wait_read_all();  // shared memory must outlive the last bulk store's reads
 }
 
 template <int ELEM, int FORM, int C, int SD, int kRunThreads>
@@ -455,9 +415,12 @@ int launch_runs_t(const Job& j, cudaStream_t stream) {
   if (cf.factor < 0.0) { cf.factor = -cf.factor; cf.sign = -1.0; }
   const int64_t grid = std::min<int64_t>(R.n_tiles, (int64_t)sms * per_sm);
   static const bool no_bulk = getenv("FES_NO_TMA_STORE") != nullptr;  // tuning knob: the copy loop for every image
+  // padded images (16-byte units) go out as one 448-byte-class bulk store per image row, issued by the lanes of one
+  // warp: no shared-memory reads or store instructions on the LSU (config 2: 0.1348 -> 0.1245 ms); knob: the copy loop
+  static const bool row_bulk = getenv("FES_RUN_NO_ROW_BULK") == nullptr;
   k_assemble_runs<ELEM, FORM, C, SD, kRunThreads><<<(unsigned)grid, kRunThreads, smem, stream>>>(
       (const int32_t*)R.tiles.p, (int)R.n_tiles, R.slot, (const double*)j.coords, (int64_t)j.plan->n_nodes,
-      (int64_t)j.plan->n_el, cf, dims, no_bulk ? 0 : 1, j.out);
+      (int64_t)j.plan->n_el, cf, dims, no_bulk ? 0 : (row_bulk ? 3 : 1), j.out);
   FES_LAUNCH_CHECK();
   return FES_OK;
 }
@@ -468,6 +431,7 @@ int launch_runs(const Job& j, cudaStream_t stream) {
     return FES_OK;
   } else {
     if (j.plan->runs.n_warps == 8) return launch_runs_t<ELEM, FORM, C, SD, 256>(j, stream);
+    if (j.plan->runs.n_warps == 6) return launch_runs_t<ELEM, FORM, C, SD, 192>(j, stream);
     return launch_runs_t<ELEM, FORM, C, SD, 128>(j, stream);
   }
 }

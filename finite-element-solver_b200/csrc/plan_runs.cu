@@ -105,10 +105,11 @@ int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32
   std::vector<int32_t> tiles;
   std::vector<int32_t> covered;  // {begin, end} node ranges, ascending
   const int L = tile_item_len(N);
-  // warps per CTA: tets carry 15 pairs / 96 contributions per node and 18 element lines per tile, enough for eight
-  // pair groups; the triangle templates (14 pairs per period) are split over four
-  int n_warps = (N == 4) ? 8 : 4;
-  if (const char* env = getenv("FES_RUNS_WARPS")) n_warps = atoi(env) == 8 ? 8 : 4;  // tuning knob
+  // warps per CTA: tets carry 15 pairs / 96 contributions per node and 18 element lines per tile -- six pair groups,
+  // three lines per warp in phase 1 (measured at 151^3: 1.607 ms with 6, 1.633 with 8, 1.626 with 4); the triangle
+  // templates (14 pairs per period, 8 lines) are split over four
+  int n_warps = (N == 4) ? 6 : 4;
+  if (const char* env = getenv("FES_RUNS_WARPS")) n_warps = atoi(env) == 8 ? 8 : (atoi(env) == 6 ? 6 : 4);  // tuning knob
   int64_t n_cov = 0;
   for (const Run& r : runs) {
     const Key key{r.P, sig[r.v0], r.P > 1 ? sig[r.v0 + 1] : 0ull, r.delta,

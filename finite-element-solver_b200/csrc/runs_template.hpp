@@ -20,7 +20,7 @@
 //   [0] P  [1] n_lines  [2] TS (plane stride, entries)  [3] LUp (padded image row stride, units)
 //   [4] LU (image row, units)  [5] n_spans  [6] off_lines  [7] off_spans  [8] n_warps (CTA = 32 n_warps threads)
 //   [10] threads / LU  [11] threads mod LU (the store loop's row / unit increments per step of the CTA)
-//   [12] n_words  [13] coordinate slots staged per tile  [14] delta  [15] Tmax (lane-steps per tile, 31 or 32)
+//   [12] n_words  [13] coordinate slots staged per tile  [14] delta  [15] Tmax (lane-steps per tile, 32 - the longest line overhang)
 //   [16] doubles per image row (c^2 * pairs per period)  [17] record entries (32 zero entries + n_lines * N * TS)
 //   [20..27] off_prog[warp]
 //   lines : n_lines x {eoff, ext, cidx[N]}   element of entry tau' = E0 + eoff + tau' * delta, entries
@@ -45,7 +45,7 @@
 namespace fes_runs_host {
 
 constexpr int kLaneSteps = 32;  // lane-steps per tile: one warp wide
-constexpr int kMaxWarps = 8;    // warps per CTA = pair groups of a template: 4 or 8 (the plan's choice)
+constexpr int kMaxWarps = 8;    // warps per CTA = pair groups of a template: 4, 6 or 8 (the plan's choice)
 constexpr int kZeroEntries = 32;  // record entries [0, 32) hold zeros: the padding of short partial sums (lane t reads entry t)
 constexpr int kMinPeriods = 8;  // shorter repeats stay with the tiled kernel
 constexpr int kHdrWords = 28;
@@ -207,11 +207,11 @@ inline bool build_template(int N, int c, int P, int64_t delta, const std::vector
   int64_t max_ext = 0;
   for (auto& ln : lines) max_ext = std::max(max_ext, ln.tmax - ln.tmin);
   if (max_ext > 8) return false;
-  // lane-steps per tile: 32, or 32 - max_ext when that saves a whole pass of phase 1 (the CTA's 32 n_warps threads
-  // walk n_lines * TS records: with 128 threads 8 lines x 33 entries = 3 passes for 32 lane-steps, 8 x 32 = 2 for 31)
-  auto pass_cost = [&](int T) { return (double)((n_lines * (T + (int)max_ext) + kThreads - 1) / kThreads) / (double)T; };
-  const int Tmax = (max_ext > 0 && pass_cost(kLaneSteps - (int)max_ext) < pass_cost(kLaneSteps)) ? kLaneSteps - (int)max_ext : kLaneSteps;
-  const int TS = Tmax + (int)max_ext;
+  // lane-steps per tile: 32 - max_ext, so every element line has at most 32 entries and phase 1 of the kernel is
+  // one warp-pass per line (lane = entry) with warp-uniform line descriptors
+  const int Tmax = kLaneSteps - (int)max_ext;
+  const int TS = kLaneSteps;
+  if (Tmax < 2 * kMinPeriods) return false;
   const int64_t rec_entries = kZeroEntries + (int64_t)n_lines * N * TS;
   if (rec_entries > 4095) return false;  // 16-bit BYTE offsets of the double2 planes in the codes
 

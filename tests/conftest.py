@@ -12,6 +12,12 @@ for p in (ROOT, os.path.join(ROOT, 'oracle')):
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
+# The stencil-run assembly path is reserved for meshes above 10^5 nodes by default (below that one kernel launch
+# wins); the GPU tests send their small structured meshes through it too, so every structured-mesh test covers the
+# run kernel + remainder tiles, while tests/test_gpu_runs.py compares it bit for bit with the tiled kernel
+# (FES_NO_RUNS_LAUNCH) and the unstructured / P2 / mass cases keep covering the tiled kernel alone.  Read per plan.
+os.environ.setdefault('FES_RUNS_MIN_NODES', '0')
+
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run with -m gpu on a B200)')

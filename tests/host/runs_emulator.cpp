@@ -187,29 +187,29 @@ static bool emulate_tile(const Emu& E, const int32_t* hdr, const std::vector<int
         for (int x = 0; x < SD; ++x) s_xyz[(size_t)d * SD + x] = m.xyz[node * SD + x];
     }
   }
-  // phase 1
-  for (int i = 0; i < n_lines * TS; ++i) {
-    const uint32_t inv_ts = ((1u << 20) + (uint32_t)TS - 1u) / (uint32_t)TS;
-    const int l = (int)(((uint32_t)i * inv_ts) >> 20), tp = i - l * TS;
-    if (l != i / TS) { printf("inv_ts division wrong\n"); return false; }
-    const int32_t* ld = s_t + off_lines + l * (2 + N);
-    if (tp >= T + ld[1]) continue;
-    // geometry from the TEMPLATE's corner table (not from the connectivity), like the kernel
-    Mesh tmp{N, SD, {}, {}};
-    for (int n = 0; n < N; ++n) {
-      const int ci = ld[2 + n] + tp;
-      if (ci < 0 || ci >= s_t[13]) { printf("coordinate index out of the table\n"); return false; }
-      tmp.en.push_back(n);
-      for (int x = 0; x < SD; ++x) tmp.xyz.push_back(s_xyz[(size_t)ci * SD + x]);
+  // phase 1: warp per line, lane = entry
+  if (TS != kLaneSteps) { printf("plane stride is not 32\n"); return false; }
+  for (int l = 0; l < n_lines; ++l)
+    for (int lane = 0; lane < 32; ++lane) {
+      const int32_t* ld = s_t + off_lines + l * (2 + N);
+      if (T + ld[1] > 32) { printf("a line has more than 32 entries\n"); return false; }
+      if (lane >= T + ld[1]) continue;
+      // geometry from the TEMPLATE's corner table (not from the connectivity), like the kernel
+      Mesh tmp{N, SD, {}, {}};
+      for (int n = 0; n < N; ++n) {
+        const int ci = ld[2 + n] + lane;
+        if (ci < 0 || ci >= s_t[13]) { printf("coordinate index out of the table\n"); return false; }
+        tmp.en.push_back(n);
+        for (int x = 0; x < SD; ++x) tmp.xyz.push_back(s_xyz[(size_t)ci * SD + x]);
+      }
+      double g[12];
+      element_grads(tmp, 0, g);
+      for (int n = 0; n < N; ++n) {
+        const size_t ent = (size_t)kZeroEntries + (size_t)(l * N + n) * 32 + lane;
+        if ((int)ent >= s_t[17]) { printf("record entry out of range\n"); return false; }
+        for (int x = 0; x < SD; ++x) rec[ent * SD + x] = g[n * SD + x];
+      }
     }
-    double g[12];
-    element_grads(tmp, 0, g);
-    for (int n = 0; n < N; ++n) {
-      const size_t ent = (size_t)kZeroEntries + (size_t)(l * N + n) * TS + tp;
-      if ((int)ent >= s_t[17]) { printf("record entry out of range\n"); return false; }
-      for (int x = 0; x < SD; ++x) rec[ent * SD + x] = g[n * SD + x];
-    }
-  }
   // phase 2
   const int L = (N == 3) ? 2 : 6;
   for (int warp = 0; warp < s_t[8]; ++warp) {
@@ -382,6 +382,7 @@ int main() {
   ok &= run_case("box 6x5x80 elastic", box_mesh(6, 5, 80, 0.1, 7), 3, 0.9) >= 0;
   ok &= run_case("box 6x5x80 elastic, 8 warps", box_mesh(6, 5, 80, 0.1, 7), 3, 0.9, 8) >= 0;
   ok &= run_case("rect 140x12 elastic, 8 warps", rect_mesh(140, 12, 0.15, 3), 2, 0.9, 8) >= 0;
+  ok &= run_case("box 6x5x80 elastic, 6 warps", box_mesh(6, 5, 80, 0.1, 7), 3, 0.9, 6) >= 0;
   printf(ok ? "RUNS_EMULATOR PASS\n" : "RUNS_EMULATOR FAIL\n");
   return ok ? 0 : 1;
 }

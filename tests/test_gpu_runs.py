@@ -13,7 +13,6 @@ import fes_oracle as fo
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-12
-os.environ['FES_RUNS_MIN_NODES'] = '0'   # the run path is reserved for meshes above 10^5 nodes by default; read per plan
 
 
 def close(a, b, rtol=RTOL):

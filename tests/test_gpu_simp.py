@@ -144,8 +144,13 @@ def test_simp_100_iterations_against_the_reference_run():
     mesh of tests/golden/simp100.npz, against the reference's own run with its direct solver:
       (i)  FREE-RUNNING: total compliance of every one of the 100 iterations within 1e-8 relative, the volume
            fraction held, no solve at the iteration cap;
-      (ii) TEACHER-FORCED at iterations 0 ... 99 (void elements at rho = 1e-6 from ~10 on): rho_{k+1} within 1e-9,
-           per-element compliance within 1e-8 of its maximum (checks i-iv)."""
+      (ii) TEACHER-FORCED at iterations 0 ... 99 (void elements at rho = 1e-6 from ~10 on): rho_{k+1} within 2e-8,
+           per-element compliance within 1e-8 of its maximum (checks i-iv).
+    The optimality-criteria update bisects its multiplier m to `hi - lo <= 1e-8 hi` (ref fem/design.py:39-78), so
+    rho_{k+1} ~ m^(-1/2) is DEFINED only to ~5e-9 relative on the elements no bound or move limit clips: when the
+    last bisection steps compare a volume sum at near equality, the device's fixed-tree sum and numpy's pairwise sum
+    may take different branches.  Nine of the ten checkpoints agree to 1e-10 .. 1e-12; at iteration 75 the two
+    unclipped elements (of 2400) differ by 7.5e-9, independently of the CG tolerance (1e-12 .. 1e-14 measured)."""
     F = fes()
     g = load_golden('simp100')
     topo = _mbb100(F, g, backend=F.JacobiPCGBackend(rtol=1e-12), history=None)
@@ -163,4 +168,4 @@ def test_simp_100_iterations_against_the_reference_run():
         sol = forced.step()
         assert sol.total_compliance == pytest.approx(g['total_compliance'][k], rel=1e-8)
         np.testing.assert_allclose(sol.compliance, g['compliance_kept'][j], atol=1e-8 * g['compliance_kept'][j].max())
-        np.testing.assert_allclose(forced.rho, g['rho_next_kept'][j], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(forced.rho, g['rho_next_kept'][j], rtol=2e-8, atol=2e-8)
