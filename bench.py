@@ -507,18 +507,24 @@ def run_gpu(args):
     total_el = n_el * world if world == 1 else int(2 * (RES[0] - 1) * (RES[1] - 1) * world)
     value = total_el / (ms_step * 1e-3)
 
-    # roofline of the fused assembly kernel (one launch per step): algorithmic bytes per SURVEY 8(d)
+    # roofline of the fused assembly (algorithmic bytes per SURVEY 8(d) over the whole step).  A step is two launches
+    # on a structured mesh: k_assemble_runs (the stencil-run tiles, 99.9 % of the nodes of config 2) on the caller's
+    # stream and k_assemble_tiles (the remainder: the two end nodes of every mesh row) concurrently on a side stream;
+    # `achieved` divides by the step time, so it charges the dominant kernel with everything.
     alg_bytes = 4 * 3 * n_el + 8 * 2 * n_nodes + 8 * plan.nnz
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    runs = plan.n_run_tiles > 0
+    kernel = 'k_assemble_runs<P1_TRI,ELASTIC,2,2,128>' if runs else 'k_assemble_tiles<P1_TRI,ELASTIC,2,2,128>'
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get('k_assemble_tiles_c2_bytes_per_launch')
+    if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, this round
+        traffic = json.load(open(tpath)).get(('k_assemble_runs' if runs else 'k_assemble_tiles') + '_c2_bytes_per_launch')
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': traffic, 'kernel': 'k_assemble_tiles<P1_TRI,ELASTIC,2,2,128>', 'peak_source': peak_src,
+                'traffic': traffic, 'kernel': kernel, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg_bytes, 'bytes_per_element': alg_bytes / n_el,
-                'plan_bytes_read_per_launch': plan.read_bytes}
+                'plan_bytes_read_per_launch': plan.read_bytes,
+                'run_tiles': plan.n_run_tiles, 'nodes_in_run_tiles': plan.run_nodes, 'nodes': n_nodes}
 
     # end to end through the C ABI with HOST buffers: H2D coordinates, assemble, D2H values
     h_coords = torch.as_tensor(mesh.vertices).pin_memory()

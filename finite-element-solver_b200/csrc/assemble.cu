@@ -853,12 +853,14 @@ int run(const Job& j) {
   } else {
     const fes_plan* P = j.plan;
     if (P->n_pairs == 0) return FES_OK;
-    if (P->full.tiled && !j.untiled) {
+    const bool no_runs = getenv("FES_NO_RUNS_LAUNCH") != nullptr;  // A-B knob, read per call: the tiled kernel on every node
+    const bool use_runs = runs_supported<ELEM, FORM, C, SD>() && P->runs.active && !no_runs && !j.untiled &&
+                          ((reinterpret_cast<uintptr_t>(j.out) | reinterpret_cast<uintptr_t>(j.coords)) & 15) == 0;  // 16-byte units
+    if (!use_runs && !j.untiled && !P->full_built)  // a form the run kernel does not cover, on a plan that deferred the full tiling
+      FES_TRY(ensure_full_tiling(const_cast<fes_plan*>(P), j.en, j.stream));
+    if ((use_runs || P->full.tiled) && !j.untiled) {
       static const int env_threads = getenv("FES_TILE_THREADS") ? atoi(getenv("FES_TILE_THREADS")) : 0;  // tuning knob
       const int threads = env_threads ? env_threads : tile_threads<FORM>();
-      const bool no_runs = getenv("FES_NO_RUNS_LAUNCH") != nullptr;  // A-B knob, read per call: the tiled kernel on every node
-      const bool use_runs = runs_supported<ELEM, FORM, C, SD>() && P->runs.active && !no_runs &&
-                            ((reinterpret_cast<uintptr_t>(j.out) | reinterpret_cast<uintptr_t>(j.coords)) & 15) == 0;  // 16-byte units
       const fes_tileset& T = use_runs ? P->rest : P->full;
       static const bool skip_rest = getenv("FES_EXP_SKIP_REST") != nullptr;  // timing experiment only: leaves the remainder rows unwritten
       if (use_runs) {

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "plan.cuh"
@@ -645,6 +646,15 @@ int tile_with_retries(fes_plan* P, fes_tileset& T, const std::vector<int32_t>& r
 
 }  // namespace
 
+// The tiling of every node, on first use by a form the run kernel does not cover (see fes_plan_create).
+int ensure_full_tiling(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(P->full_mutex);
+  if (P->full_built) return FES_OK;
+  FES_TRY(tile_with_retries(P, P->full, {0, (int32_t)P->n_nodes}, P->h_ne, P->h_np, d_elem_nodes, stream));
+  P->full_built = true;
+  return FES_OK;
+}
+
 int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32_t>& h_ne, const std::vector<int32_t>& h_np,
                cudaStream_t stream, std::vector<int32_t>& rest_ranges);  // plan_runs.cu
 }  // namespace fes
@@ -747,17 +757,26 @@ extern "C" int fes_plan_create(const int32_t* d_elem_nodes, int64_t n_el, int N,
   FES_LAUNCH_CHECK();
   FES_CUDA(cudaStreamSynchronize(stream));
   {
-    std::vector<int32_t> h_ne, h_np;
+    std::vector<int32_t>& h_ne = P->h_ne;
+    std::vector<int32_t>& h_np = P->h_np;
     FES_TRY(build_incidence(P, stream, h_ne, h_np));
-    FES_TRY(tile_with_retries(P, P->full, {0, (int32_t)n_nodes}, h_ne, h_np, d_elem_nodes, stream));
-    // stencil runs + the tiling of whatever they leave uncovered (plan_runs.cu)
-    if (P->full.tiled && !getenv("FES_NO_RUNS")) {
+    // Stencil runs first (plan_runs.cu) + the tiling of whatever they leave uncovered.  When they take the mesh, the
+    // tiling of EVERY node -- needed only by the forms the run kernel does not cover (mass, P2) -- is built on its
+    // first use (ensure_full_tiling): a structured mesh pays neither its build time nor its 0.3 GB of index streams
+    // unless it asks for such a form.
+    if (P->n_geo > 0 && !getenv("FES_NO_RUNS")) {
       std::vector<int32_t> rest;
       FES_TRY(build_runs(P, d_elem_nodes, h_ne, h_np, stream, rest));
       if (P->runs.active) {
         FES_TRY(tile_with_retries(P, P->rest, rest, h_ne, h_np, d_elem_nodes, stream));
         if (!rest.empty() && !P->rest.tiled) P->runs.active = false;  // cannot tile the remainder: keep the full tiling only
       }
+    }
+    if (!P->runs.active) {
+      FES_TRY(tile_with_retries(P, P->full, {0, (int32_t)n_nodes}, h_ne, h_np, d_elem_nodes, stream));
+      P->full_built = true;
+      std::vector<int32_t>().swap(P->h_ne);
+      std::vector<int32_t>().swap(P->h_np);
     }
   }
   guard.p = nullptr;
@@ -795,7 +814,11 @@ extern "C" void fes_plan_destroy(fes_plan* plan) { delete plan; }
 extern "C" int64_t fes_plan_n_dofs(const fes_plan* p) { return p ? p->n_dofs : 0; }
 extern "C" int64_t fes_plan_nnz(const fes_plan* p) { return p ? p->nnz : 0; }
 extern "C" int64_t fes_plan_n_pairs(const fes_plan* p) { return p ? p->n_pairs : 0; }
-extern "C" int64_t fes_plan_n_tiles(const fes_plan* p) { return (p && p->full.tiled) ? p->full.n_tiles : 0; }
+extern "C" int64_t fes_plan_n_tiles(const fes_plan* p) {
+  if (!p) return 0;
+  if (p->runs.active) return p->runs.n_tiles + p->rest.n_tiles;
+  return p->full.tiled ? p->full.n_tiles : 0;
+}
 extern "C" int64_t fes_plan_n_run_tiles(const fes_plan* p) { return (p && p->runs.active) ? p->runs.n_tiles : 0; }
 extern "C" int64_t fes_plan_run_nodes(const fes_plan* p) { return (p && p->runs.active) ? p->runs.n_nodes_covered : 0; }
 extern "C" const int32_t* fes_plan_indptr(const fes_plan* p) { return p ? p->indptr.p : nullptr; }

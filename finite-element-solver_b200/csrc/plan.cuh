@@ -1,5 +1,6 @@
 // The CSR pattern + scatter plan handle shared between plan.cu (builder) and assemble.cu.
 #pragma once
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -79,6 +80,7 @@ struct fes_runs {
 namespace fes {
 int runs_slot_acquire(const int32_t* words, size_t n_words, cudaStream_t stream, int* slot);  // assemble.cu; *slot = -1: none free
 void runs_slot_release(int slot);
+int ensure_full_tiling(fes_plan* P, const int32_t* d_elem_nodes, cudaStream_t stream);  // plan.cu
 }
 inline fes_runs::~fes_runs() {
   if (slot >= 0) fes::runs_slot_release(slot);
@@ -106,7 +108,11 @@ struct fes_plan {
   int64_t n_geo = 0;
   fes::DevBuf<int32_t> ne_ptr;         // n_nodes + 1 : incident-element ranges per node
   fes::DevBuf<uint32_t> ne_code;       // n_geo : e*8 + a, ascending e per node
-  fes_tileset full;                    // every node: forms / element types the run kernel does not cover
+  fes_tileset full;                    // every node: forms / element types the run kernel does not cover; built at plan
+                                       // creation when the mesh has no runs, else on first use (ensure_full_tiling)
+  bool full_built = false;
+  std::mutex full_mutex;
+  std::vector<int32_t> h_ne, h_np;     // host copies of ne_ptr / node_ptr, kept for that deferred build
   fes_tileset rest;                    // the nodes outside stencil runs (used together with `runs`)
   fes_runs runs;
 

@@ -105,10 +105,11 @@ int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32
   std::vector<int32_t> tiles;
   std::vector<int32_t> covered;  // {begin, end} node ranges, ascending
   const int L = tile_item_len(N);
-  // warps per CTA: tets carry 15 pairs / 96 contributions per node and 18 element lines per tile -- six pair groups,
-  // three lines per warp in phase 1 (measured at 151^3: 1.607 ms with 6, 1.633 with 8, 1.626 with 4); the triangle
-  // templates (14 pairs per period, 8 lines) are split over four
-  int n_warps = (N == 4) ? 6 : 4;
+  // warps per CTA (= pair groups of a template), measured at 151^3 / config 2: tet elasticity (15 pairs, 96
+  // contributions of 9 FMAs per node, 18 element lines = three per warp in phase 1) 1.396 ms with 6, 1.578 with 4,
+  // 1.549 with 8; the scalar tet forms 1.158 ms with 4, 1.270 with 6; triangles (14 pairs per period, 8 lines)
+  // 0.1345 ms with 4, 0.155 with 8
+  int n_warps = (N == 4 && c > 1) ? 6 : 4;
   if (const char* env = getenv("FES_RUNS_WARPS")) n_warps = atoi(env) == 8 ? 8 : (atoi(env) == 6 ? 6 : 4);  // tuning knob
   int64_t n_cov = 0;
   for (const Run& r : runs) {
