@@ -707,7 +707,8 @@ def config5_metrics(F, world, rank, dev, n=151, pcg_iters=300):
             'assembly_hbm_frac_of_measured': alg / (asm_ms * 1e-3) / 1e9 / measured_peak()[0],
             'plan_build_s': plan_s, 'host_mesh_partition_s': host_s, 'pcg_us_per_iteration': us_iter,
             'pcg_iterations_timed': pcg_iters, 'scaling': 'strong', 'parity': parity,
-            'pcg_loop': 'classic (3 barriers)' if world == 1 else 'overlapped single-reduction (distributed default)'}
+            'pcg_loop': 'classic (3 barriers)' if world == 1 else
+                        'classic recurrences, halo shipped inside the p update, interior rows first, mailbox reductions (distributed default)'}
 
 
 def assembly_case(F, V, form, reps=20):

@@ -336,7 +336,8 @@ __device__ __forceinline__ double sparse_product(const PcgArgs& A, int64_t tid, 
 // products and the two extra vector reads inside the product phase cost the HBM-bound SpMV more than the
 // barrier and the reduction they remove, so the textbook loop stays the default.
 //
-// Distributed default = FUSED with overlap: one rank reduction instead of two per iteration (a whole NVLink
+// Distributed FUSED variant (FES_PCG_DIST_FUSED=1; the default is the three-phase loop with overlap level 3, see
+// fes_solver_solve): one rank reduction instead of two per iteration (a whole NVLink
 // round trip less), and the halo of p is posted without a grid barrier at the top of the iteration and
 // awaited only by the rows that read ghost entries, after the interior rows have been multiplied.
 #ifndef FES_PCG_DIST_BLOCKS

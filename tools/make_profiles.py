@@ -10,12 +10,12 @@ import sys
 from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-R = sys.argv[1] if len(sys.argv) > 1 else 'r01'
+R = sys.argv[1] if len(sys.argv) > 1 else 'r02'
 G, P = os.path.join(ROOT, 'gpurun_out'), os.path.join(ROOT, 'profiles')
 run = lambda *a: subprocess.run([sys.executable, *a], capture_output=True, text=True, cwd=ROOT).stdout
 
-for tag, note in (('assemble_c2', 'k_assemble_tiles<P1_TRI,ELASTIC,2,2,128>, config 2 (inside bench.py --no-extra)'),
-                  ('assemble_tet', 'k_assemble_tiles<P1_TET,ELASTIC,3,3,128>, 61^3 box (tools/profile_hotpath.py tet)'),
+for tag, note in (('assemble_c2', 'k_assemble_runs<P1_TRI,ELASTIC,2,2,128>, config 2 (inside bench.py --no-extra)'),
+                  ('assemble_tet', 'k_assemble_runs<P1_TET,ELASTIC,3,3,192>, config 5 on one GPU: 151^3 box (tools/profile_tet151.py)'),
                   ('assemble_p2', 'k_assemble_tiles<P2_TRI,ELASTIC,2,2,128>, config 3: 708^2 vertices, 999 698 six-node triangles (tools/profile_hotpath.py p2)'),
                   ('pcg_c2', 'k_pcg<2>, config 2, 40 iterations (tools/profile_hotpath.py all)')):
     rep = os.path.join(G, f'{R}_{tag}.ncu-rep')
@@ -23,7 +23,7 @@ for tag, note in (('assemble_c2', 'k_assemble_tiles<P1_TRI,ELASTIC,2,2,128>, con
         continue
     text = f'ncu --set full --clock-control none: {note}\n' + run('tools/ncu_summary.py', rep)
     if tag.startswith('assemble'):
-        text += '\n-- per phase (split at BAR.SYNC): prologue | prologue | phase 1 | coordinates + phase 2 | store | ...\n'
+        text += '\n-- per phase (split at BAR.SYNC); run kernel: prologue | phase 1 | staging + phase 2 | store; tiled kernel: prologue | prologue | phase 1 | coordinates + phase 2 | store | ...\n'
         text += run('tools/ncu_phases.py', rep)
         text += '\n-- LSU cost per SASS instruction (>= 1.5 % of the kernel)\n' + run('tools/ncu_src.py', rep, '0.015')
         text += '\n-- top stall sites\n' + run('tools/ncu_stalls.py', rep, '12')
@@ -36,9 +36,11 @@ if os.path.exists(rep):
     idx = {h: i for i, h in enumerate(rows[0])}
     val = lambda k: float(rows[2][idx[k]]) * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1}[rows[1][idx[k]]]
     traffic = int(val('dram__bytes_read.sum') + val('dram__bytes_write.sum'))
-    json.dump({'k_assemble_tiles_c2_bytes_per_launch': traffic,
-               'source': f'ncu --set full, profiles/{R}_assemble_c2.txt (dram__bytes_read.sum + dram__bytes_write.sum)'},
-              open(os.path.join(P, 'traffic.json'), 'w'), indent=1)
+    old = json.load(open(os.path.join(P, 'traffic.json'))) if os.path.exists(os.path.join(P, 'traffic.json')) else {}
+    old.update({'k_assemble_runs_c2_bytes_per_launch': traffic,
+                'source_runs': f'ncu --set full, profiles/{R}_assemble_c2.txt (dram__bytes_read.sum + dram__bytes_write.sum of one '
+                               'k_assemble_runs launch; the remainder-tile launch beside it writes 0.1 % of the values)'})
+    json.dump(old, open(os.path.join(P, 'traffic.json'), 'w'), indent=1)
 
 src = os.path.join(G, f'{R}_launches_bench_noextra.csv')
 if os.path.exists(src):
@@ -52,7 +54,8 @@ if os.path.exists(src):
     tot = sum(agg.values())
     lines = ['ncu --metrics gpu__time_duration.sum --clock-control none: python bench.py --steps 5 --warmup 3 --no-extra',
              '(cold-cache, serialised launches: compare shares, not absolutes).  The timed region of the bench is the',
-             '5 + 3 warm-up launches of k_assemble_tiles<1,2,2,2,128>; everything else is the one-off plan build and the',
+             '5 + 3 warm-up steps = launches of k_assemble_runs<1,2,2,2,128> + k_assemble_tiles<1,2,2,2,128> (the remainder tiles);',
+             'everything else is the one-off plan build and the',
              'end-to-end leg (which launches the same kernel).', '']
     for name, us in sorted(agg.items(), key=lambda kv: -kv[1]):
         lines.append(f'{us:12.1f} us {100 * us / tot:5.1f}%  x{cnt[name]:<4d} {name}')
