@@ -189,34 +189,34 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
   // tile headers {v0, T, template offset, E0 | first pair ...}, fetched two tiles ahead so neither the staging of the
   // next tile nor this tile's phases ever wait for one
   const int4* hdr4 = reinterpret_cast<const int4*>(tiles);
-  auto load_hdr = [&](int k, int4& h, int32_t& p0) {
+  auto load_hdr = [&](int k, int4& h, int4& g) {  // h = {v0, T, template offset, E0}, g = {first pair, -, pair stride, -}
     const int64_t t = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
     // volatile asm: the loads stay where they are written (two tiles ahead) and their results in vector registers
     // (the compiler otherwise proves them warp-uniform and converts them to uniform registers right behind the
     // load, a long-scoreboard stall per tile)
     asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "l"(hdr4 + 2 * t));
-    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(p0) : "l"(tiles + 8 * t + 4));
+    asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(g.x), "=r"(g.y), "=r"(g.z), "=r"(g.w) : "l"(hdr4 + 2 * t + 1));
   };
-  int4 h0, h1 = make_int4(0, 0, 0, 0);
-  int32_t pair0, pair1 = 0;
-  load_hdr(0, h0, pair0);
-  if (n_my > 1) load_hdr(1, h1, pair1);
+  int4 h0, h1 = make_int4(0, 0, 0, 0), g0, g1 = make_int4(0, 0, 0, 0);
+  load_hdr(0, h0, g0);
+  if (n_my > 1) load_hdr(1, h1, g1);
 
-  // staging of one tile's coordinate spans: warp w takes spans w, w + 4, ...
+  // staging of one tile's coordinate spans (strided node sequences v0 + start + step * i -> slots base + i): warp w
+  // takes spans w, w + kWarps, ...
   auto stage = [&](int32_t v0, int32_t T, int32_t toff) {
-    const int P = tm.w[toff], n_spans = tm.w[toff + 5], so = toff + tm.w[toff + 7];
-    constexpr int G = (SD == 2) ? 1 : SD;  // copy items per node: one 16-byte node (2D) or SD doubles
+    const int step = tm.w[toff + 9], n_spans = tm.w[toff + 5], so = toff + tm.w[toff + 7];
     for (int s = warp; s < n_spans; s += kRunThreads / 32) {
-      const int32_t start = tm.w[so + 4 * s], ext = tm.w[so + 4 * s + 1], base = tm.w[so + 4 * s + 2], blk = tm.w[so + 4 * s + 3];
-      const int len = (P * (T - 1) + ext + 1) * G;
-      const int64_t g0 = ((int64_t)v0 + start) * G;
-      for (int j = lane; j < len; j += 32) {
-        const int64_t g = g0 + j;
-        if (g < 0 || g >= n_nodes * G) continue;  // entries no lane references may fall outside the mesh
-        const int i = j / G, comp = j - i * G;
-        const int slot = base + (P == 2 ? (i & 1) * blk + (i >> 1) : (P == 1 ? i : (i % P) * blk + i / P));
-        if constexpr (SD == 2) cp_async16(reinterpret_cast<double2*>(s_xyz) + slot, reinterpret_cast<const double2*>(coords) + g);
-        else cp_async8(s_xyz + slot * SD + comp, coords + g);
+      const int32_t start = tm.w[so + 4 * s], n_ext = tm.w[so + 4 * s + 1], base = tm.w[so + 4 * s + 2];
+      const int cnt = T + n_ext;
+      for (int i = lane; i < cnt; i += 32) {
+        const int64_t node = (int64_t)v0 + start + (int64_t)step * i;
+        if (node < 0 || node >= n_nodes) continue;  // entries no lane references may fall outside the mesh
+        if constexpr (SD == 2) {
+          cp_async16(reinterpret_cast<double2*>(s_xyz) + base + i, reinterpret_cast<const double2*>(coords) + node);
+        } else {
+#pragma unroll
+          for (int comp = 0; comp < SD; ++comp) cp_async8(s_xyz + (base + i) * SD + comp, coords + node * SD + comp);
+        }
       }
     }
   };
@@ -226,16 +226,17 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
 
   for (int k = 0; k < n_my; ++k) {
     const int32_t T = h0.y, toff = h0.z, E0 = h0.w;
-    const int32_t my_pair0 = pair0;
+    const int32_t my_pair0 = g0.x, pstride = g0.z;
     const bool has_next = k + 1 < n_my;
-    int4 h2 = make_int4(0, 0, 0, 0);
-    int32_t pair2 = 0;
-    if (k + 2 < n_my) load_hdr(k + 2, h2, pair2);
+    int4 h2 = make_int4(0, 0, 0, 0), g2 = make_int4(0, 0, 0, 0);
+    if (k + 2 < n_my) load_hdr(k + 2, h2, g2);
     const int n_lines = tm.w[toff + 1], LUp = tm.w[toff + 3], LU = tm.w[toff + 4];
     // 8-byte units and an odd row length: the image needs no padding (LUp == LU), i.e. it IS the tile's contiguous
     // slice of `values` and one TMA bulk store writes it.  An odd first value index is mirrored by an 8-byte skew of
     // the image, so both sides of the copy share their 16-byte phase.
-    const bool bulk = UB == 8 && LUp == LU && use_bulk;
+    // A strided run's rows are pstride pairs apart in `values` (contiguous runs: pstride = the pairs per lane-step)
+    const int GR = C * C * pstride / (UB / 8);  // units between consecutive image rows in `values`
+    const bool bulk = UB == 8 && LUp == LU && GR == LU && use_bulk;
     const bool row_bulk = UB == 16 && (use_bulk & 2);
     const uint32_t skew = bulk ? (uint32_t)(((int64_t)C * C * my_pair0) & 1) : 0u;
 
@@ -301,7 +302,7 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
         }
       }
     }
-    if (warp == 0) bulk_wait_read_all();  // the previous tile's bulk stores have finished reading the image
+    bulk_wait_read_all();  // the previous tile's bulk stores (issued by this thread, if any) have finished reading the image
     __syncthreads();  // records visible; the coordinate table is free; the previous image has been copied out
 
     if (has_next) stage(h1.x, h1.y, h1.z);  // lands under phase 2
@@ -362,10 +363,14 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
         if (head) values[val0] = img[0];
         if (tail) values[val0 + n_out - 1] = img[n_out - 1];
       }
-    } else if (row_bulk) {  // padded rows, 16-byte units: one bulk store per image row, issued by the lanes of warp 0
-      if (warp == 0 && lane < T)
-        bulk_s2g(reinterpret_cast<unsigned char*>(values + (int64_t)C * C * my_pair0) + (size_t)lane * LU * UB,
-                 s_img + (size_t)lane * LUp * UB, (uint32_t)(LU * UB));
+    } else if (row_bulk) {  // padded rows, 16-byte units: one bulk store per image row; every warp issues its share
+      // (UBLKCP takes uniform operands, so a warp's lanes are served one after the other: spread over the warps,
+      // none of them arrives late at the next tile's phase 1)
+      constexpr int kWarps = kRunThreads / 32;
+      const int rpw = (T + kWarps - 1) / kWarps, r = warp * rpw + lane;
+      if (lane < rpw && r < T)
+        bulk_s2g(reinterpret_cast<unsigned char*>(values + (int64_t)C * C * my_pair0) + (size_t)r * GR * UB,
+                 s_img + (size_t)r * LUp * UB, (uint32_t)(LU * UB));
     } else {  // padded rows: thread x takes units x, x + threads, ...
       unsigned char* dst = reinterpret_cast<unsigned char*>(values + (int64_t)C * C * my_pair0);
       const int total = T * LU, dr = tm.w[toff + 10], du = tm.w[toff + 11];
@@ -373,20 +378,21 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
 #pragma unroll 2
       for (int x = tid; x < total; x += kRunThreads) {
         const uint32_t src = img_b + (uint32_t)(r * LUp + u) * (uint32_t)UB;
+        const size_t o = (size_t)(uint32_t)(r * GR + u) * UB;
         if constexpr (UB == 16) {
           const double2 v = lds_f64x2(src);
-          *reinterpret_cast<double2*>(dst + (size_t)(uint32_t)x * 16) = v;
+          *reinterpret_cast<double2*>(dst + o) = v;
         } else {
-          *reinterpret_cast<double*>(dst + (size_t)(uint32_t)x * 8) = lds_f64(src);
+          *reinterpret_cast<double*>(dst + o) = lds_f64(src);
         }
         r += dr; u += du;
         if (u >= LU) { u -= LU; ++r; }
       }
     }
-    h0 = h1; pair0 = pair1;
-    h1 = h2; pair1 = pair2;
+    h0 = h1; g0 = g1;
+    h1 = h2; g1 = g2;
   }
-  if (warp == 0) bulk_wait_read_all();  // shared memory must outlive the last bulk store's reads
+  bulk_wait_read_all();  // shared memory must outlive the last bulk stores' reads
 }
 
 template <int ELEM, int FORM, int C, int SD, int kRunThreads>

@@ -4,6 +4,7 @@
 // template program per distinct (period, signatures, element stride).
 #include <stdlib.h>
 
+#include <algorithm>
 #include <map>
 #include <tuple>
 #include <vector>
@@ -39,21 +40,21 @@ __global__ void k_verify_runs(const int32_t* __restrict__ tiles, int64_t n_tiles
   const int t = (int)(i - tile * kLaneSteps);
   if (tile >= n_tiles) return;
   const int32_t* h = tiles + tile * kTileInts;
-  const int32_t v0 = h[0], T = h[1], E0 = h[3], pair0 = h[4];
+  const int32_t v0 = h[0], T = h[1], E0 = h[3], pair0 = h[4], pstride = h[6];
   if (t >= T) return;
   const int32_t* R = raw + h[5];
   const int P = R[0];
   const int64_t delta = R[1];
-  const int ppp = R[2];
+  const int step = R[3];
   const int32_t* p = R + 4;
   bool ok = true;
   for (int phi = 0; phi < P; ++phi) {
     const int ninc = p[0], deg = p[1], prefix = p[2];
     p += 3;
-    const int64_t base = (int64_t)v0 + (int64_t)P * t, v = base + phi;
+    const int64_t base = (int64_t)v0 + (int64_t)step * t, v = base + phi;
     if (v >= n_nodes) { ok = false; break; }
     const int32_t g0 = ne_ptr[v];
-    ok = ok && (ne_ptr[v + 1] - g0 == ninc) && (node_ptr[v] == pair0 + t * ppp + prefix) && (node_ptr[v + 1] - node_ptr[v] == deg);
+    ok = ok && (ne_ptr[v + 1] - g0 == ninc) && (node_ptr[v] == pair0 + t * pstride + prefix) && (node_ptr[v + 1] - node_ptr[v] == deg);
     if (!ok) break;
     for (int r = 0; r < ninc; ++r) {
       const int64_t e = (int64_t)E0 + (int64_t)t * delta + p[0];
@@ -94,16 +95,43 @@ int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32
   d_sig.release();
   d_eref.release();
   for (int64_t v = 0; v < nn; ++v) ninc[v] = h_ne[v + 1] - h_ne[v];
-  const std::vector<Run> runs = segment_runs(sig.data(), eref.data(), ninc.data(), nn);
+  std::vector<Run> runs = segment_runs(sig.data(), eref.data(), ninc.data(), nn);
   if (runs.empty()) return FES_OK;
+  // strided runs among the nodes left over (row / z-line end nodes of structured meshes); ascending v0 overall
+  {
+    std::vector<char> free_node(nn, 1);
+    for (Run& r : runs) {
+      r.pstride = h_np[r.v0 + r.P] - h_np[r.v0];
+      for (int64_t v = r.v0; v < (int64_t)r.v0 + (int64_t)r.P * r.periods; ++v) free_node[v] = 0;
+    }
+    if (!getenv("FES_NO_STRIDED_RUNS")) {
+      // repeated: what one pass leaves (the four corner nodes of every i-plane of a box: the ends of the strided runs
+      // along j) is itself strided (along i)
+      for (int pass = 0; pass < 4; ++pass) {
+        const std::vector<Run> strided = segment_strided(sig.data(), eref.data(), ninc.data(), h_np.data(), nn, free_node);
+        if (strided.empty()) break;
+        runs.insert(runs.end(), strided.begin(), strided.end());
+      }
+      // A handful of nodes left (the corners of a structured mesh): one single-node tile each, so the step needs no
+      // second kernel at all (a remainder kernel on a side stream costs ~8 us of fork / join per assembly however
+      // small it is).  More than that is an irregular region: it keeps the tiled kernel.
+      std::vector<int64_t> left;
+      for (int64_t v = 0; v < nn && left.size() <= 64; ++v)
+        if (free_node[v]) left.push_back(v);
+      if (left.size() <= 64)
+        for (int64_t v : left)
+          if (ninc[v] > 0) runs.push_back(Run{(int32_t)v, 1, 1, 1, 1, h_np[v + 1] - h_np[v]});
+    }
+  }
 
   // one template per distinct (P, signatures, element stride, phase offset of the element base)
-  using Key = std::tuple<int, uint64_t, uint64_t, int64_t, int64_t>;
+  using Key = std::tuple<int, uint64_t, uint64_t, int64_t, int64_t, int>;
   std::map<Key, int> tmpl_of;  // -> index into tmpls, or -1 (not encodable)
   std::vector<Template> tmpls;
   std::vector<int32_t> word_off, raw_off, blob, raw;
   std::vector<int32_t> tiles;
   std::vector<int32_t> covered;  // {begin, end} node ranges, ascending
+  std::vector<std::pair<int32_t, int32_t>> covered_ranges;
   const int L = tile_item_len(N);
   // warps per CTA (= pair groups of a template), measured at 151^3 / config 2: tet elasticity (15 pairs, 96
   // contributions of 9 FMAs per node, 18 element lines = three per warp in phase 1) 1.396 ms with 6, 1.578 with 4,
@@ -114,7 +142,7 @@ int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32
   int64_t n_cov = 0;
   for (const Run& r : runs) {
     const Key key{r.P, sig[r.v0], r.P > 1 ? sig[r.v0 + 1] : 0ull, r.delta,
-                  r.P > 1 ? (int64_t)eref[r.v0 + 1] - eref[r.v0] : 0};
+                  r.P > 1 ? (int64_t)eref[r.v0 + 1] - eref[r.v0] : 0, r.step};
     auto it = tmpl_of.find(key);
     int ti;
     if (it != tmpl_of.end()) {
@@ -142,7 +170,7 @@ int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32
         }
       }
       Template t;
-      if (build_template(N, c, r.P, r.delta, ph, L, n_warps, t) && blob.size() + t.words.size() <= (size_t)fes_runs::kMaxTmplWords) {
+      if (build_template(N, c, r.P, r.delta, ph, L, n_warps, t, r.step) && blob.size() + t.words.size() <= (size_t)fes_runs::kMaxTmplWords) {
         ti = (int)tmpls.size();
         word_off.push_back((int32_t)blob.size());
         raw_off.push_back((int32_t)raw.size());
@@ -158,14 +186,22 @@ int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32
     std::vector<std::pair<int32_t, int32_t>> parts;
     split_run(r, tmpls[ti].Tmax, parts);
     for (auto& pt : parts) {
-      const int32_t v0 = r.v0 + r.P * pt.first;
-      const int32_t hdr[kTileInts] = {v0, pt.second, word_off[ti], eref[v0], h_np[v0], raw_off[ti], 0, 0};
+      const int32_t v0 = r.v0 + r.step * pt.first;
+      const int32_t hdr[kTileInts] = {v0, pt.second, word_off[ti], eref[v0], h_np[v0], raw_off[ti], r.pstride, 0};
       tiles.insert(tiles.end(), hdr, hdr + kTileInts);
     }
-    const int32_t b = r.v0, e = r.v0 + r.P * r.periods;
-    if (!covered.empty() && covered.back() == b) covered.back() = e;
-    else { covered.push_back(b); covered.push_back(e); }
-    n_cov += e - b;
+    if (r.step == r.P) {
+      covered_ranges.emplace_back(r.v0, r.v0 + r.P * r.periods);
+    } else {
+      for (int32_t k = 0; k < r.periods; ++k) covered_ranges.emplace_back(r.v0 + r.step * k, r.v0 + r.step * k + 1);
+    }
+    n_cov += (int64_t)r.P * r.periods;
+  }
+  // the covered nodes as ascending, merged {begin, end} ranges
+  std::sort(covered_ranges.begin(), covered_ranges.end());
+  for (auto& cr : covered_ranges) {
+    if (!covered.empty() && covered.back() == cr.first) covered.back() = cr.second;
+    else { covered.push_back(cr.first); covered.push_back(cr.second); }
   }
   const int64_t nt = (int64_t)tiles.size() / kTileInts;
   // Worth two kernels (run tiles + remainder tiles on a side stream) only when the runs cover a good part of a mesh

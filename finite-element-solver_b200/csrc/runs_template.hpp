@@ -19,14 +19,14 @@
 // Template blob (int32 words; offsets relative to the template's first word):
 //   [0] P  [1] n_lines  [2] TS (plane stride, entries)  [3] LUp (padded image row stride, units)
 //   [4] LU (image row, units)  [5] n_spans  [6] off_lines  [7] off_spans  [8] n_warps (CTA = 32 n_warps threads)
+//   [9] step (node stride per lane-step: P for consecutive nodes, S for a strided run)
 //   [10] threads / LU  [11] threads mod LU (the store loop's row / unit increments per step of the CTA)
 //   [12] n_words  [13] coordinate slots staged per tile  [14] delta  [15] Tmax (lane-steps per tile, 32 - the longest line overhang)
 //   [16] doubles per image row (c^2 * pairs per period)  [17] record entries (32 zero entries + n_lines * N * TS)
 //   [20..27] off_prog[warp]
 //   lines : n_lines x {eoff, ext, cidx[N]}   element of entry tau' = E0 + eoff + tau' * delta, entries
 //           tau' < T + ext; corner c sits in coordinate slot cidx[c] + tau'
-//   spans : n_spans x {start, ext, base, blk}  nodes v0 + start + i, i < P (T - 1) + ext + 1, staged in slot
-//           base + (i mod P) * blk + i / P (de-interleaved by period phase)
+//   spans : n_spans x {start, n_ext, base, 0}  nodes v0 + start + step * i, i <= (T - 1) + n_ext, staged in slot base + i
 //   prog  : per warp {n_pairs, then per pair: head, codes[2^lg * L]}
 //           head = img_b (15) | row_b (12) << 15 | lg (2) << 27 | diag << 29: byte offset 8 (c^2 prefix_phi + c k) of the
 //                  block in the lane's image row, bytes 8 c deg between the block's rows
@@ -49,7 +49,7 @@ constexpr int kMaxWarps = 8;    // warps per CTA = pair groups of a template: 4,
 constexpr int kZeroEntries = 32;  // record entries [0, 32) hold zeros: the padding of short partial sums (lane t reads entry t)
 constexpr int kMinPeriods = 8;  // shorter repeats stay with the tiled kernel
 constexpr int kHdrWords = 28;
-constexpr int kTileInts = 8;    // {v0, T, template word offset, E0, first pair, raw word offset, 0, 0}
+constexpr int kTileInts = 8;    // {v0, T, template word offset, E0, first pair, raw word offset, pair stride per lane-step, 0}
 
 // 64-bit mix shared by the device signature kernel and the host emulator
 #if defined(__CUDACC__)
@@ -76,9 +76,11 @@ FES_RUNS_HD inline uint64_t node_signature(int32_t v, int32_t ninc, const uint32
 
 struct Run {
   int32_t v0;
-  int32_t P;
-  int32_t periods;
-  int64_t delta;
+  int32_t P;        // nodes per lane-step (consecutive): 1 or 2
+  int32_t periods;  // lane-steps
+  int64_t delta;    // element stride per lane-step
+  int32_t step;     // node stride per lane-step: P for a run of consecutive nodes, S > 1 for a STRIDED run (P = 1)
+  int32_t pstride;  // stored pairs between consecutive lane-steps: node_ptr[v + step] - node_ptr[v]
 };
 
 // Greedy segmentation of the node range into runs; everything else is left to the tiled kernel.
@@ -99,12 +101,50 @@ inline std::vector<Run> segment_runs(const uint64_t* sig, const int32_t* eref, c
       while (w < n && sig[w] == sig[w - P] && (int64_t)eref[w] - eref[w - P] == delta) ++w;
       const int64_t periods = (w - v) / P;
       if (periods >= min_periods) {
-        runs.push_back(Run{(int32_t)v, P, (int32_t)periods, delta});
+        runs.push_back(Run{(int32_t)v, P, (int32_t)periods, delta, P, 0});  // pstride: filled in by the caller from node_ptr
         v += periods * P;
         found = true;
       }
     }
     if (!found) ++v;
+  }
+  return runs;
+}
+
+// STRIDED runs among the nodes the consecutive runs left over (`free_node[v]` != 0): v0 + S t with the same relative
+// stencil, a constant element stride and a constant pair stride.  The two end nodes of every row of a structured
+// mesh are such runs (S = the row pitch, or twice that when the diagonals alternate), as are the first / last nodes
+// of the z-lines of a box mesh: with them in the run kernel a structured mesh needs no remainder tiles at all but
+// for a handful of corner nodes.  Marks the nodes it takes in free_node (set to 0).
+inline std::vector<Run> segment_strided(const uint64_t* sig, const int32_t* eref, const int32_t* ninc, const int32_t* node_ptr,
+                                        int64_t n, std::vector<char>& free_node, int min_periods = kMinPeriods) {
+  std::vector<Run> runs;
+  std::vector<int64_t> rest;
+  for (int64_t v = 0; v < n; ++v)
+    if (free_node[v] && ninc[v] > 0) rest.push_back(v);
+  for (size_t a = 0; a < rest.size(); ++a) {
+    const int64_t v = rest[a];
+    if (!free_node[v]) continue;
+    // candidate strides: the distances to the next few left-over nodes with the same signature
+    int tried = 0;
+    for (size_t b = a + 1; b < rest.size() && b < a + 64 && tried < 3; ++b) {
+      const int64_t w1 = rest[b];
+      if (!free_node[w1] || sig[w1] != sig[v]) continue;
+      ++tried;
+      const int64_t S = w1 - v, delta = (int64_t)eref[w1] - eref[v], ps = (int64_t)node_ptr[w1] - node_ptr[v];
+      if (S < 2 || S > 0x3fffffff || delta <= 0 || ps <= 0) continue;
+      int64_t w = w1, cnt = 1;
+      while (w < n && free_node[w] && sig[w] == sig[v] && (int64_t)eref[w] - eref[w - S] == delta &&
+             (int64_t)node_ptr[w] - node_ptr[w - S] == ps) {
+        ++cnt;
+        w += S;
+      }
+      if (cnt >= min_periods) {
+        runs.push_back(Run{(int32_t)v, 1, (int32_t)cnt, delta, (int32_t)S, (int32_t)ps});
+        for (int64_t k = 0; k < cnt; ++k) free_node[v + k * S] = 0;
+        break;
+      }
+    }
   }
   return runs;
 }
@@ -142,7 +182,9 @@ inline void item_split_host(uint32_t cnt, uint32_t L, uint32_t& lg, uint32_t& m)
 // with the tiled kernel).  L = contributions per partial sum (tile_item_len(N)): the summation tree of a pair
 // is the tiled kernel's, so both kernels produce the same bits for the same pair.
 inline bool build_template(int N, int c, int P, int64_t delta, const std::vector<PhaseStencil>& ph, int L, int n_warps,
-                           Template& out) {
+                           Template& out, int step = 0 /* node stride per lane-step; 0 = P (consecutive nodes) */) {
+  if (step <= 0) step = P;
+  if (step != P && P != 1) return false;
   out = Template();
   out.P = P; out.N = N; out.c = c; out.delta = delta;
   if (delta <= 0 || delta > 0x7fffffff || (int)ph.size() != P || n_warps < 1 || n_warps > kMaxWarps) return false;
@@ -170,7 +212,7 @@ inline bool build_template(int N, int c, int P, int64_t delta, const std::vector
     for (int r = 0; r < ninc; ++r) {
       const int64_t q = floor_div(s.de[r], delta), d0 = s.de[r] - q * delta;
       std::vector<int64_t> oc(N);
-      for (int k = 0; k < N; ++k) oc[k] = (int64_t)s.corner[r * N + k] - (int64_t)P * q;
+      for (int k = 0; k < N; ++k) oc[k] = (int64_t)s.corner[r * N + k] - (int64_t)step * q;
       if (s.a[r] < 0 || s.a[r] >= N || s.corner[r * N + s.a[r]] != phi) return false;  // the node itself
       const auto lkey = std::make_pair(d0, oc);
       auto it = line_of.find(lkey);
@@ -215,40 +257,40 @@ inline bool build_template(int N, int c, int P, int64_t delta, const std::vector
   const int64_t rec_entries = kZeroEntries + (int64_t)n_lines * N * TS;
   if (rec_entries > 4095) return false;  // 16-bit BYTE offsets of the double2 planes in the codes
 
-  // coordinate spans: every corner of every line covers nodes [o + P tmin, o + P tmax + P (T - 1)]
+  // Coordinate spans.  Corner c of line l sits at node v0 + o + step * tau for the entries tau in [tmin, T - 1 + tmax]:
+  // a STRIDED node sequence.  Sequences of one residue class (mod step) that overlap are merged into one span
+  // {start, n_ext}: nodes v0 + start + step * i, i <= (T - 1) + n_ext, staged in slots base + i -- so the corner
+  // of entry tau' is slot(c) + tau', unit stride across the threads of phase 1 whatever the period or the stride.
   struct Iv { int64_t lo, hi; };
   std::vector<Iv> ivs;
   for (auto& ln : lines)
-    for (int k = 0; k < N; ++k) ivs.push_back(Iv{ln.ocan[k] + P * ln.tmin, ln.ocan[k] + P * ln.tmax});
-  std::sort(ivs.begin(), ivs.end(), [](const Iv& x, const Iv& y) { return x.lo < y.lo; });
-  struct Span { int64_t start, ext, base, blk; };
+    for (int k = 0; k < N; ++k) ivs.push_back(Iv{ln.ocan[k] + step * ln.tmin, ln.ocan[k] + step * ln.tmax});
+  auto residue = [&](int64_t x) { return ((x % step) + step) % step; };
+  std::sort(ivs.begin(), ivs.end(), [&](const Iv& x, const Iv& y) {
+    return residue(x.lo) != residue(y.lo) ? residue(x.lo) < residue(y.lo) : x.lo < y.lo;
+  });
+  struct Span { int64_t start, n_ext, base; };
   std::vector<Span> spans;
   for (auto& iv : ivs) {
-    if (!spans.empty() && iv.lo <= spans.back().start + spans.back().ext + (int64_t)P * (kMinPeriods - 1) + 1) {
-      spans.back().ext = std::max(spans.back().ext, iv.hi - spans.back().start);
+    if (!spans.empty() && residue(iv.lo) == residue(spans.back().start) &&
+        iv.lo <= spans.back().start + (int64_t)step * (spans.back().n_ext + kMinPeriods)) {
+      spans.back().n_ext = std::max(spans.back().n_ext, (iv.hi - spans.back().start) / step);
     } else {
-      spans.push_back(Span{iv.lo, iv.hi - iv.lo, 0, 0});
+      spans.push_back(Span{iv.lo, (iv.hi - iv.lo) / step, 0});
     }
   }
-  // A span is staged de-interleaved by node parity (period): node i of the span sits in slot
-  // base + (i mod P) * blk + i / P, so the corner of entry tau' (node i0 + P tau') is slot(i0) + tau': unit stride
-  // across the threads of phase 1 whatever the period
   int64_t coord_slots = 0;
   for (auto& sp : spans) {
-    if (sp.start < -0x3fffffff || sp.start > 0x3fffffff || sp.ext > 4096) return false;
+    if (sp.start < -0x3fffffff || sp.start > 0x3fffffff || sp.n_ext > 64) return false;
     sp.base = coord_slots;
-    sp.blk = ((int64_t)P * (Tmax - 1) + sp.ext + 1 + P - 1) / P;
-    if (P == 2) while (sp.blk % 8 != 4) ++sp.blk;  // a quarter-warp's even / odd nodes land in disjoint bank groups
-    coord_slots += (int64_t)P * sp.blk;
+    coord_slots += (int64_t)(Tmax - 1) + sp.n_ext + 1;
     coord_slots = (coord_slots + 1) & ~(int64_t)1;
   }
   if (coord_slots > 8192 || spans.size() > 64) return false;
   auto cidx_of = [&](int64_t node_rel) -> int64_t {
     for (auto& sp : spans)
-      if (node_rel >= sp.start && node_rel <= sp.start + sp.ext) {
-        const int64_t i = node_rel - sp.start;
-        return sp.base + (i % P) * sp.blk + i / P;
-      }
+      if (residue(node_rel) == residue(sp.start) && node_rel >= sp.start && node_rel <= sp.start + step * sp.n_ext)
+        return sp.base + (node_rel - sp.start) / step;
     return -1;
   };
 
@@ -314,7 +356,7 @@ inline bool build_template(int N, int c, int P, int64_t delta, const std::vector
   W.assign(kHdrWords, 0);
   W[0] = P; W[1] = n_lines; W[2] = TS; W[3] = LUp; W[4] = LU; W[5] = (int32_t)spans.size();
   W[13] = (int32_t)coord_slots; W[14] = (int32_t)delta; W[15] = Tmax; W[16] = row_doubles; W[17] = (int32_t)rec_entries;
-  W[8] = n_warps; W[10] = kThreads / LU; W[11] = kThreads % LU;
+  W[8] = n_warps; W[9] = step; W[10] = kThreads / LU; W[11] = kThreads % LU;
   W[6] = (int32_t)W.size();
   for (auto& ln : lines) {
     const int64_t eoff = ln.d0 + ln.tmin * delta;
@@ -322,14 +364,14 @@ inline bool build_template(int N, int c, int P, int64_t delta, const std::vector
     W.push_back((int32_t)eoff);
     W.push_back((int32_t)(ln.tmax - ln.tmin));
     for (int k = 0; k < N; ++k) {
-      const int64_t ci = cidx_of(ln.ocan[k] + P * ln.tmin);
+      const int64_t ci = cidx_of(ln.ocan[k] + step * ln.tmin);
       if (ci < 0) return false;
       W.push_back((int32_t)ci);
     }
   }
   W[7] = (int32_t)W.size();
   for (auto& sp : spans) {
-    W.push_back((int32_t)sp.start); W.push_back((int32_t)sp.ext); W.push_back((int32_t)sp.base); W.push_back((int32_t)sp.blk);
+    W.push_back((int32_t)sp.start); W.push_back((int32_t)sp.n_ext); W.push_back((int32_t)sp.base); W.push_back(0);
   }
   for (int w = 0; w < n_warps; ++w) {
     W[20 + w] = (int32_t)W.size();
@@ -354,7 +396,7 @@ inline bool build_template(int N, int c, int P, int64_t delta, const std::vector
   out.n_spans = (int)spans.size(); out.Tmax = Tmax; out.rec_entries = (int)rec_entries;
 
   std::vector<int32_t>& R = out.raw;
-  R = {P, (int32_t)delta, ppp, 0};
+  R = {P, (int32_t)delta, ppp, step};
   for (int phi = 0; phi < P; ++phi) {
     const PhaseStencil& s = ph[phi];
     R.push_back((int32_t)s.de.size());

@@ -164,9 +164,10 @@ static bool emulate_tile(const Emu& E, const int32_t* hdr, const std::vector<int
                          std::vector<double>& values) {
   const Mesh& m = E.m;
   const int N = m.N, SD = m.sd, C = E.c;
-  const int32_t v0 = hdr[0], T = hdr[1], toff = hdr[2], pair0 = hdr[4];
+  const int32_t v0 = hdr[0], T = hdr[1], toff = hdr[2], pair0 = hdr[4], pstride = hdr[6];
   const int32_t* s_t = blob.data() + toff;
-  const int P = s_t[0], n_lines = s_t[1], TS = s_t[2], LUp = s_t[3], LU = s_t[4], n_spans = s_t[5];
+  const int step = s_t[9];
+  const int n_lines = s_t[1], TS = s_t[2], LUp = s_t[3], LU = s_t[4], n_spans = s_t[5];
   const int off_lines = s_t[6], off_spans = s_t[7];
   const int UD = (C % 2 == 0) ? 2 : 1;  // doubles per unit
   const int64_t nn = m.n_nodes();
@@ -175,13 +176,13 @@ static bool emulate_tile(const Emu& E, const int32_t* hdr, const std::vector<int
   std::vector<double> rec((size_t)s_t[17] * SD, NAN);  // [entry][SD]
   for (int i = 0; i < kZeroEntries * SD; ++i) rec[i] = 0.0;
   std::vector<double> img((size_t)kLaneSteps * LUp * UD, NAN);
-  // staging
+  // staging: strided spans
   for (int s = 0; s < n_spans; ++s) {
     const int32_t* sp = s_t + off_spans + 4 * s;
-    const int len = P * (T - 1) + sp[1] + 1;
-    for (int i = 0; i < len; ++i) {
-      const int64_t node = (int64_t)v0 + sp[0] + i;
-      const int d = sp[2] + (i % P) * sp[3] + i / P;
+    const int cnt = T + sp[1];
+    for (int i = 0; i < cnt; ++i) {
+      const int64_t node = (int64_t)v0 + sp[0] + (int64_t)step * i;
+      const int d = sp[2] + i;
       if (d >= s_t[13]) { printf("span overflow\n"); return false; }
       if (node >= 0 && node < nn)
         for (int x = 0; x < SD; ++x) s_xyz[(size_t)d * SD + x] = m.xyz[node * SD + x];
@@ -248,11 +249,17 @@ static bool emulate_tile(const Emu& E, const int32_t* hdr, const std::vector<int
   }
   // store: row r of the image -> values[c^2 pair0 + r * row_doubles ...]
   const int kThreads = 32 * s_t[8];
+  const int GR = C * C * pstride / UD;  // units between consecutive image rows in `values`
+  if (GR < LU) { printf("rows overlap in the output\n"); return false; }
   for (int tid = 0; tid < kThreads; ++tid) {  // the kernel's flat copy: thread tid takes units tid, tid + threads, ...
     int r = tid / LU, u = tid % LU;
     for (int x = tid; x < T * LU; x += kThreads) {
       if (r != x / LU || u != x % LU) { printf("store increments wrong\n"); return false; }
-      for (int d = 0; d < UD; ++d) values[(size_t)C * C * pair0 + (size_t)x * UD + d] = img[((size_t)r * LUp + u) * UD + d];
+      for (int d = 0; d < UD; ++d) {
+        double& out = values[(size_t)C * C * pair0 + ((size_t)r * GR + u) * UD + d];
+        if (!std::isnan(out)) { printf("a value is written twice\n"); return false; }
+        out = img[((size_t)r * LUp + u) * UD + d];
+      }
       r += s_t[10]; u += s_t[11];
       if (u >= LU) { u -= LU; ++r; }
     }
@@ -263,20 +270,20 @@ static bool emulate_tile(const Emu& E, const int32_t* hdr, const std::vector<int
 static bool host_verify(const Emu& E, const int32_t* h, const std::vector<int32_t>& rawblob) {
   const Mesh& m = E.m;
   const int N = m.N;
-  const int32_t v0 = h[0], T = h[1], E0 = h[3], pair0 = h[4];
+  const int32_t v0 = h[0], T = h[1], E0 = h[3], pair0 = h[4], pstride = h[6];
   const int32_t* R = rawblob.data() + h[5];
   const int P = R[0];
   const int64_t delta = R[1];
-  const int ppp = R[2];
+  const int step = R[3];
   for (int t = 0; t < T; ++t) {
     const int32_t* p = R + 4;
     for (int phi = 0; phi < P; ++phi) {
       const int ninc = p[0], deg = p[1], prefix = p[2];
       p += 3;
-      const int64_t base = (int64_t)v0 + (int64_t)P * t, v = base + phi;
+      const int64_t base = (int64_t)v0 + (int64_t)step * t, v = base + phi;
       if (v >= m.n_nodes()) return false;
       const int32_t g0 = E.ne_ptr[v];
-      if (E.ne_ptr[v + 1] - g0 != ninc || E.node_ptr[v] != pair0 + t * ppp + prefix || E.node_ptr[v + 1] - E.node_ptr[v] != deg) return false;
+      if (E.ne_ptr[v + 1] - g0 != ninc || E.node_ptr[v] != pair0 + t * pstride + prefix || E.node_ptr[v + 1] - E.node_ptr[v] != deg) return false;
       for (int r = 0; r < ninc; ++r) {
         const int64_t e = (int64_t)E0 + (int64_t)t * delta + p[0];
         if (e < 0 || e >= m.n_el()) return false;
@@ -302,7 +309,27 @@ static double run_case(const char* name, const Mesh& m, int c, double min_cover,
     sig[v] = node_signature((int32_t)v, ninc[v], E.ne_code.data() + E.ne_ptr[v], m.en.data(), N);
     eref[v] = ninc[v] ? (int32_t)(E.ne_code[E.ne_ptr[v]] >> 3) : -1;
   }
-  const std::vector<Run> runs = segment_runs(sig.data(), eref.data(), ninc.data(), nn);
+  std::vector<Run> runs = segment_runs(sig.data(), eref.data(), ninc.data(), nn);
+  size_t n_strided = 0;
+  {
+    std::vector<char> free_node(nn, 1);
+    for (Run& r : runs) {
+      r.pstride = E.node_ptr[r.v0 + r.P] - E.node_ptr[r.v0];
+      for (int64_t v = r.v0; v < (int64_t)r.v0 + (int64_t)r.P * r.periods; ++v) free_node[v] = 0;
+    }
+    for (int pass = 0; pass < 4; ++pass) {   // as plan_runs.cu: strided passes, then single-node tiles for a handful of corners
+      const std::vector<Run> strided = segment_strided(sig.data(), eref.data(), ninc.data(), E.node_ptr.data(), nn, free_node);
+      if (strided.empty()) break;
+      n_strided += strided.size();
+      runs.insert(runs.end(), strided.begin(), strided.end());
+    }
+    std::vector<int64_t> left;
+    for (int64_t v = 0; v < nn && left.size() <= 64; ++v)
+      if (free_node[v]) left.push_back(v);
+    if (left.size() <= 64)
+      for (int64_t v : left)
+        if (ninc[v] > 0) runs.push_back(Run{(int32_t)v, 1, 1, 1, 1, E.node_ptr[v + 1] - E.node_ptr[v]});
+  }
   std::vector<int32_t> blob, rawblob, tiles;
   std::vector<char> covered(nn, 0);
   int n_tmpl = 0, n_fail = 0;
@@ -319,7 +346,7 @@ static double run_case(const char* name, const Mesh& m, int c, double min_cover,
       }
     }
     Template t;  // the emulator builds one template per run (the library shares them by key)
-    if (!build_template(N, c, r.P, r.delta, ph, L, n_warps, t)) { ++n_fail; continue; }
+    if (!build_template(N, c, r.P, r.delta, ph, L, n_warps, t, r.step)) { ++n_fail; continue; }
     ++n_tmpl;
     if (getenv("RUNS_EMU_VERBOSE"))
       printf("  run v0=%d P=%d periods=%d delta=%lld: lines=%d Tmax=%d TS=%d LU=%d LUp=%d coord nodes=%d spans=%d words=%zu\n", r.v0, r.P,
@@ -330,10 +357,14 @@ static double run_case(const char* name, const Mesh& m, int c, double min_cover,
     std::vector<std::pair<int32_t, int32_t>> parts;
     split_run(r, t.Tmax, parts);
     for (auto& pt : parts) {
-      const int32_t v0 = r.v0 + r.P * pt.first;
-      const int32_t hdr[kTileInts] = {v0, pt.second, woff, eref[v0], E.node_ptr[v0], roff, 0, 0};
+      const int32_t v0 = r.v0 + r.step * pt.first;
+      const int32_t hdr[kTileInts] = {v0, pt.second, woff, eref[v0], E.node_ptr[v0], roff, r.pstride, 0};
       tiles.insert(tiles.end(), hdr, hdr + kTileInts);
-      for (int32_t v = v0; v < v0 + r.P * pt.second; ++v) covered[v] = 1;
+      for (int32_t k = 0; k < pt.second; ++k)
+        for (int phi = 0; phi < r.P; ++phi) {
+          if (covered[v0 + r.step * k + phi]) { printf("%s: node covered twice\n", name); return -1; }
+          covered[v0 + r.step * k + phi] = 1;
+        }
     }
   }
   const double lam_over_mu = 1.5;
@@ -364,8 +395,8 @@ static double run_case(const char* name, const Mesh& m, int c, double min_cover,
     }
   }
   const double cover = (double)n_cov / (double)nn;
-  printf("%s: nodes=%lld runs=%zu templates=%d unencodable=%d tiles=%lld covered=%.3f max rel err=%.2e\n", name, (long long)nn,
-         runs.size(), n_tmpl, n_fail, (long long)nt, cover, worst);
+  printf("%s: nodes=%lld runs=%zu (strided %zu) templates=%d unencodable=%d tiles=%lld covered=%.3f max rel err=%.2e\n", name, (long long)nn,
+         runs.size(), n_strided, n_tmpl, n_fail, (long long)nt, cover, worst);
   if (worst > 1e-13) { printf("%s: values differ\n", name); return -1; }
   if (cover < min_cover) { printf("%s: coverage below %.2f\n", name, min_cover); return -1; }
   return cover;
@@ -383,6 +414,10 @@ int main() {
   ok &= run_case("box 6x5x80 elastic, 8 warps", box_mesh(6, 5, 80, 0.1, 7), 3, 0.9, 8) >= 0;
   ok &= run_case("rect 140x12 elastic, 8 warps", rect_mesh(140, 12, 0.15, 3), 2, 0.9, 8) >= 0;
   ok &= run_case("box 6x5x80 elastic, 6 warps", box_mesh(6, 5, 80, 0.1, 7), 3, 0.9, 6) >= 0;
+  // strided runs: the end nodes of the mesh rows / z-lines (node stride = row pitch, twice that with alternating diagonals)
+  ok &= run_case("rect 44x40 elastic (strided row ends)", rect_mesh(44, 40, 0.15, 8), 2, 0.97) >= 0;
+  ok &= run_case("box 4x14x24 elastic (strided line ends)", box_mesh(4, 14, 24, 0.1, 9), 3, 0.97, 6) >= 0;
+  ok &= run_case("box 4x14x24 laplace (strided line ends)", box_mesh(4, 14, 24, 0.1, 9), 1, 0.97) >= 0;
   printf(ok ? "RUNS_EMULATOR PASS\n" : "RUNS_EMULATOR FAIL\n");
   return ok ? 0 : 1;
 }
