@@ -39,7 +39,7 @@ if os.path.exists(rep):
     old = json.load(open(os.path.join(P, 'traffic.json'))) if os.path.exists(os.path.join(P, 'traffic.json')) else {}
     old.update({'k_assemble_runs_c2_bytes_per_launch': traffic,
                 'source_runs': f'ncu --set full, profiles/{R}_assemble_c2.txt (dram__bytes_read.sum + dram__bytes_write.sum of one '
-                               'k_assemble_runs launch; the remainder-tile launch beside it writes 0.1 % of the values)'})
+                               'k_assemble_runs launch = one assembly of config 2)'})
     json.dump(old, open(os.path.join(P, 'traffic.json'), 'w'), indent=1)
 
 src = os.path.join(G, f'{R}_launches_bench_noextra.csv')
