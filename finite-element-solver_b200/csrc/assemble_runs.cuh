@@ -53,24 +53,52 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Gradient loads of phase 2 by 32-bit shared address.  FES_RUN_PLAIN_LDS=1 (A-B build): ordinary C++ loads through a
+// shared-memory pointer instead of volatile asm, so the compiler may hoist the loads of the next partial sum over the
+// FMAs of the current one (it still orders them against the barriers).
+#ifndef FES_RUN_PLAIN_LDS
+#define FES_RUN_PLAIN_LDS 0
+#endif
+#ifndef FES_RUN_PAIR_UNROLL
+#define FES_RUN_PAIR_UNROLL 1  // pairs of phase 2 unrolled together
+#endif
+#ifndef FES_RUN_SHORT_PARTIALS
+#define FES_RUN_SHORT_PARTIALS 1
+#endif
+__device__ __forceinline__ double2 run_lds2(uint32_t addr) {
+#if FES_RUN_PLAIN_LDS
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  return *reinterpret_cast<const double2*>(smem_raw + (addr - smem_u32(smem_raw)));
+#else
+  return lds_f64x2(addr);
+#endif
+}
+__device__ __forceinline__ double run_lds1(uint32_t addr) {
+#if FES_RUN_PLAIN_LDS
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  return *reinterpret_cast<const double*>(smem_raw + (addr - smem_u32(smem_raw)));
+#else
+  return lds_f64(addr);
+#endif
+}
+
 // One partial sum of a pair: exactly L contributions, codes at program words [cw, cw + L); every load is issued
 // before the FMAs.  kDiag: the pair (v, v), both gradients of a contribution are the same vector.
-template <int FORM, int C, int SD, int N, bool kDiag, int NACC>
-__device__ __forceinline__ void run_partial(const int32_t* __restrict__ tmw, int cw, uint32_t lane2, uint32_t lane1,
-                                            double (&acc)[NACC]) {
-  constexpr int L = item_len_of(N);
+template <int FORM, int C, int SD, int L, bool kDiag, int NACC>
+__device__ __forceinline__ void run_partial_m(const int32_t* __restrict__ tmw, int cw, uint32_t lane2, uint32_t lane1,
+                                              double (&acc)[NACC]) {
   double2 ta[L], tb[L];
   [[maybe_unused]] double za[L], zb[L];
 #pragma unroll
   for (int x = 0; x < L; ++x) {
     const uint32_t code = (uint32_t)tmw[cw + x];
     const uint32_t oa = code & 0xffffu;
-    ta[x] = lds_f64x2(lane2 + oa);
-    if constexpr (SD & 1) za[x] = lds_f64(lane1 + (oa >> 1));
+    ta[x] = run_lds2(lane2 + oa);
+    if constexpr (SD & 1) za[x] = run_lds1(lane1 + (oa >> 1));
     if constexpr (!kDiag) {
       const uint32_t ob = code >> 16;
-      tb[x] = lds_f64x2(lane2 + ob);
-      if constexpr (SD & 1) zb[x] = lds_f64(lane1 + (ob >> 1));
+      tb[x] = run_lds2(lane2 + ob);
+      if constexpr (SD & 1) zb[x] = run_lds1(lane1 + (ob >> 1));
     }
   }
 #pragma unroll
@@ -97,6 +125,19 @@ __device__ __forceinline__ void run_partial(const int32_t* __restrict__ tmw, int
         for (int b_ = 0; b_ < C; ++b_) acc[a_ * C + b_] = fma(A_[a_], B_[b_], acc[a_ * C + b_]);
     }
   }
+}
+
+// A partial sum = exactly L codes, short ones padded with code 0 (the zero entries) at the tail.  On tets (L = 6) six
+// of a node's fourteen off-diagonal pairs have 4 contributions: when the fifth code is padding only four are
+// executed (one warp-uniform test per partial sum; fma(0, 0, acc) == acc, so the bits do not change).
+template <int FORM, int C, int SD, int N, bool kDiag, int NACC>
+__device__ __forceinline__ void run_partial(const int32_t* __restrict__ tmw, int cw, uint32_t lane2, uint32_t lane1,
+                                            double (&acc)[NACC]) {
+  constexpr int L = item_len_of(N);
+  if constexpr (L == 6 && FES_RUN_SHORT_PARTIALS) {
+    if (tmw[cw + 4] == 0) { run_partial_m<FORM, C, SD, 4, kDiag>(tmw, cw, lane2, lane1, acc); return; }
+  }
+  run_partial_m<FORM, C, SD, L, kDiag>(tmw, cw, lane2, lane1, acc);
 }
 
 template <int NACC>
@@ -314,14 +355,16 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
       const int pb = toff + tm.w[toff + 20 + warp];
       const int np = tm.w[pb];
       int w = pb + 1;
-#pragma unroll 1
+      constexpr int kPairUnroll = FES_RUN_PAIR_UNROLL;
+#pragma unroll kPairUnroll
       for (int pi = 0; pi < np; ++pi) {
         const uint32_t head = (uint32_t)tm.w[w];
         const uint32_t lg = (head >> 27) & 3u;
+        const bool diag = (head >> 29) & 1u;
         const int cw = w + 1;
         w += 1 + (L << lg);
         double acc[NACC];
-        if ((head >> 29) & 1u) run_pair_sum<FORM, C, SD, N, true>(tm.w, cw, lg, lane2, lane1, acc);
+        if (diag) run_pair_sum<FORM, C, SD, N, true>(tm.w, cw, lg, lane2, lane1, acc);
         else run_pair_sum<FORM, C, SD, N, false>(tm.w, cw, lg, lane2, lane1, acc);
         double K[C][C];
         if constexpr (FORM == FES_FORM_ELASTIC) {
@@ -437,6 +480,7 @@ int launch_runs(const Job& j, cudaStream_t stream) {
     return FES_OK;
   } else {
     if (j.plan->runs.n_warps == 8) return launch_runs_t<ELEM, FORM, C, SD, 256>(j, stream);
+    if (j.plan->runs.n_warps == 7) return launch_runs_t<ELEM, FORM, C, SD, 224>(j, stream);
     if (j.plan->runs.n_warps == 6) return launch_runs_t<ELEM, FORM, C, SD, 192>(j, stream);
     return launch_runs_t<ELEM, FORM, C, SD, 128>(j, stream);
   }

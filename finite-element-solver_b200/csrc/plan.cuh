@@ -65,7 +65,7 @@ struct fes_runs {
   // Every template program of the plan (layout: runs_template.hpp) sits in one slot of the kernel's __constant__
   // memory: the warp-uniform program reads of phase 2 and the line / span descriptors are constant-bank loads and
   // cost no shared-memory or L1 bandwidth.  The slot is owned from plan creation to destruction.
-  static constexpr int kMaxTmplWords = 4608, kSlots = 3;
+  static constexpr int kMaxTmplWords = 5120, kSlots = 3;
   int slot = -1;
   int n_warps = 4;                     // warps per CTA of the run kernel (= pair groups of the templates): 4 or 8
   // The remainder tiles (fes_plan::rest) run concurrently with the run kernel on this side stream, forked from and

@@ -138,7 +138,7 @@ int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32
   // 1.549 with 8; the scalar tet forms 1.158 ms with 4, 1.270 with 6; triangles (14 pairs per period, 8 lines)
   // 0.1345 ms with 4, 0.155 with 8
   int n_warps = (N == 4 && c > 1) ? 6 : 4;
-  if (const char* env = getenv("FES_RUNS_WARPS")) n_warps = atoi(env) == 8 ? 8 : (atoi(env) == 6 ? 6 : 4);  // tuning knob
+  if (const char* env = getenv("FES_RUNS_WARPS")) n_warps = (atoi(env) >= 4 && atoi(env) <= 8 && atoi(env) != 5) ? atoi(env) : 4;  // tuning knob: 4, 6, 7, 8
   int64_t n_cov = 0;
   for (const Run& r : runs) {
     const Key key{r.P, sig[r.v0], r.P > 1 ? sig[r.v0 + 1] : 0ull, r.delta,
@@ -259,8 +259,9 @@ int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32
   if (prev < nn) { rest_ranges.push_back((int32_t)prev); rest_ranges.push_back((int32_t)nn); }
   Rn.active = true;
   if (getenv("FES_PLAN_DEBUG"))
-    fprintf(stderr, "[fes runs] N=%d c=%d runs=%zu templates=%zu tiles=%lld nodes covered=%lld of %lld, rest ranges=%zu\n", N, c,
-            runs.size(), tmpls.size(), (long long)nt, (long long)n_cov, (long long)nn, rest_ranges.size() / 2);
+    fprintf(stderr, "[fes runs] N=%d c=%d runs=%zu templates=%zu (%zu of %d words) tiles=%lld nodes covered=%lld of %lld, rest ranges=%zu\n",
+            N, c, runs.size(), tmpls.size(), blob.size(), fes_runs::kMaxTmplWords, (long long)nt, (long long)n_cov, (long long)nn,
+            rest_ranges.size() / 2);
   return FES_OK;
 }
 
