@@ -448,9 +448,11 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
           if (per_elem) {
             double c2 = w * (ref_measure(RD) / (double)NQ);
             if constexpr (FORM == FES_FORM_ELASTIC) c2 *= m.mu;
-            f = c2 > 0.0 ? c2 * rsqrt(c2) : 0.0;
+            // sqrt(c2) / sqrt(|det|) = c2 rsqrt(c2 |det|): one rsqrt; a void element (weight 0) contributes exact zeros
+            f = c2 > 0.0 ? copysign(c2 * rsqrt(c2 * fabs(det)), det) : 0.0;
+          } else {
+            f = copysign(f * rsqrt(fabs(det)), det);
           }
-          f = copysign(f * rsqrt(fabs(det)), det);
 #pragma unroll
           for (int i = 0; i < RD; ++i)
 #pragma unroll

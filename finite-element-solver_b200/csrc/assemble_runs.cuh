@@ -20,6 +20,7 @@
 
 struct RunDims {
   int rec_entries, coord_nodes, img_units;
+  int lines;  // element lines per tile, upper bound: sizes the per-element coefficient tables (allocated only when used)
 };
 
 // Template slots: a plan with runs owns one from fes_plan_create to fes_plan_destroy; a plan that finds none free
@@ -39,8 +40,10 @@ struct RunSmem {
   __host__ __device__ static size_t v2_bytes(int entries) { return up16((size_t)entries * 16); }
   __host__ __device__ static size_t v1_bytes(int entries) { return (SD & 1) ? up16((size_t)entries * 8) : 0; }
   __host__ __device__ static size_t img_bytes(int units) { return up16((size_t)units * UB + 16); }
-  __host__ __device__ static size_t total(const RunDims& d) {
-    return xyz_bytes(d.coord_nodes) + v2_bytes(d.rec_entries) + v1_bytes(d.rec_entries) + img_bytes(d.img_units);
+  __host__ __device__ static size_t coef_bytes(int lines) { return up16((size_t)lines * 33 * 8); }  // one table per coefficient array
+  __host__ __device__ static size_t total(const RunDims& d, int n_coef) {
+    return xyz_bytes(d.coord_nodes) + v2_bytes(d.rec_entries) + v1_bytes(d.rec_entries) + img_bytes(d.img_units) +
+           (size_t)n_coef * coef_bytes(d.lines);
   }
 };
 
@@ -210,7 +213,11 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
   double* s_xyz = reinterpret_cast<double*>(sp);    sp += RS::xyz_bytes(dims.coord_nodes);
   double2* v2 = reinterpret_cast<double2*>(sp);     sp += RS::v2_bytes(dims.rec_entries);
   double* v1 = reinterpret_cast<double*>(sp);       sp += RS::v1_bytes(dims.rec_entries);
-  unsigned char* s_img = sp;
+  unsigned char* s_img = sp;                        sp += RS::img_bytes(dims.img_units);
+  // per-element coefficients of the tile's element lines, [line][entry], staged with the coordinates (the SIMP
+  // reassembly: rho^p as d_scale; a modulus field as d_E); present only when the launch carries such arrays
+  double* s_scale = reinterpret_cast<double*>(sp);  sp += cf.d_scale ? RS::coef_bytes(dims.lines) : 0;
+  double* s_E = reinterpret_cast<double*>(sp);
   const uint32_t v2_b = smem_u32(v2), v1_b = smem_u32(v1), img_b = smem_u32(s_img);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool per_elem = cf.d_E != nullptr || cf.d_scale != nullptr;
@@ -244,8 +251,28 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
 
   // staging of one tile's coordinate spans (strided node sequences v0 + start + step * i -> slots base + i): warp w
   // takes spans w, w + kWarps, ...
-  auto stage = [&](int32_t v0, int32_t T, int32_t toff) {
+  auto stage = [&](int32_t v0, int32_t T, int32_t toff, int32_t E0) {
     const int step = tm.w[toff + 9], n_spans = tm.w[toff + 5], so = toff + tm.w[toff + 7];
+    if (per_elem) {
+      // Element of entry tau' of line l = E0 + eoff_l + tau' * delta.  Consecutive THREADS take consecutive LINES of
+      // one entry: the lines are sorted by eoff and the elements of a cell column are numbered consecutively, so a
+      // quarter-warp's 8-byte reads fall into one or two sectors (thread = entry would touch 32 sectors per
+      // instruction: measured +45 % on config 2 with a rho^p scale).  Tables are [line][33]: the odd pitch keeps the
+      // scattered 8-byte writes of one entry on distinct banks.
+      const int n_lines = tm.w[toff + 1], lo = toff + tm.w[toff + 6];
+      const int64_t delta = tm.w[toff + 14];
+      const uint32_t inv = ((1u << 20) + (uint32_t)n_lines - 1u) / (uint32_t)n_lines;
+      for (int i = tid; i < n_lines * 32; i += kRunThreads) {
+        const int tp = (int)(((uint32_t)i * inv) >> 20), l = i - tp * n_lines;
+        const int ld = lo + l * (2 + N);
+        if (tp < T + tm.w[ld + 1]) {
+          int64_t e = (int64_t)E0 + tm.w[ld] + (int64_t)tp * delta;
+          e = e < 0 ? 0 : (e >= n_el ? n_el - 1 : e);  // entries no lane references may fall outside the mesh
+          if (cf.d_scale) cp_async8(s_scale + l * 33 + tp, cf.d_scale + e);
+          if (cf.d_E) cp_async8(s_E + l * 33 + tp, cf.d_E + e);
+        }
+      }
+    }
     for (int s = warp; s < n_spans; s += kRunThreads / 32) {
       const int32_t start = tm.w[so + 4 * s], n_ext = tm.w[so + 4 * s + 1], base = tm.w[so + 4 * s + 2];
       const int cnt = T + n_ext;
@@ -261,7 +288,7 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
       }
     }
   };
-  stage(h0.x, h0.y, h0.z);
+  stage(h0.x, h0.y, h0.z, h0.w);
   cp_async_wait_all();
   __syncthreads();
 
@@ -318,16 +345,16 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
           double cof[RD][SD], det;
           make_cof<RD, SD>(X[r], cof, det);
           double f = sq_uniform;
-          if (per_elem) {
-            int64_t e = (int64_t)E0 + tm.w[lo + l * (2 + N)] + (int64_t)lane * delta;
-            e = e < 0 ? 0 : (e >= n_el ? n_el - 1 : e);  // entries no lane references may fall outside the mesh
-            Material m; double w;
-            element_coeffs(cf, e, m, w);
+          if (per_elem) {  // element_coeffs' arithmetic on the staged values
+            const double E = cf.d_E ? s_E[l * 33 + lane] : cf.E;
+            const double w = cf.d_scale ? cf.factor * s_scale[l * 33 + lane] : cf.factor;
             double c2 = w * (ref_measure(RD) / 1.0);
-            if constexpr (FORM == FES_FORM_ELASTIC) c2 *= m.mu;
-            f = c2 > 0.0 ? c2 * rsqrt(c2) : 0.0;
+            if constexpr (FORM == FES_FORM_ELASTIC) c2 *= E * cf.mu1;
+            // sqrt(c2) / sqrt(|det|) = c2 rsqrt(c2 |det|): one rsqrt; a void element (weight 0) contributes exact zeros
+            f = c2 > 0.0 ? copysign(c2 * rsqrt(c2 * fabs(det)), det) : 0.0;
+          } else {
+            f = copysign(f * rsqrt(fabs(det)), det);
           }
-          f = copysign(f * rsqrt(fabs(det)), det);
 #pragma unroll
           for (int i2 = 0; i2 < RD; ++i2)
 #pragma unroll
@@ -346,7 +373,7 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
     bulk_wait_read_all();  // the previous tile's bulk stores (issued by this thread, if any) have finished reading the image
     __syncthreads();  // records visible; the coordinate table is free; the previous image has been copied out
 
-    if (has_next) stage(h1.x, h1.y, h1.z);  // lands under phase 2
+    if (has_next) stage(h1.x, h1.y, h1.z, h1.w);  // lands under phase 2
 
     // ---- phase 2: warp = pair group, lane = lane-step
     if (lane < T) {
@@ -441,8 +468,9 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
 template <int ELEM, int FORM, int C, int SD, int kRunThreads>
 int launch_runs_t(const Job& j, cudaStream_t stream) {
   const fes_runs& R = j.plan->runs;
-  const RunDims dims{R.max_rec_entries, R.max_coord_nodes, R.max_img_units};
-  const size_t smem = RunSmem<C, SD>::total(dims);
+  const RunDims dims{R.max_rec_entries, R.max_coord_nodes, R.max_img_units, R.max_lines};
+  static const int exp_coef = getenv("FES_EXP_COEF_SMEM") ? atoi(getenv("FES_EXP_COEF_SMEM")) : 0;  // occupancy experiment
+  const size_t smem = RunSmem<C, SD>::total(dims, (j.cf.d_scale ? 1 : 0) + (j.cf.d_E ? 1 : 0) + exp_coef);
   static size_t configured = 0, occ_smem = 0;
   static int per_sm = 0, sms = 0;
   if (per_sm == 0 || smem != occ_smem) {

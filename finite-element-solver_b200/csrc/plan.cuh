@@ -60,7 +60,7 @@ struct fes_runs {
   int64_t n_tiles = 0, n_nodes_covered = 0, n_templates = 0;
   // shared-memory sizing of k_assemble_runs: maxima over the templates
   int max_rec_entries = 0;             // 32 zero entries + n_lines * N * TS
-  int max_coord_nodes = 0, max_img_units = 0;
+  int max_coord_nodes = 0, max_img_units = 0, max_lines = 0;
   static constexpr int kTileInts = 8;  // {v0, T, template word offset, E0, first pair, raw word offset, 0, 0}
   // Every template program of the plan (layout: runs_template.hpp) sits in one slot of the kernel's __constant__
   // memory: the warp-uniform program reads of phase 2 and the line / span descriptors are constant-bank loads and

@@ -233,11 +233,12 @@ int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32
   Rn.n_tiles = nt;
   Rn.n_nodes_covered = n_cov;
   Rn.n_templates = (int64_t)tmpls.size();
-  Rn.max_rec_entries = Rn.max_coord_nodes = Rn.max_img_units = 0;
+  Rn.max_rec_entries = Rn.max_coord_nodes = Rn.max_img_units = Rn.max_lines = 0;
   for (const Template& t : tmpls) {
     Rn.max_rec_entries = std::max(Rn.max_rec_entries, t.rec_entries);
     Rn.max_coord_nodes = std::max(Rn.max_coord_nodes, t.coord_nodes);
     Rn.max_img_units = std::max(Rn.max_img_units, t.Tmax * t.LUp);
+    Rn.max_lines = std::max(Rn.max_lines, t.n_lines);
   }
   if (Rn.slot >= 0) { runs_slot_release(Rn.slot); Rn.slot = -1; }
   FES_TRY(runs_slot_acquire(blob.data(), blob.size(), stream, &Rn.slot));
