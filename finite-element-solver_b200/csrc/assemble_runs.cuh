@@ -1,16 +1,18 @@
 // k_assemble_runs: fused assembly of stencil-run tiles (layout and idea: runs_template.hpp; the plan side is
 // plan_runs.cu).  Included by assemble.cu inside namespace fes { namespace {, after Coeffs / element_coeffs.
 //
-// A tile is T <= 32 lane-steps of a run; lane t of every warp owns lane-step t (the P nodes v0 + P t + phi).
+// A tile is T <= 32 lane-steps of a run; lane t of every warp owns lane-step t (the P nodes v0 + step t + phi;
+// step = P for a run of consecutive nodes, the node stride of a strided run).
 // The template programs of a plan live in a slot of __constant__ memory (uploaded when the plan is built): every
 // descriptor and program word is a warp-uniform constant-bank load, not a shared-memory or L1 access.
-//   staging : the coordinate spans of the NEXT tile, global -> shared memory with cp.async (contiguous node
-//             ranges; de-interleaved by period phase), issued after phase 1 so they land under phase 2
-//   phase 1 : thread per (element line, entry): cofactors, one rsqrt, the N gradients scaled by sqrt(w mu vol)
+//   staging : the coordinate spans of the NEXT tile (strided node sequences -> consecutive slots) and, when the launch
+//             carries them, the per-element coefficients of its element lines, global -> shared memory with
+//             cp.async, issued after phase 1 so they land under phase 2
+//   phase 1 : warp per element line, lane = entry: cofactors, one rsqrt, the N gradients scaled by sqrt(w mu vol)
 //             -- the arithmetic of k_assemble_tiles, to the bit -- into planes indexed by the entry
 //   phase 2 : warp w walks its share of the period's pairs; a contribution is two gradient loads at
 //             (code + t): unit stride across the warp, conflict-free, no predicates (short partial sums are
-//             padded with the zero entries).  The partial sums of L contributions are combined in the balanced
+//             padded with the zero entries; on tets a padded tail is skipped by one uniform test).  The partial sums of L contributions are combined in the balanced
 //             tree the tiled kernel's xor shuffles form, so a pair gets the same bits from either kernel.  The
 //             block goes into a padded shared-memory image (odd row stride: the lanes' stores hit distinct banks)
 //   store   : TMA bulk stores (cp.async.bulk.global.shared::cta): one per tile when the image needs no padding,

@@ -10,11 +10,15 @@
 // alternate --, a z-line of create_box_mesh one run of period 1; ref fem/mesh/structured.py:17-96); the
 // detection reads the connectivity only, so a structured mesh with arbitrary coordinates qualifies.
 //
+// What the consecutive runs leave over is searched for STRIDED runs v0 + S t (segment_strided: the end nodes of the
+// mesh rows / z-lines), and a last handful of nodes become single-node tiles, so a structured mesh is covered
+// completely and one kernel launch assembles it.
+//
 // A run is cut into TILES of <= 32 lane-steps.  The kernel evaluates the geometry of every element LINE
 // {E0 + d0 + tau * delta} touching the tile once per tau into shared-memory planes indexed by tau, then
 // lane t of a warp sums the pairs of its P nodes from addresses (code + t): unit stride across the warp,
 // no bank conflicts, and nothing but a 32-byte tile header, the node coordinates and the per-element
-// coefficients is read from HBM.  The four warps of a CTA split the PAIRS of the period between them.
+// coefficients is read from HBM.  The warps of a CTA (4 or 6) split the PAIRS of the period between them.
 //
 // Template blob (int32 words; offsets relative to the template's first word):
 //   [0] P  [1] n_lines  [2] TS (plane stride, entries)  [3] LUp (padded image row stride, units)
