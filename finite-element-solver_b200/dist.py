@@ -41,8 +41,15 @@ class NodePartition:
         touch = ((elements >= self.lo) & (elements < self.hi)).any(axis=1)
         self.local_elements = np.flatnonzero(touch)                # ascending global element ids
         le = elements[touch]
-        self.l2g = np.union1d(le.ravel(), np.arange(self.lo, self.hi, dtype=np.int64))
-        self.elements_local = np.searchsorted(self.l2g, le)
+        # local nodes = the owned block plus every node of a touching element, ascending; a mark array and a
+        # global -> local lookup instead of a sort of all (element, corner) entries (20 M tets: 4.1 -> 1.x s per rank)
+        mark = np.zeros(self.n_nodes_global, dtype=bool)
+        mark[le.ravel()] = True
+        mark[self.lo:self.hi] = True
+        self.l2g = np.flatnonzero(mark)
+        g2l = np.empty(self.n_nodes_global, dtype=np.int64)
+        g2l[self.l2g] = np.arange(len(self.l2g), dtype=np.int64)
+        self.elements_local = g2l[le]
         self.owned_begin = int(np.searchsorted(self.l2g, self.lo))
         self.owned_end = int(np.searchsorted(self.l2g, self.hi))
         ghost = np.ones(len(self.l2g), dtype=bool)
