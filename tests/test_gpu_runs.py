@@ -126,3 +126,63 @@ def test_unstructured_numbering_has_no_runs():
     mesh = F.Mesh(v[perm], inv[e], np.zeros((0, 2), dtype=np.int64))
     V = F.FunctionSpace(mesh, n_components=2)
     assert V.plan().n_run_tiles == 0 and V.plan().n_tiles > 0
+
+
+def test_more_plans_than_template_slots_and_graph_replay():
+    """The template programs of a plan with runs live in one of three __constant__ slots.  A fourth live plan finds
+    none free and keeps the tiled kernel -- same results; a destroyed plan frees its slot.  And a run-path assembly
+    (with an irregular region, i.e. remainder tiles forked onto the plan's side stream) is capturable in a CUDA
+    graph: the replay writes the same bits."""
+    import ctypes as C
+    F = fes()
+    from fes_b200 import _lib
+    spaces, datas = [], []
+    form = F.LinearElasticForm(F.LinearElasticMaterial(70.0, 0.25))
+    for k in range(5):
+        v, e = fo.rect_mesh([[0, 0], [2, 1]], (40 + 3 * k, 21 + k))
+        mesh = F.Mesh(jitter(v, (40 + 3 * k, 21 + k), 10 + k), e, np.zeros((0, 2), dtype=np.int64))
+        V = F.FunctionSpace(mesh, n_components=2)
+        a, b = both_kernels(V, form)
+        np.testing.assert_array_equal(a, b)
+        spaces.append(V)
+    with_runs = [V.plan().n_run_tiles > 0 for V in spaces]
+    assert with_runs[:3] == [True, True, True] and with_runs[3:] == [False, False]
+    del spaces[0]                                    # frees a slot
+    import gc
+    gc.collect()
+    nx, ny = 50, 30
+    v, e = fo.rect_mesh([[0, 0], [2, 1]], (nx, ny))
+    # an irregular patch: the other diagonal in a block of 9 x 9 cells, so > 64 nodes fall out of every run and the
+    # plan keeps remainder tiles (the tiled kernel on the plan's side stream) next to the run tiles
+    e = e.copy()
+    for i in range(20, 29):
+        for j in range(10, 19):
+            a, b, c, d = j * nx + i, j * nx + i + 1, (j + 1) * nx + i + 1, (j + 1) * nx + i
+            k = 2 * (i * (ny - 1) + j)
+            if (i + j) % 2 == 0:
+                e[k], e[k + 1] = [a, b, d], [b, c, d]
+            else:
+                e[k], e[k + 1] = [a, b, c], [a, c, d]
+    V = F.FunctionSpace(F.Mesh(v, e, np.zeros((0, 2), dtype=np.int64)), n_components=2)
+    assert 0 < V.plan().n_run_tiles < V.plan().n_tiles and V.plan().run_nodes < len(v) - 64
+    A = V.assemble_device(form)
+    want = A.data_d.clone()
+    ref = fo.assemble(e, 2, len(v), fo.ke_elastic(fo.geometry(fo.P1_TRI, v[e]), np.full(len(e), 70.0), 0.25))
+    close(want.cpu().numpy(), ref.data)
+    low = form.lower(V, False)
+    cf = low.coeffs()
+    L = _lib.lib()
+    side = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        A.data_d.zero_()
+        side.synchronize()
+        with torch.cuda.graph(g, stream=side):
+            _lib.check(L.fes_assemble(V.plan().handle, V.element_type.KIND, low.form, V.spatial_dim, _lib.ptr(V._en_d),
+                                      _lib.ptr(V._coords_d), C.byref(cf), _lib.ptr(A.data_d), _lib.stream()))
+        A.data_d.zero_()
+        g.replay()
+        side.synchronize()
+    torch.cuda.current_stream().wait_stream(side)
+    assert torch.equal(A.data_d, want)
