@@ -22,7 +22,8 @@ BASE = ['metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', '
         'vs_baseline', 'dtype', 'data', 'config']
 
 
-@pytest.mark.parametrize('name', ['r01_bench_n1.json', 'r01_bench_n2.json', 'r01_bench_n4.json', 'r01_bench_n8.json'])
+@pytest.mark.parametrize('name', ['r01_bench_n1.json', 'r01_bench_n2.json', 'r01_bench_n4.json', 'r01_bench_n8.json',
+                                  'r02_bench_n1.json', 'r02_bench_n2.json', 'r02_bench_n4.json', 'r02_bench_n8.json'])
 def test_own_arm_line(name):
     d = _line(name)
     for k in BASE + ['roofline', 'e2e', 'gpu_launches', 'clocks']:
@@ -48,8 +49,9 @@ def test_own_arm_line(name):
         assert b['kind'] in ('port', 'reference') and b['cores'] >= 1
 
 
-def test_reference_arm_line():
-    d = _line('r01_bench_reference.json')
+@pytest.mark.parametrize('name', ['r01_bench_reference.json', 'r02_bench_reference.json'])
+def test_reference_arm_line(name):
+    d = _line(name)
     for k in BASE + ['impl', 'cpu_baseline', 'e2e']:
         assert k in d, k
     assert d['impl'] == 'reference' and d['unit'] == 'elements/s'
