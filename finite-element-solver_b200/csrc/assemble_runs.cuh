@@ -236,20 +236,20 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
   }
   const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   if (n_my <= 0) return;
-  // tile headers {v0, T, template offset, E0 | first pair ...}, fetched two tiles ahead so neither the staging of the
-  // next tile nor this tile's phases ever wait for one
+  // Tile headers {v0, T, template offset, E0 | first pair, -, pair stride, -} travel global -> shared memory with
+  // cp.async two tiles ahead, into a ring of four 32-byte slots, and are read from shared memory when their tile comes
+  // up: no thread ever waits for a header.  (Loaded into registers -- even through volatile asm -- the compiler moves
+  // them to uniform registers right behind the load: a long-scoreboard stall per tile, 12 % of the samples on
+  // config 2.)  Completion rides on the cp.async wait + barrier the coordinate staging already has.
+  __shared__ __align__(16) int4 s_hdr[4][2];
   const int4* hdr4 = reinterpret_cast<const int4*>(tiles);
-  auto load_hdr = [&](int k, int4& h, int4& g) {  // h = {v0, T, template offset, E0}, g = {first pair, -, pair stride, -}
-    const int64_t t = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
-    // volatile asm: the loads stay where they are written (two tiles ahead) and their results in vector registers
-    // (the compiler otherwise proves them warp-uniform and converts them to uniform registers right behind the
-    // load, a long-scoreboard stall per tile)
-    asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "l"(hdr4 + 2 * t));
-    asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(g.x), "=r"(g.y), "=r"(g.z), "=r"(g.w) : "l"(hdr4 + 2 * t + 1));
+  auto fetch_hdr = [&](int k) {
+    if (tid < 2) cp_async16(&s_hdr[k & 3][tid], hdr4 + 2 * ((int64_t)blockIdx.x + (int64_t)k * gridDim.x) + tid);
   };
-  int4 h0, h1 = make_int4(0, 0, 0, 0), g0, g1 = make_int4(0, 0, 0, 0);
-  load_hdr(0, h0, g0);
-  if (n_my > 1) load_hdr(1, h1, g1);
+  fetch_hdr(0);
+  if (n_my > 1) fetch_hdr(1);
+  cp_async_wait_all();
+  __syncthreads();
 
   // staging of one tile's coordinate spans (strided node sequences v0 + start + step * i -> slots base + i): warp w
   // takes spans w, w + kWarps, ...
@@ -290,16 +290,19 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
       }
     }
   };
-  stage(h0.x, h0.y, h0.z, h0.w);
+  {
+    const int4 h0 = s_hdr[0][0];
+    stage(h0.x, h0.y, h0.z, h0.w);
+  }
   cp_async_wait_all();
   __syncthreads();
 
   for (int k = 0; k < n_my; ++k) {
+    const int4 h0 = s_hdr[k & 3][0], g0 = s_hdr[k & 3][1];
     const int32_t T = h0.y, toff = h0.z, E0 = h0.w;
     const int32_t my_pair0 = g0.x, pstride = g0.z;
     const bool has_next = k + 1 < n_my;
-    int4 h2 = make_int4(0, 0, 0, 0), g2 = make_int4(0, 0, 0, 0);
-    if (k + 2 < n_my) load_hdr(k + 2, h2, g2);
+    if (k + 2 < n_my) fetch_hdr(k + 2);  // its slot held tile k - 2, last read two barriers ago
     const int n_lines = tm.w[toff + 1], LUp = tm.w[toff + 3], LU = tm.w[toff + 4];
     // 8-byte units and an odd row length: the image needs no padding (LUp == LU), i.e. it IS the tile's contiguous
     // slice of `values` and one TMA bulk store writes it.  An odd first value index is mirrored by an 8-byte skew of
@@ -375,7 +378,10 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
     bulk_wait_read_all();  // the previous tile's bulk stores (issued by this thread, if any) have finished reading the image
     __syncthreads();  // records visible; the coordinate table is free; the previous image has been copied out
 
-    if (has_next) stage(h1.x, h1.y, h1.z, h1.w);  // lands under phase 2
+    if (has_next) {  // lands under phase 2
+      const int4 h1 = s_hdr[(k + 1) & 3][0];
+      stage(h1.x, h1.y, h1.z, h1.w);
+    }
 
     // ---- phase 2: warp = pair group, lane = lane-step
     if (lane < T) {
@@ -461,8 +467,6 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
         if (u >= LU) { u -= LU; ++r; }
       }
     }
-    h0 = h1; g0 = g1;
-    h1 = h2; g1 = g2;
   }
   bulk_wait_read_all();  // shared memory must outlive the last bulk stores' reads
 }
