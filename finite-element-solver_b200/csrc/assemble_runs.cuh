@@ -299,7 +299,7 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
 
   for (int k = 0; k < n_my; ++k) {
     const int4 h0 = s_hdr[k & 3][0], g0 = s_hdr[k & 3][1];
-    const int32_t T = h0.y, toff = h0.z, E0 = h0.w;
+    const int32_t T = h0.y, toff = h0.z;  // (E0 = h0.w is consumed by the staging of the tile, one iteration earlier)
     const int32_t my_pair0 = g0.x, pstride = g0.z;
     const bool has_next = k + 1 < n_my;
     if (k + 2 < n_my) fetch_hdr(k + 2);  // its slot held tile k - 2, last read two barriers ago
@@ -318,7 +318,6 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
     // reads and record writes unit-stride, and the long fp64 rsqrt chains of the kB records overlap
     {
       const int lo = toff + tm.w[toff + 6];
-      const int32_t delta = tm.w[toff + 14];
       constexpr int kB = (SD == 3) ? FES_RUN_KB3D : FES_RUN_KB2D;
       constexpr int kWarps = kRunThreads / 32;
       for (int l0 = warp; l0 < n_lines; l0 += kB * kWarps) {
