@@ -444,15 +444,16 @@ k_assemble_tiles(const int32_t* __restrict__ tile_hdr, int n_tiles, const uint32
           // accumulates plain outer products.
           double cof[RD][SD], det;
           make_cof<RD, SD>(X[r], cof, det);
-          double f = sq_uniform;
+          double f = sq_uniform, d = fabs(det);
           if (per_elem) {
             double c2 = w * (ref_measure(RD) / (double)NQ);
             if constexpr (FORM == FES_FORM_ELASTIC) c2 *= m.mu;
-            // sqrt(c2) / sqrt(|det|) = c2 rsqrt(c2 |det|): one rsqrt; a void element (weight 0) contributes exact zeros
-            f = c2 > 0.0 ? copysign(c2 * rsqrt(c2 * fabs(det)), det) : 0.0;
-          } else {
-            f = copysign(f * rsqrt(fabs(det)), det);
+            // sqrt(c2) / sqrt(|det|) = c2 rsqrt(c2 |det|): one rsqrt per record either way (f * rsqrt(d) below); a void
+            // element (weight 0) contributes exact zeros
+            f = c2 > 0.0 ? c2 : 0.0;
+            d = c2 > 0.0 ? c2 * d : 1.0;
           }
+          f = copysign(f * rsqrt(d), det);
 #pragma unroll
           for (int i = 0; i < RD; ++i)
 #pragma unroll

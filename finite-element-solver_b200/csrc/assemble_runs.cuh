@@ -348,17 +348,18 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
           const int l = l0 + r * kWarps;
           double cof[RD][SD], det;
           make_cof<RD, SD>(X[r], cof, det);
-          double f = sq_uniform;
+          double f = sq_uniform, d = fabs(det);
           if (per_elem) {  // element_coeffs' arithmetic on the staged values
             const double E = cf.d_E ? s_E[l * 33 + lane] : cf.E;
             const double w = cf.d_scale ? cf.factor * s_scale[l * 33 + lane] : cf.factor;
             double c2 = w * (ref_measure(RD) / 1.0);
             if constexpr (FORM == FES_FORM_ELASTIC) c2 *= E * cf.mu1;
-            // sqrt(c2) / sqrt(|det|) = c2 rsqrt(c2 |det|): one rsqrt; a void element (weight 0) contributes exact zeros
-            f = c2 > 0.0 ? copysign(c2 * rsqrt(c2 * fabs(det)), det) : 0.0;
-          } else {
-            f = copysign(f * rsqrt(fabs(det)), det);
+            // sqrt(c2) / sqrt(|det|) = c2 rsqrt(c2 |det|): one rsqrt per record either way (f * rsqrt(d) below); a void
+            // element (weight 0) contributes exact zeros
+            f = c2 > 0.0 ? c2 : 0.0;
+            d = c2 > 0.0 ? c2 * d : 1.0;
           }
+          f = copysign(f * rsqrt(d), det);
 #pragma unroll
           for (int i2 = 0; i2 < RD; ++i2)
 #pragma unroll
