@@ -303,13 +303,15 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
     const int32_t my_pair0 = g0.x, pstride = g0.z;
     const bool has_next = k + 1 < n_my;
     if (k + 2 < n_my) fetch_hdr(k + 2);  // its slot held tile k - 2, last read two barriers ago
-    const int n_lines = tm.w[toff + 1], LUp = tm.w[toff + 3], LU = tm.w[toff + 4];
-    // 8-byte units and an odd row length: the image needs no padding (LUp == LU), i.e. it IS the tile's contiguous
+    const int n_lines = tm.w[toff + 1], psh = tm.w[toff + 3], LU = tm.w[toff + 4];
+    // image row r starts at unit r LU + r / g, g = 2^(psh - 1) rows per pad unit (psh = 0: no padding)
+    auto row_off = [&](int r) { return (uint32_t)(r * LU + (psh ? (r >> (psh - 1)) : 0)); };
+    // 8-byte units and an odd row length: the image needs no padding (psh == 0), i.e. it IS the tile's contiguous
     // slice of `values` and one TMA bulk store writes it.  An odd first value index is mirrored by an 8-byte skew of
     // the image, so both sides of the copy share their 16-byte phase.
     // A strided run's rows are pstride pairs apart in `values` (contiguous runs: pstride = the pairs per lane-step)
     const int GR = C * C * pstride / (UB / 8);  // units between consecutive image rows in `values`
-    const bool bulk = UB == 8 && LUp == LU && GR == LU && use_bulk;
+    const bool bulk = UB == 8 && psh == 0 && GR == LU && use_bulk;
     const bool row_bulk = UB == 16 && (use_bulk & 2);
     const uint32_t skew = bulk ? (uint32_t)(((int64_t)C * C * my_pair0) & 1) : 0u;
 
@@ -386,7 +388,7 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
     // ---- phase 2: warp = pair group, lane = lane-step
     if (lane < T) {
       const uint32_t lane2 = v2_b + 16u * (uint32_t)lane, lane1 = v1_b + 8u * (uint32_t)lane;
-      const uint32_t img_lane = img_b + 8u * skew + (uint32_t)lane * (uint32_t)LUp * (uint32_t)UB;
+      const uint32_t img_lane = img_b + 8u * skew + row_off(lane) * (uint32_t)UB;
       const int pb = toff + tm.w[toff + 20 + warp];
       const int np = tm.w[pb];
       int w = pb + 1;
@@ -441,21 +443,26 @@ k_assemble_runs(const int32_t* __restrict__ tiles, int n_tiles, int slot, const 
         if (head) values[val0] = img[0];
         if (tail) values[val0 + n_out - 1] = img[n_out - 1];
       }
-    } else if (row_bulk) {  // padded rows, 16-byte units: one bulk store per image row; every warp issues its share
-      // (UBLKCP takes uniform operands, so a warp's lanes are served one after the other: spread over the warps,
-      // none of them arrives late at the next tile's phase 1)
+    } else if (row_bulk) {
+      // padded rows, 16-byte units: one bulk store per group of g adjacent rows (the rows between two pad units are
+      // contiguous on both sides; g = 1 for a strided run, whose rows are GR units apart in `values`).  Every warp
+      // issues its share (UBLKCP takes uniform operands, so a warp's lanes are served one after the other: spread
+      // over the warps, none of them arrives late at the next tile's phase 1)
       constexpr int kWarps = kRunThreads / 32;
-      const int rpw = (T + kWarps - 1) / kWarps, r = warp * rpw + lane;
-      if (lane < rpw && r < T)
-        bulk_s2g(reinterpret_cast<unsigned char*>(values + (int64_t)C * C * my_pair0) + (size_t)r * GR * UB,
-                 s_img + (size_t)r * LUp * UB, (uint32_t)(LU * UB));
+      const int gsh = psh ? psh - 1 : 0, g = 1 << gsh;
+      const int n_groups = (T + g - 1) >> gsh, gpw = (n_groups + kWarps - 1) / kWarps, j = warp * gpw + lane;
+      if (lane < gpw && j < n_groups) {
+        const int r0 = j << gsh, rows = min(g, T - r0);
+        bulk_s2g(reinterpret_cast<unsigned char*>(values + (int64_t)C * C * my_pair0) + (size_t)r0 * GR * UB,
+                 s_img + (size_t)row_off(r0) * UB, (uint32_t)(rows * LU * UB));
+      }
     } else {  // padded rows: thread x takes units x, x + threads, ...
       unsigned char* dst = reinterpret_cast<unsigned char*>(values + (int64_t)C * C * my_pair0);
       const int total = T * LU, dr = tm.w[toff + 10], du = tm.w[toff + 11];
       int r = tid / LU, u = tid - r * LU;
 #pragma unroll 2
       for (int x = tid; x < total; x += kRunThreads) {
-        const uint32_t src = img_b + (uint32_t)(r * LUp + u) * (uint32_t)UB;
+        const uint32_t src = img_b + (row_off(r) + (uint32_t)u) * (uint32_t)UB;
         const size_t o = (size_t)(uint32_t)(r * GR + u) * UB;
         if constexpr (UB == 16) {
           const double2 v = lds_f64x2(src);

@@ -237,7 +237,7 @@ int build_runs(fes_plan* P, const int32_t* d_elem_nodes, const std::vector<int32
   for (const Template& t : tmpls) {
     Rn.max_rec_entries = std::max(Rn.max_rec_entries, t.rec_entries);
     Rn.max_coord_nodes = std::max(Rn.max_coord_nodes, t.coord_nodes);
-    Rn.max_img_units = std::max(Rn.max_img_units, t.Tmax * t.LUp);
+    Rn.max_img_units = std::max(Rn.max_img_units, t.img_units);
     Rn.max_lines = std::max(Rn.max_lines, t.n_lines);
   }
   if (Rn.slot >= 0) { runs_slot_release(Rn.slot); Rn.slot = -1; }

@@ -21,7 +21,7 @@
 // coefficients is read from HBM.  The warps of a CTA (4 or 6) split the PAIRS of the period between them.
 //
 // Template blob (int32 words; offsets relative to the template's first word):
-//   [0] P  [1] n_lines  [2] TS (plane stride, entries)  [3] LUp (padded image row stride, units)
+//   [0] P  [1] n_lines  [2] TS (plane stride, entries)  [3] image padding: 0 = none, else 1 + log2(rows per pad unit)
 //   [4] LU (image row, units)  [5] n_spans  [6] off_lines  [7] off_spans  [8] n_warps (CTA = 32 n_warps threads)
 //   [9] step (node stride per lane-step: P for consecutive nodes, S for a strided run)
 //   [10] threads / LU  [11] threads mod LU (the store loop's row / unit increments per step of the CTA)
@@ -37,7 +37,8 @@
 //           code = 16 entry_a | 16 entry_b << 16 (byte offsets in the double2 planes; the z plane sits at half),
 //                  entry = 32 + (line * N + local) * TS + (shift - taumin_line); lane t adds t;
 //           partial sum j of a pair = its L codes [j L, j L + L), short ones padded with code 0 (the zero entries)
-// An image UNIT is 16 bytes when c is even, 8 bytes otherwise; LUp = LU | 1 keeps the lanes' stores on distinct banks.
+// An image UNIT is 16 bytes when c is even, 8 bytes otherwise; row r of the image starts at unit r LU + r / g (g rows
+// per pad unit), which keeps the lanes' stores on distinct banks.
 #pragma once
 #include <stdint.h>
 
@@ -163,7 +164,7 @@ struct PhaseStencil {
 struct Template {
   int P = 0, N = 0, c = 0;
   int64_t delta = 0;
-  int n_lines = 0, TS = 0, LU = 0, LUp = 0, coord_nodes = 0, ppp = 0, n_spans = 0, Tmax = 0, rec_entries = 0;
+  int n_lines = 0, TS = 0, LU = 0, pad_rows = 0, img_units = 0, coord_nodes = 0, ppp = 0, n_spans = 0, Tmax = 0, rec_entries = 0;
   std::vector<int32_t> words;  // the kernel's program (layout above)
   std::vector<int32_t> raw;    // the stencil itself, for the verification kernel:
                                //   {P, delta, ppp, 0, then per phase: ninc, deg, prefix, ninc x (de, a, corner[N])}
@@ -338,7 +339,33 @@ inline bool build_template(int N, int c, int P, int64_t delta, const std::vector
   const int row_doubles = c * c * ppp;
   if (row_doubles > 4095 || 8 * c * 127 > 4095) return false;
   const int unit_doubles = (c % 2 == 0) ? 2 : 1;
-  const int LU = row_doubles / unit_doubles, LUp = LU | 1;
+  const int LU = row_doubles / unit_doubles;
+  // Image rows are LU units long; one pad unit is inserted every g rows (row r starts at unit r LU + r / g) so that
+  // the lanes' stores of one instruction fall on distinct banks: 16-byte units are served a quarter-warp at a time
+  // over 8 bank groups, 8-byte units a half-warp over 16.  The largest g that keeps every such lane group
+  // conflict-free is taken (config 2: LU = 28, g = 2 -- two rows leave in one bulk store); an odd row of 8-byte
+  // units needs no padding at all (g = 0: the image is the tile's contiguous slice of the values).
+  int pad_rows = 1;
+  {
+    const int lanes = (c % 2 == 0) ? 8 : 16;
+    auto conflict_free = [&](int g) {
+      for (int t0 = 0; t0 < kLaneSteps; t0 += lanes) {
+        unsigned seen = 0;
+        for (int t = t0; t < t0 + lanes; ++t) {
+          const unsigned bit = 1u << (((int64_t)t * LU + (g ? t / g : 0)) % lanes);
+          if (seen & bit) return false;
+          seen |= bit;
+        }
+      }
+      return true;
+    };
+    if (conflict_free(0)) pad_rows = 0;
+    else if (step == P)  // rows of a strided run are not adjacent in the values: they leave one by one
+      for (int g = 8; g >= 2; g >>= 1)
+        if (conflict_free(g)) { pad_rows = g; break; }
+    if (pad_rows == 1 && !conflict_free(1)) return false;
+  }
+  const int img_units = Tmax * LU + (pad_rows ? (Tmax + pad_rows - 1) / pad_rows : 0);
 
   // longest-processing-time split of the pairs over the warps (cost: gradient loads + a constant per pair)
   auto pair_cost = [&](const Pair& p) { return (double)p.codes.size() * (p.diag ? 0.6 : 1.0) + 1.5; };
@@ -358,7 +385,9 @@ inline bool build_template(int N, int c, int P, int64_t delta, const std::vector
   // emit
   std::vector<int32_t>& W = out.words;
   W.assign(kHdrWords, 0);
-  W[0] = P; W[1] = n_lines; W[2] = TS; W[3] = LUp; W[4] = LU; W[5] = (int32_t)spans.size();
+  int pad_shift1 = 0;  // 0: no padding; else 1 + log2(rows per pad unit)
+  for (int g = pad_rows; g >= 1; g >>= 1) ++pad_shift1;
+  W[0] = P; W[1] = n_lines; W[2] = TS; W[3] = pad_shift1; W[4] = LU; W[5] = (int32_t)spans.size();
   W[13] = (int32_t)coord_slots; W[14] = (int32_t)delta; W[15] = Tmax; W[16] = row_doubles; W[17] = (int32_t)rec_entries;
   W[8] = n_warps; W[9] = step; W[10] = kThreads / LU; W[11] = kThreads % LU;
   W[6] = (int32_t)W.size();
@@ -396,7 +425,7 @@ inline bool build_template(int N, int c, int P, int64_t delta, const std::vector
   }
   while (W.size() % 4) W.push_back(0);  // 16-byte granularity
   W[12] = (int32_t)W.size();
-  out.n_lines = n_lines; out.TS = TS; out.LU = LU; out.LUp = LUp; out.coord_nodes = (int)coord_slots; out.ppp = ppp;
+  out.n_lines = n_lines; out.TS = TS; out.LU = LU; out.pad_rows = pad_rows; out.img_units = img_units; out.coord_nodes = (int)coord_slots; out.ppp = ppp;
   out.n_spans = (int)spans.size(); out.Tmax = Tmax; out.rec_entries = (int)rec_entries;
 
   std::vector<int32_t>& R = out.raw;

@@ -167,7 +167,8 @@ static bool emulate_tile(const Emu& E, const int32_t* hdr, const std::vector<int
   const int32_t v0 = hdr[0], T = hdr[1], toff = hdr[2], pair0 = hdr[4], pstride = hdr[6];
   const int32_t* s_t = blob.data() + toff;
   const int step = s_t[9];
-  const int n_lines = s_t[1], TS = s_t[2], LUp = s_t[3], LU = s_t[4], n_spans = s_t[5];
+  const int n_lines = s_t[1], TS = s_t[2], psh = s_t[3], LU = s_t[4], n_spans = s_t[5];
+  auto row_off = [&](int r) { return (size_t)r * LU + (psh ? (r >> (psh - 1)) : 0); };  // units
   const int off_lines = s_t[6], off_spans = s_t[7];
   const int UD = (C % 2 == 0) ? 2 : 1;  // doubles per unit
   const int64_t nn = m.n_nodes();
@@ -175,7 +176,7 @@ static bool emulate_tile(const Emu& E, const int32_t* hdr, const std::vector<int
   std::vector<double> s_xyz((size_t)s_t[13] * SD, NAN);
   std::vector<double> rec((size_t)s_t[17] * SD, NAN);  // [entry][SD]
   for (int i = 0; i < kZeroEntries * SD; ++i) rec[i] = 0.0;
-  std::vector<double> img((size_t)kLaneSteps * LUp * UD, NAN);
+  std::vector<double> img((row_off(kLaneSteps) + 1) * UD, NAN);
   // staging: strided spans
   for (int s = 0; s < n_spans; ++s) {
     const int32_t* sp = s_t + off_spans + 4 * s;
@@ -233,7 +234,7 @@ static bool emulate_tile(const Emu& E, const int32_t* hdr, const std::vector<int
             for (int j = 0; j < SD; ++j) S[i][j] += A[i] * B[j];   // a NaN here = an entry nobody computed
         }
         w += 1 + (L << lg);
-        double* rowp = &img[(size_t)lane * LUp * UD];
+        double* rowp = &img[row_off(lane) * UD];
         if (C == 1) {
           double t = 0;
           for (int s = 0; s < SD; ++s) t += S[s][s];
@@ -244,6 +245,17 @@ static bool emulate_tile(const Emu& E, const int32_t* hdr, const std::vector<int
           for (int i = 0; i < C; ++i)
             for (int j = 0; j < C; ++j) rowp[im + (uint32_t)i * row + j] = lam_over_mu * S[i][j] + S[j][i] + (i == j ? tr : 0.0);
         }
+      }
+    }
+  }
+  {  // the stores of one instruction: distinct banks within a quarter-warp (16-byte units) / half-warp (8-byte)
+    const int lanes = (UD == 2) ? 8 : 16;
+    for (int t0 = 0; t0 < kLaneSteps; t0 += lanes) {
+      unsigned seen = 0;
+      for (int t = t0; t < t0 + lanes; ++t) {
+        const unsigned bit = 1u << (row_off(t) % lanes);
+        if (seen & bit) { printf("image rows collide on a bank\n"); return false; }
+        seen |= bit;
       }
     }
   }
@@ -258,7 +270,7 @@ static bool emulate_tile(const Emu& E, const int32_t* hdr, const std::vector<int
       for (int d = 0; d < UD; ++d) {
         double& out = values[(size_t)C * C * pair0 + ((size_t)r * GR + u) * UD + d];
         if (!std::isnan(out)) { printf("a value is written twice\n"); return false; }
-        out = img[((size_t)r * LUp + u) * UD + d];
+        out = img[(row_off(r) + u) * UD + d];
       }
       r += s_t[10]; u += s_t[11];
       if (u >= LU) { u -= LU; ++r; }
@@ -349,8 +361,8 @@ static double run_case(const char* name, const Mesh& m, int c, double min_cover,
     if (!build_template(N, c, r.P, r.delta, ph, L, n_warps, t, r.step)) { ++n_fail; continue; }
     ++n_tmpl;
     if (getenv("RUNS_EMU_VERBOSE"))
-      printf("  run v0=%d P=%d periods=%d delta=%lld: lines=%d Tmax=%d TS=%d LU=%d LUp=%d coord nodes=%d spans=%d words=%zu\n", r.v0, r.P,
-             r.periods, (long long)r.delta, t.n_lines, t.Tmax, t.TS, t.LU, t.LUp, t.coord_nodes, t.n_spans, t.words.size());
+      printf("  run v0=%d P=%d periods=%d delta=%lld: lines=%d Tmax=%d TS=%d LU=%d pad_rows=%d coord nodes=%d spans=%d words=%zu\n", r.v0, r.P,
+             r.periods, (long long)r.delta, t.n_lines, t.Tmax, t.TS, t.LU, t.pad_rows, t.coord_nodes, t.n_spans, t.words.size());
     const int32_t woff = (int32_t)blob.size(), roff = (int32_t)rawblob.size();
     blob.insert(blob.end(), t.words.begin(), t.words.end());
     rawblob.insert(rawblob.end(), t.raw.begin(), t.raw.end());
