@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <random>
 #include <vector>
 
@@ -430,6 +431,34 @@ int main() {
   ok &= run_case("rect 44x40 elastic (strided row ends)", rect_mesh(44, 40, 0.15, 8), 2, 0.97) >= 0;
   ok &= run_case("box 4x14x24 elastic (strided line ends)", box_mesh(4, 14, 24, 0.1, 9), 3, 0.97, 6) >= 0;
   ok &= run_case("box 4x14x24 laplace (strided line ends)", box_mesh(4, 14, 24, 0.1, 9), 1, 0.97) >= 0;
+  {  // an irregular patch inside a structured mesh: the other diagonal in a block of cells.  The nodes around it fall
+     // out of the runs (their rows are cut into shorter runs or left to the tiled kernel); everything still covered
+     // by a tile must be exact.
+    Mesh m = rect_mesh(60, 34, 0.1, 11);
+    const int nx = 60, ny = 34;
+    for (int i = 20; i < 29; ++i)
+      for (int j = 10; j < 19; ++j) {
+        const int32_t a = j * nx + i, b = a + 1, c = (j + 1) * nx + i + 1, d = (j + 1) * nx + i;
+        const int64_t k = 2 * ((int64_t)i * (ny - 1) + j);
+        const int32_t t0[3] = {a, b, d}, t1[3] = {b, c, d}, u0[3] = {a, b, c}, u1[3] = {a, c, d};
+        const bool even = (i + j) % 2 == 0;
+        for (int x = 0; x < 3; ++x) { m.en[3 * k + x] = even ? t0[x] : u0[x]; m.en[3 * (k + 1) + x] = even ? t1[x] : u1[x]; }
+      }
+    const double cover = run_case("rect 60x34 elastic with an irregular patch", m, 2, 0.5);
+    ok &= cover >= 0 && cover < 0.99;
+  }
+  {  // a random node numbering: no run at all, nothing written
+    Mesh m = rect_mesh(30, 30, 0.1, 12);
+    std::vector<int32_t> perm(m.n_nodes());
+    for (size_t i = 0; i < perm.size(); ++i) perm[i] = (int32_t)i;
+    std::mt19937 rng(5);
+    std::shuffle(perm.begin(), perm.end(), rng);
+    std::vector<double> xyz(m.xyz.size());
+    for (size_t v = 0; v < perm.size(); ++v) { xyz[2 * perm[v]] = m.xyz[2 * v]; xyz[2 * perm[v] + 1] = m.xyz[2 * v + 1]; }
+    m.xyz = xyz;
+    for (auto& n : m.en) n = perm[n];
+    ok &= run_case("rect 30x30 elastic, random node numbering", m, 2, 0.0) == 0.0;
+  }
   printf(ok ? "RUNS_EMULATOR PASS\n" : "RUNS_EMULATOR FAIL\n");
   return ok ? 0 : 1;
 }
