@@ -575,7 +575,7 @@ def run_gpu(args):
     if rank == 0 and world == 1:
         out['cpu_baseline'] = cpu_baseline_sample()
         if not args.no_extra:
-            extra.update(extra_metrics(F, V, mesh, dev, args.cpu_budget))
+            extra.update(extra_metrics(F, V, mesh, dev, args.cpu_budget, args.cpu_simp_iters))
     if not args.no_extra:
         del values
         torch.cuda.empty_cache()
@@ -772,7 +772,7 @@ def graph_replay_case(F, V, form, launches=200, replays=5):
             'note': 'the working set (4.8 MB) stays in L2 between replays: a launch-/latency-bound figure, not an HBM one'}
 
 
-def extra_metrics(F, V, mesh, dev, cpu_budget_s=240.0):
+def extra_metrics(F, V, mesh, dev, cpu_budget_s=240.0, cpu_simp_iters=1):
     """Secondary numbers of BASELINE.json: configs 1 and 3 (assembly only), the PCG solve of
     config 2 and SIMP iterations/sec on config 4 (1201x401 nodes, 960 000 triangles, MBB beam, all 100
     design iterations), each with the CPU arm timed beside it in this run (SURVEY 8d i-v; bounded samples,
@@ -863,7 +863,7 @@ def extra_metrics(F, V, mesh, dev, cpu_budget_s=240.0):
                            'warm_start': True}
     del topo
     torch.cuda.empty_cache()
-    out['simp_config4']['cpu'] = cpu(cpu_simp_iterations, 2, max(60.0, cpu_budget_s - t_cpu[0]))
+    out['simp_config4']['cpu'] = cpu(cpu_simp_iterations, cpu_simp_iters, max(60.0, cpu_budget_s - t_cpu[0]))
     out['cpu_seconds_spent_on_baselines'] = t_cpu[0]
     return out
 
@@ -876,6 +876,8 @@ if __name__ == '__main__':
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-extra', action='store_true')
     ap.add_argument('--tet-n', type=int, default=151, help='nodes per side of the config-5 tet box')
+    ap.add_argument('--cpu-simp-iters', type=int, default=1,
+                    help='design iterations of the reference TopologyOptimizer timed in extra (about 50 s each on config 4)')
     ap.add_argument('--cpu-budget', type=float, default=240.0, help='seconds of host time for the CPU arms in extra')
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != 'reference' else a.warmup
